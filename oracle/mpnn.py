@@ -1,0 +1,91 @@
+"""Oracle: MPNN Q-network forward, fp32, CPU torch, arithmetic as the reference writes it.
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Restates reference src/networks/mpnn.py:
+
+  MPNN.forward                      mpnn.py:40-77    -> mpnn_forward
+  MPNN.get_normalisation            mpnn.py:34-38    -> degree_norm
+  EdgeAndNodeEmbeddingLayer.forward mpnn.py:89-104   -> edge_embedding   (dense [B,N,N,8] -> [B,N,N,63], as written)
+  UpdateNodeEmbeddingLayer.forward  mpnn.py:114-120  -> update_layer
+  ReadoutLayer.forward              mpnn.py:143-159  -> readout
+
+The reference's arithmetic library for this path is PyTorch ATen (pinned torch 1.12.1; 2.11 in this image), so
+the restatement calls the same ATen ops in the same order on the same dtypes rather than re-deriving them.
+Weights are passed as a dict keyed like the reference's state_dict, so the shipped
+`.pth` checkpoints and the `w::*` arrays in tests/golden/*.npz load unchanged.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+KEYS = (
+    "node_init_embedding_layer.0.weight",                 # (64, 7)
+    "edge_embedding_layer.edge_embedding_NN.weight",      # (63, 8)   col 0 multiplies a_ij
+    "edge_embedding_layer.edge_feature_NN.weight",        # (64, 64)
+    "update_node_embedding_layer.0.message_layer.weight",  # (64, 128)
+    "update_node_embedding_layer.0.update_layer.weight",   # (64, 128)
+    "update_node_embedding_layer.1.message_layer.weight",
+    "update_node_embedding_layer.1.update_layer.weight",
+    "update_node_embedding_layer.2.message_layer.weight",
+    "update_node_embedding_layer.2.update_layer.weight",
+    "readout_layer.layer_pooled.weight",                  # (64, 64)
+    "readout_layer.layers_readout.0.weight",              # (1, 128)
+    "readout_layer.layers_readout.0.bias",                # (1,)
+)
+
+
+def as_torch_weights(w):
+    return {k: torch.as_tensor(np.asarray(w[k]), dtype=torch.float32) for k in KEYS}
+
+
+def weights_from_npz(z):
+    """Pull the `w::<state_dict key>` arrays out of a golden .npz."""
+    return {k: np.asarray(z["w::" + k], dtype=np.float32) for k in KEYS}
+
+
+def degree_norm(adj):
+    norm = torch.sum((adj != 0), dim=1).unsqueeze(-1)      # mpnn.py:36 (adj symmetric: dim 1 == dim 2 count)
+    norm[norm == 0] = 1
+    return norm.float()
+
+
+def edge_embedding(w, x, adj, norm):
+    B, N, _ = adj.shape
+    nbr = x.unsqueeze(1).expand(B, N, N, x.shape[-1])      # feature of j at [b, i, j]   (mpnn.py:90-92)
+    ef = torch.cat([adj.unsqueeze(-1), nbr], dim=-1)
+    ef = ef * (adj.unsqueeze(-1) != 0).float()             # mpnn.py:94
+    emb = F.relu(F.linear(ef.reshape(B, N * N, -1), w[KEYS[1]]))    # mpnn.py:96-97
+    emb = emb.reshape(B, N, N, -1).sum(dim=2) / norm       # mpnn.py:98-100
+    return F.relu(F.linear(torch.cat([emb, norm / norm.max()], dim=-1), w[KEYS[2]]))   # mpnn.py:102
+
+
+def update_layer(w, layer, h, e, norm, adj):
+    agg = torch.matmul(adj, h) / norm                      # mpnn.py:115
+    msg = F.relu(F.linear(torch.cat([agg, e], dim=-1), w[KEYS[3 + 2 * layer]]))     # mpnn.py:117
+    return F.relu(F.linear(torch.cat([h, msg], dim=-1), w[KEYS[4 + 2 * layer]]))    # mpnn.py:118
+
+
+def readout(w, h):
+    pooled = F.linear(h.sum(dim=1) / h.shape[1], w[KEYS[9]])           # mpnn.py:147
+    f = F.relu(torch.cat([pooled.unsqueeze(1).expand_as(h), h], dim=-1))   # mpnn.py:148-150
+    return F.linear(f, w[KEYS[10]], w[KEYS[11]])                        # mpnn.py:152-157
+
+
+@torch.no_grad()
+def mpnn_forward(weights, obs):
+    """obs: float32 [B, 7+N, N] (rows 0..6 features, rows 7.. adjacency) -> Q float32 [B, N].
+
+    Unlike the reference this does not transpose the caller's tensor in place (mpnn.py:44, quirk A.4-2)
+    and always returns [B, N] (the reference squeezes B == 1 away, mpnn.py:75)."""
+    w = weights if isinstance(next(iter(weights.values())), torch.Tensor) else as_torch_weights(weights)
+    obs = torch.as_tensor(obs, dtype=torch.float32)
+    if obs.dim() == 2:
+        obs = obs.unsqueeze(0)
+    obs = obs.transpose(-1, -2)
+    x = obs[:, :, :7]
+    adj = obs[:, :, 7:]
+    norm = degree_norm(adj)
+    h = F.relu(F.linear(x, w[KEYS[0]]))                    # mpnn.py:55
+    e = edge_embedding(w, x, adj, norm)
+    for layer in range(3):                                 # mpnn.py:68-72 (untied weights)
+        h = update_layer(w, layer, h, e, norm, adj)
+    return readout(w, h).squeeze(-1)

@@ -1,0 +1,248 @@
+"""Generate golden vectors by running the UNMODIFIED reference (BetterBelle/eco-dqn) on CPU.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU box):
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+Outputs (committed): tests/golden/*.npz.  Nothing at test time reads /root/reference.
+
+What is recorded ("golden-vector protocol"):
+  * the graph (int8), the env config, the pretrained weights used (12 tensors, fp32);
+  * per episode: init spins, the greedy-Q action sequence the reference took, per-step reward (fp64),
+    per-step score (fp64), final best_solution / best_spins;
+  * for the first few episodes: observation rows 0..6 cast to fp32 exactly as the reference's driver
+    casts them (experiments/utils.py:174), and the reference MPNN's Q-values on those observations;
+  * the reference's own `test_network` result frames for the same seed (cut / greedy columns).
+
+The driver loop below mirrors experiments/utils.py:125-207 but calls only reference objects
+(`make`, `env.reset/step`, `MPNN.forward`); it additionally checks itself against the reference's
+own `test_network` output for the same seed so the recorded trajectories are the reference's.
+"""
+import os
+import sys
+import types
+import pickle
+import warnings
+
+import numpy as np
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+# docplex is absent and only used by CplexSolver (src/agents/solver.py:9) -> stub it.
+for name in ("docplex", "docplex.mp", "docplex.mp.model"):
+    m = types.ModuleType(name)
+    m.Model = object
+    sys.modules[name] = m
+sys.path.insert(0, REF)
+sys.dont_write_bytecode = True
+warnings.filterwarnings("ignore")
+
+import torch  # noqa: E402
+
+import src.envs.core as ising_env  # noqa: E402
+from src.envs.utils import (SingleGraphGenerator, DEFAULT_OBSERVABLES, RewardSignal, ExtraAction,  # noqa: E402
+                            OptimisationTarget, SpinBasis, Stopping)
+from src.networks.mpnn import MPNN  # noqa: E402
+from src.agents.solver import Greedy  # noqa: E402
+from experiments.utils import test_network, load_graph_set  # noqa: E402
+
+torch.set_num_threads(8)
+
+
+def env_args_for(n, basin=True):
+    return {'observables': DEFAULT_OBSERVABLES,
+            'reward_signal': RewardSignal.BLS,
+            'extra_action': ExtraAction.NONE,
+            'optimisation_target': OptimisationTarget.CUT,
+            'spin_basis': SpinBasis.SIGNED,
+            'norm_rewards': True,
+            'memory_length': None,
+            'horizon_length': None,
+            'stag_punishment': None,
+            'basin_reward': (1. / n) if basin else None,
+            'reversible_spins': True,
+            'stopping': Stopping.NORMAL}
+
+
+def load_net(path):
+    net = MPNN(n_obs_in=7, n_layers=3, n_features=64, n_hid_readout=[], tied_weights=False)
+    sd = torch.load(path, map_location="cpu")
+    net.load_state_dict(sd)
+    net.eval()
+    for p in net.parameters():
+        p.requires_grad = False
+    return net, {k: v.numpy().astype(np.float32) for k, v in sd.items()}
+
+
+def run_case(name, graph, net, weights, seed, n_attempts, n_obs_eps, obs_steps, basin=True):
+    """Reference rollout on one graph: B=n_attempts episodes, greedy-Q, T=2N steps."""
+    from copy import deepcopy
+    n = graph.shape[0]
+    T = 2 * n
+    env_args = env_args_for(n, basin)
+
+    # --- 1. the reference's own test_network for this seed ------------------------------------
+    np.random.seed(seed)
+    with open(os.devnull, "w") as devnull:
+        old = sys.stdout
+        sys.stdout = devnull
+        try:
+            res, raw, hist = test_network(net, env_args, [graph], "cpu", 2, n_attempts=n_attempts,
+                                          return_raw=True, return_history=True)
+        finally:
+            sys.stdout = old
+
+    # --- 2. our instrumented driver, same seed -> must reproduce (1) ---------------------------
+    np.random.seed(seed)
+    test_env = ising_env.make("SpinSystem", SingleGraphGenerator(graph), T, **env_args)
+    g_env = deepcopy(test_env)
+    g_env.reset(spins=np.array([-1] * n))
+    Greedy(g_env).solve()
+    greedy_single_cut = g_env.best_solution
+    greedy_single_spins = np.array(g_env.best_spins)
+
+    envs, greedy_envs, obs = [], [], []
+    for _ in range(n_attempts):
+        e = deepcopy(test_env)
+        obs.append(e.reset())
+        envs.append(e)
+        greedy_envs.append(deepcopy(e))
+    init_spins = np.stack([e.best_spins.copy() for e in envs]).astype(np.int8)
+    init_score = np.array([e.score for e in envs], dtype=np.float64)
+    init_cut = np.array([e.best_solution for e in envs], dtype=np.float64)
+
+    actions = np.zeros((n_attempts, T), dtype=np.int32)
+    rewards = np.zeros((n_attempts, T), dtype=np.float64)
+    scores = np.zeros((n_attempts, T + 1), dtype=np.float64)
+    scores[:, 0] = init_score
+    dones = np.zeros((n_attempts, T), dtype=np.uint8)
+    best_scores = np.zeros((n_attempts, T + 1), dtype=np.float64)
+    best_scores[:, 0] = init_score
+    obs_steps = sorted(set(s for s in obs_steps if s <= T))
+    obs_rec = np.zeros((n_obs_eps, len(obs_steps), 7, n), dtype=np.float32)
+    q_rec = np.zeros((n_obs_eps, len(obs_steps), n), dtype=np.float32)
+    for t in range(T):
+        ob = torch.FloatTensor(np.array(obs))           # experiments/utils.py:174
+        if t in obs_steps:
+            obs_rec[:, obs_steps.index(t)] = ob[:n_obs_eps, :7, :].numpy()
+        qs = net(ob.clone())                            # forward transposes its argument in place
+        if t in obs_steps:
+            q_rec[:, obs_steps.index(t)] = qs[:n_obs_eps].numpy()
+        acts = qs.argmax(1, True).squeeze(1).numpy()    # experiments/utils.py:65
+        obs = []
+        for i, (e, a) in enumerate(zip(envs, acts)):
+            o, r, d, _ = e.step(a)
+            actions[i, t] = a
+            rewards[i, t] = r
+            scores[i, t + 1] = e.score
+            best_scores[i, t + 1] = e.best_score
+            dones[i, t] = d
+            obs.append(o)
+    if T in obs_steps:
+        ob = torch.FloatTensor(np.array(obs))
+        obs_rec[:, obs_steps.index(T)] = ob[:n_obs_eps, :7, :].numpy()
+        q_rec[:, obs_steps.index(T)] = net(ob.clone())[:n_obs_eps].numpy()
+    best_cut = np.array([e.best_solution for e in envs], dtype=np.float64)
+    best_spins = np.stack([e.best_spins for e in envs]).astype(np.int8)
+    final_spins = np.stack([e.state[0, :n] for e in envs]).astype(np.int8)
+
+    greedy_cuts, greedy_spins, greedy_steps = [], [], []
+    for e in greedy_envs:
+        Greedy(e).solve()
+        greedy_cuts.append(e.best_solution)
+        greedy_spins.append(np.array(e.best_spins))
+        greedy_steps.append(e.current_step)
+
+    # --- 3. cross-check driver (2) against the reference's own loop (1) -----------------------
+    assert np.array_equal(np.array(raw["init spins"][0]).astype(np.int8), init_spins)
+    assert np.array_equal(np.array(raw["cuts"][0], dtype=np.float64), best_cut)
+    assert np.array_equal(np.array(raw["greedy cuts"][0], dtype=np.float64), np.array(greedy_cuts))
+    h_actions = np.array([[int(a) for a in row[1:]] for row in hist["actions"][0]])
+    assert np.array_equal(h_actions, actions), "driver diverged from reference test_network"
+    h_rewards = np.array([[float(x) for x in row[1:]] for row in hist["rewards"][0]])
+    assert np.array_equal(h_rewards, rewards)
+    assert res["greedy (+1 init) cut"][0] == greedy_single_cut
+
+    sc = test_env.scorer
+    out = dict(
+        J=graph.astype(np.int8), n=np.int32(n), T=np.int32(T), seed=np.int32(seed),
+        basin_reward=np.float64(1. / n if basin else -1.0),
+        mlr=np.float64(sc._max_local_reward), qn=np.float64(sc._solution_quality_normalizer),
+        lb=np.float64(sc._lower_bound),
+        init_spins=init_spins, init_score=init_score, init_cut=init_cut,
+        actions=actions, rewards=rewards, scores=scores, best_scores=best_scores, dones=dones,
+        best_cut=best_cut, best_spins=best_spins, final_spins=final_spins,
+        obs_steps=np.array(obs_steps, dtype=np.int32), obs=obs_rec, q=q_rec,
+        greedy_single_cut=np.float64(greedy_single_cut), greedy_single_spins=greedy_single_spins.astype(np.int8),
+        greedy_cuts=np.array(greedy_cuts, dtype=np.float64), greedy_spins=np.stack(greedy_spins).astype(np.int8),
+        greedy_steps=np.array(greedy_steps, dtype=np.int32),
+        res_cut=np.float64(res["cut"][0]), res_mean_cut=np.float64(res["mean cut"][0]),
+        res_greedy_rand_cut=np.float64(res["greedy (rand init) cut"][0]),
+        res_greedy_rand_mean_cut=np.float64(res["greedy (rand init) mean cut"][0]),
+    )
+    for k, v in weights.items():
+        out["w::" + k] = v
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print("wrote %s (%.1f kB): best cuts %s" % (path, os.path.getsize(path) / 1e3, best_cut[:6]))
+
+
+def main():
+    nets = os.path.join(REF, "experiments/pretrained_agent/networks/eco")
+    val = os.path.join(REF, "_graphs/validation")
+    tst = os.path.join(REF, "_graphs/testing")
+
+    def graphs(p):
+        with open(os.devnull, "w") as dn:
+            old = sys.stdout
+            sys.stdout = dn
+            try:
+                return load_graph_set(p)
+            finally:
+                sys.stdout = old
+
+    er20 = graphs(os.path.join(val, "ER_20spin_p15_100graphs.pkl"))
+    net20, w20 = load_net(os.path.join(nets, "network_best_ER_20spin.pth"))
+    for gi in (0, 1, 7):
+        run_case("er20_g%d" % gi, er20[gi], net20, w20, seed=100 + gi, n_attempts=8, n_obs_eps=4,
+                 obs_steps=range(0, 41))
+    run_case("er20_g3_nobasin", er20[3], net20, w20, seed=7, n_attempts=6, n_obs_eps=2,
+             obs_steps=range(0, 41), basin=False)
+
+    er40 = graphs(os.path.join(val, "ER_40spin_p15_100graphs.pkl"))
+    net40, w40 = load_net(os.path.join(nets, "network_best_ER_40spin.pth"))
+    run_case("er40_g0", er40[0], net40, w40, seed=40, n_attempts=6, n_obs_eps=2, obs_steps=range(0, 81, 2))
+
+    bau = graphs(os.path.join(val, "BA_40spin_m4_uniform_100graphs.pkl"))
+    netb40, wb40 = load_net(os.path.join(nets, "network_best_BA_40spin.pth"))
+    run_case("ba40u_g0", bau[0], netb40, wb40, seed=41, n_attempts=4, n_obs_eps=2, obs_steps=range(0, 81, 4))
+
+    ba60 = graphs(os.path.join(val, "BA_60spin_m4_100graphs.pkl"))
+    netb60, wb60 = load_net(os.path.join(nets, "network_best_BA_60spin.pth"))
+    run_case("ba60_g2", ba60[2], netb60, wb60, seed=60, n_attempts=4, n_obs_eps=2, obs_steps=range(0, 121, 8))
+
+    er200 = graphs(os.path.join(tst, "ER_200spin_p15_50graphs.pkl"))
+    net200, w200 = load_net(os.path.join(nets, "network_best_ER_200spin.pth"))
+    run_case("er200_g0", er200[0], net200, w200, seed=200, n_attempts=4, n_obs_eps=2,
+             obs_steps=list(range(0, 12)) + list(range(20, 401, 20)))
+
+    ba200 = graphs(os.path.join(val, "BA_200spin_m4_100graphs.pkl"))
+    netb200, wb200 = load_net(os.path.join(nets, "network_best_BA_200spin.pth"))
+    run_case("ba200_g0", ba200[0], netb200, wb200, seed=201, n_attempts=4, n_obs_eps=2,
+             obs_steps=list(range(0, 12)) + list(range(20, 401, 20)))
+
+    # A handful of extra BA-200 validation graphs (int8) for the multi-graph GPU tests and known-answer
+    # upper bounds (README.md:82: opts/cuts_* are best-known cut values).
+    with open(os.path.join(val, "opts/cuts_BA_200spin_m4_100graphs.pkl"), "rb") as f:
+        cuts200 = np.array(pickle.load(f), dtype=np.float64)
+    with open(os.path.join(val, "opts/cuts_ER_20spin_p15_100graphs.pkl"), "rb") as f:
+        cuts20 = np.array(pickle.load(f), dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "graphsets.npz"),
+                        ba200=np.stack(ba200[:8]).astype(np.int8), ba200_opt=cuts200[:8],
+                        er20=np.stack(er20[:16]).astype(np.int8), er20_opt=cuts20[:16])
+    print("wrote graphsets.npz")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,103 @@
+"""Pin the CPU oracle against trajectories recorded from the unmodified reference (tests/golden/*.npz)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, golden_cases
+from oracle.spin_env import MaxCutEnv, time_since_flip_table, immanency_table
+from oracle.mpnn import weights_from_npz, mpnn_forward
+from oracle.rollout import rollout, greedy_baseline
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def basin(z):
+    b = float(z["basin_reward"])
+    return None if b < 0 else b
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_env_teacher_forced_bit_exact(name):
+    z = load(name)
+    J, T = z["J"].astype(np.float64), int(z["T"])
+    out = rollout(J, None, z["init_spins"], T, basin(z), forced_actions=z["actions"], record_obs=True)
+    assert np.array_equal(out["rewards"].view(np.uint64), z["rewards"].view(np.uint64)), "fp64 rewards differ"
+    assert np.array_equal(out["scores"], z["scores"])
+    assert np.array_equal(out["best_cut"], z["best_cut"])
+    assert np.array_equal(out["best_spins"], z["best_spins"])
+    assert np.array_equal(out["final_spins"], z["final_spins"])
+    k = z["obs"].shape[0]
+    got = out["obs"][:k][:, z["obs_steps"]]
+    # `==` on fp32 (treats -0.0 == 0.0, like the survey's protocol), plus a sign check on the spin row
+    assert np.array_equal(got, z["obs"])
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_scalars(name):
+    z = load(name)
+    e = MaxCutEnv(z["J"].astype(np.float64), int(z["T"]), basin(z))
+    e.reset(z["init_spins"][0])
+    assert e.mlr == float(z["mlr"]) and e.qn == float(z["qn"]) and e.lb == float(z["lb"])
+    assert e.score == z["init_score"][0] and e.best_solution == z["init_cut"][0]
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_mpnn_q_values(name):
+    z = load(name)
+    w = weights_from_npz(z)
+    J = z["J"].astype(np.float32)
+    k, ns = z["obs"].shape[:2]
+    for si in range(ns):
+        obs = np.concatenate([z["obs"][:, si], np.broadcast_to(J, (k,) + J.shape)], axis=1)
+        q = mpnn_forward(w, obs).numpy()
+        ref = z["q"][:, si]
+        # the golden Q was computed with all n_attempts episodes in the batch (same graph => same norm.max())
+        assert np.allclose(q, ref, rtol=1e-5, atol=1e-5 * np.abs(ref).max()), (name, si)
+        assert np.array_equal(q.argmax(1), ref.argmax(1))
+
+
+@pytest.mark.parametrize("name", ["er20_g0", "er20_g3_nobasin", "ba40u_g0"])
+def test_free_running_rollout_matches_reference(name):
+    z = load(name)
+    w = weights_from_npz(z)
+    torch.set_num_threads(4)
+    out = rollout(z["J"].astype(np.float64), w, z["init_spins"], int(z["T"]), basin(z))
+    assert np.array_equal(out["actions"], z["actions"])
+    assert np.array_equal(out["best_cut"], z["best_cut"])
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_greedy_baseline(name):
+    z = load(name)
+    cuts, spins, steps = greedy_baseline(z["J"].astype(np.float64), z["init_spins"], int(z["T"]), basin(z))
+    assert np.array_equal(cuts, z["greedy_cuts"])
+    assert np.array_equal(spins, z["greedy_spins"])
+    assert np.array_equal(steps, z["greedy_steps"])
+    c1, s1, _ = greedy_baseline(z["J"].astype(np.float64), -np.ones((1, int(z["n"])), dtype=np.int8), int(z["T"]), basin(z))
+    assert c1[0] == float(z["greedy_single_cut"]) and np.array_equal(s1[0], z["greedy_single_spins"])
+
+
+def test_tables_match_repeated_addition():
+    for T in (40, 80, 400):
+        t = time_since_flip_table(T)
+        acc = 0.0
+        for k in range(1, T + 1):
+            acc += 1. / T
+            assert t[k] == acc
+        im = immanency_table(T)
+        assert im[0] == 0 and im[T] == 1.0 and im[1] == max(0, ((1 - T) / T) + 1)
+
+
+def test_known_answer_upper_bounds():
+    """reference README.md:82 -- opts/cuts_* are best-known cuts: no rollout may exceed them."""
+    gs = np.load(os.path.join(GOLDEN, "graphsets.npz"))
+    for name in golden_cases():
+        z = load(name)
+        if name.startswith("er20_g") and "nobasin" not in name:
+            gi = int(name.split("_g")[1])
+            assert np.array_equal(gs["er20"][gi], z["J"])
+            assert z["best_cut"].max() <= gs["er20_opt"][gi]
