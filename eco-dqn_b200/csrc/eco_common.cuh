@@ -1,0 +1,90 @@
+// Shared device/host helpers for the ECO-DQN B200 engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "ecodqn_b200.h"
+
+namespace eco {
+
+// ---- error plumbing -------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+void prof_begin(int kind, cudaStream_t st);   // no-ops unless eco_profile_enable(1)
+void prof_end(int kind, cudaStream_t st);
+
+#define ECO_CHECK_ARG(cond, code, ...)            \
+    do {                                          \
+        if (!(cond)) {                            \
+            eco::set_error(__VA_ARGS__);          \
+            return (code);                        \
+        }                                         \
+    } while (0)
+
+#define ECO_CUDA(call)                                                                        \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            eco::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, \
+                           __LINE__);                                                         \
+            return ECO_ERR_CUDA;                                                              \
+        }                                                                                     \
+    } while (0)
+
+#define ECO_LAUNCH_CHECK()                                                                        \
+    do {                                                                                          \
+        cudaError_t e__ = cudaGetLastError();                                                     \
+        if (e__ != cudaSuccess) {                                                                 \
+            eco::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, \
+                           __LINE__);                                                             \
+            return ECO_ERR_CUDA;                                                                  \
+        }                                                                                         \
+        eco::count_launch();                                                                      \
+    } while (0)
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+static inline int padded_n(int n) { return round_up(n, 16); }
+
+// ---- episode flags --------------------------------------------------------------------------------------
+constexpr int FLAG_DONE = 1;
+constexpr int FLAG_STOPPED = 2;
+constexpr uint64_t VISITED_SALT0 = 0x9E3779B97F4A7C15ull;  // stored key = key ^ salt, so 0 means "empty slot"
+constexpr uint64_t VISITED_SALT1 = 0xC2B2AE3D27D4EB4Full;
+
+// ---- sub-warp group reductions (TPE lanes per episode, TPE <= 32 handled with shuffles) -------------------
+template <int W>
+__device__ __forceinline__ int group_sum(int v) {
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, W);
+    return v;
+}
+template <int W>
+__device__ __forceinline__ int group_max(int v) {
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o, W));
+    return v;
+}
+
+// ---- internal launchers (one translation unit each) -------------------------------------------------------
+int launch_graph_prepare(const eco_graphs_t* g, cudaStream_t st);
+int launch_graph_pad(const eco_graphs_t* g, const int8_t* dense_dev, cudaStream_t st);
+int launch_env_reset(const eco_graphs_t* g, eco_env_t* env, const int32_t* gidx, const int8_t* spins, cudaStream_t st);
+int launch_env_step(const eco_graphs_t* g, eco_env_t* env, int policy, const int32_t* actions, double* reward,
+                    uint8_t* done, int32_t* ha, double* hr, double* hs, cudaStream_t st);
+int launch_env_observation(const eco_env_t* env, float* obs7, cudaStream_t st);
+int launch_env_results(const eco_env_t* env, int32_t* best_cut, int8_t* best_spins, int32_t* steps, cudaStream_t st);
+int launch_mpnn_simt(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int32_t* gidx, const float* xn,
+                     const float* xg, float norm_max, float* q, int32_t* actions, void* scratch, cudaStream_t st);
+size_t mpnn_simt_scratch_bytes(int B, int N);
+int launch_mpnn_tc(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int32_t* gidx, const float* xn,
+                   const float* xg, float norm_max, float* q, int32_t* actions, void* scratch, cudaStream_t st);
+size_t mpnn_tc_scratch_bytes(int B, int N);
+size_t mpnn_tc_packed_bytes();
+int launch_mpnn_pack(const eco_mpnn_t* w, void* packed, cudaStream_t st);
+bool mpnn_tc_supported(const eco_graphs_t* g);
+
+}  // namespace eco

@@ -1,0 +1,407 @@
+// Kernel family 1: the fused, batched environment step (and reset) for Max-Cut ECO-DQN episodes.
+//
+// Replaces (reference, file:line)
+//   src/envs/spinsystem.py:355-559   SpinSystemBase.step      -> env_step_kernel
+//   src/envs/spinsystem.py:183-259   SpinSystemBase.reset     -> env_reset_kernel
+//   src/envs/spinsystem.py:283-330   _reset_state             -> env_reset_kernel
+//   src/envs/spinsystem.py:561-574   get_observation          -> env_observation_kernel (rows 0..6 only)
+//   src/envs/score_solver.py:377-419 MaximumCutUnbiasedScorer masks  -> O(N) incremental local fields
+//   src/envs/utils.py:97-102         calculate_cut_changes    -> s_i * h_i with h updated from row a of J
+//   src/envs/utils.py:438-464        HistoryBuffer            -> 128-bit Zobrist key + open-addressed set
+//   src/agents/solver.py:105-131     Greedy.step              -> ECO_POLICY_GREEDY inside env_step_kernel
+//
+// One flip touches, per episode: row a of the int8 adjacency (N B), the spins (N B), the int16 local
+// fields (2N B read + 2N B write), the uint16 last-flip steps (2N B), the best-diff bitmask, the three fp32
+// per-vertex observable rows (12N B written) and a 96-byte scalar block: 20.25 N + 96 bytes, all in
+// 8-vertex (8/16/32-byte) vector accesses, TPE lanes per episode.  The fp64 bookkeeping reproduces the
+// reference's operation order with explicit round-to-nearest intrinsics so the
+// compiler cannot contract it.
+#include "eco_common.cuh"
+
+namespace eco {
+
+namespace {
+
+template <int TPE, bool BLOCK>
+struct Grp {
+    // BLOCK == false: TPE <= 32 lanes of one warp own an episode; BLOCK == true: the whole CTA (TPE threads).
+    __device__ static int lane() { return BLOCK ? threadIdx.x : (threadIdx.x % TPE); }
+    __device__ static long long episode() {
+        return BLOCK ? (long long)blockIdx.x : ((long long)blockIdx.x * blockDim.x + threadIdx.x) / TPE;
+    }
+    __device__ static void sync() {
+        if (BLOCK) __syncthreads(); else __syncwarp();
+    }
+    __device__ static int sum(int v, int* sm) {
+        if constexpr (!BLOCK) {
+            return group_sum<TPE>(v);
+        } else {
+            v = group_sum<32>(v);
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+            __syncthreads();
+            int t = 0;
+            for (int w = 0; w < TPE / 32; ++w) t += sm[w];
+            return t;
+        }
+    }
+    __device__ static int maxv(int v, int* sm) {
+        if constexpr (!BLOCK) {
+            return group_max<TPE>(v);
+        } else {
+            v = group_max<32>(v);
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+            __syncthreads();
+            int t = INT_MIN;
+            for (int w = 0; w < TPE / 32; ++w) t = max(t, sm[w]);
+            return t;
+        }
+    }
+    __device__ static int bcast(int v, int* sm) {  // value of lane 0
+        if constexpr (!BLOCK) {
+            return __shfl_sync(0xffffffffu, v, 0, TPE);
+        } else {
+            __syncthreads();
+            if (threadIdx.x == 0) sm[0] = v;
+            __syncthreads();
+            return sm[0];
+        }
+    }
+};
+
+union V8s { uint2 v; int8_t b[8]; };
+union V8h { uint4 v; int16_t h[8]; };
+union V8u { uint4 v; uint16_t h[8]; };
+
+__device__ __forceinline__ float feat_gain(int gain, double mlr) {
+    // row 1: immediate_quality_changes / max_local_reward in fp64, then the driver's fp32 cast
+    return (float)__ddiv_rn((double)gain, mlr);
+}
+
+// ------------------------------------------------------------------------------------------------ step
+template <int TPE, bool BLOCK>
+__global__ void __launch_bounds__(BLOCK ? TPE : 128)
+env_step_kernel(const eco_graphs_t g, const eco_env_t env, const int policy, const int32_t* __restrict__ actions,
+                double* __restrict__ reward_out, uint8_t* __restrict__ done_out, int32_t* __restrict__ hist_a,
+                double* __restrict__ hist_r, double* __restrict__ hist_s) {
+    using G = Grp<TPE, BLOCK>;
+    __shared__ int sm[8];
+    const int lane = G::lane();
+    long long b = G::episode();
+    const bool in_range = b < env.B;
+    if (!in_range) b = env.B - 1;  // keep every lane alive for the group shuffles
+    const int N = env.N, NP = env.NP, NCH = NP / 8;
+
+    eco_episode_t* ep = env.ep + b;
+    const int flags = ep->flags;
+    bool active = in_range && !(flags & (FLAG_DONE | FLAG_STOPPED));
+    const int step_new = ep->step + 1;
+    if (active && step_new > env.T) active = false;  // reference raises here (spinsystem.py:365-367)
+
+    const int gi = env.graph_idx[b];
+    const int8_t* Jg = g.J + (size_t)gi * NP * NP;
+    int8_t* spins = env.spins + (size_t)b * NP;
+    int16_t* hf = env.hfield + (size_t)b * NP;
+    uint16_t* lf = env.last_flip + (size_t)b * NP;
+    const double mlr = g.gscal[(size_t)gi * 4 + 0];
+
+    // ---- choose the action ----------------------------------------------------------------------------
+    int a;
+    if (policy == ECO_POLICY_GREEDY) {
+        // argmax_i s_i h_i, first maximal index (numpy argmax, solver.py:116)
+        int best = INT_MIN;
+        for (int c = lane; c < NCH; c += TPE) {
+            V8s s; V8h h;
+            s.v = *reinterpret_cast<const uint2*>(spins + c * 8);
+            h.v = *reinterpret_cast<const uint4*>(hf + c * 8);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int i = c * 8 + k;
+                if (i < N) best = max(best, ((s.b[k] * h.h[k] + 32768) << 16) | (0xFFFF - i));
+            }
+        }
+        best = G::maxv(best, sm);
+        a = 0xFFFF - (best & 0xFFFF);
+        if (active && ((best >> 16) - 32768) < 0) {  // solver.py:124: stop only if the best gain is < 0
+            active = false;
+            if (lane == 0) ep->flags = flags | FLAG_STOPPED;
+        }
+    } else {
+        a = actions[b];
+    }
+    if (a < 0 || a >= N) { a = 0; active = false; }
+
+    const int s_a_old = spins[a];
+    const int h_a_old = hf[a];
+    const int s_a_new = -s_a_old;
+    const uint32_t old_word = env.diff_bits[(size_t)b * env.NW + (a >> 5)];
+    G::sync();  // everyone has read the pre-flip values before anyone writes
+
+    // ---- O(N) local-field update + per-vertex observables ------------------------------------------
+    int nimp = 0;
+    if (active) {
+        const int8_t* Jrow = Jg + (size_t)a * NP;
+        float* x0 = env.xn + (size_t)b * 3 * NP;
+        float* x1 = x0 + NP;
+        float* x2 = x1 + NP;
+        for (int c = lane; c < NCH; c += TPE) {
+            V8s s, j; V8h h; V8u l;
+            s.v = *reinterpret_cast<const uint2*>(spins + c * 8);
+            j.v = *reinterpret_cast<const uint2*>(Jrow + c * 8);
+            h.v = *reinterpret_cast<const uint4*>(hf + c * 8);
+            l.v = *reinterpret_cast<const uint4*>(lf + c * 8);
+            float f0[8], f1[8], f2[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int i = c * 8 + k;
+                int si = s.b[k];
+                if (i == a) { si = s_a_new; s.b[k] = (int8_t)si; l.h[k] = (uint16_t)step_new; }
+                const int hi = h.h[k] + 2 * j.b[k] * s_a_new;  // J_aa == 0, so h_a is unchanged
+                h.h[k] = (int16_t)hi;
+                const int gain = si * hi;
+                nimp += gain > 0;
+                f0[k] = (float)si;
+                f1[k] = feat_gain(gain, mlr);
+                f2[k] = env.tsf_tab[step_new - l.h[k]];
+            }
+            *reinterpret_cast<uint4*>(hf + c * 8) = h.v;
+            if ((a >> 3) == c) {
+                *reinterpret_cast<uint2*>(spins + c * 8) = s.v;
+                *reinterpret_cast<uint4*>(lf + c * 8) = l.v;
+            }
+            *reinterpret_cast<float4*>(x0 + c * 8) = make_float4(f0[0], f0[1], f0[2], f0[3]);
+            *reinterpret_cast<float4*>(x0 + c * 8 + 4) = make_float4(f0[4], f0[5], f0[6], f0[7]);
+            *reinterpret_cast<float4*>(x1 + c * 8) = make_float4(f1[0], f1[1], f1[2], f1[3]);
+            *reinterpret_cast<float4*>(x1 + c * 8 + 4) = make_float4(f1[4], f1[5], f1[6], f1[7]);
+            *reinterpret_cast<float4*>(x2 + c * 8) = make_float4(f2[0], f2[1], f2[2], f2[3]);
+            *reinterpret_cast<float4*>(x2 + c * 8 + 4) = make_float4(f2[4], f2[5], f2[6], f2[7]);
+        }
+    }
+    nimp = G::sum(nimp, sm);
+
+    // ---- scalar bookkeeping, lane 0, in the reference's fp64 operation order (appendix A.2) ---------
+    int new_best = 0;
+    if (lane == 0 && active) {
+        const double qn = g.gscal[(size_t)gi * 4 + 1];
+        const int delta = s_a_old * h_a_old;                            // spinsystem.py:393
+        const double delta_n = __ddiv_rn((double)delta, qn);            // :394
+        const double score = __dadd_rn(ep->score, (double)delta);       // :399
+        const double nscore = __dadd_rn(ep->nscore, delta_n);           // :400
+        const double best_score = ep->best_score, best_nscore = ep->best_nscore;
+        const int cut = ep->cut + delta;
+        double rew = 0.0;
+        if (score > best_score) rew = __dsub_rn(nscore, best_nscore);   // :418-424 (BLS, normalised)
+
+        uint64_t k0 = ep->key[0] ^ env.zobrist[2 * a], k1 = ep->key[1] ^ env.zobrist[2 * a + 1];
+        int n_visited = ep->n_visited;
+        if (env.use_basin) {                                            // :443-457
+            const uint64_t e0 = k0 ^ VISITED_SALT0, e1 = k1 ^ VISITED_SALT1;
+            uint64_t* tab = env.visited + (size_t)b * env.HCAP * 2;
+            uint32_t slot = (uint32_t)(k0 ^ (k0 >> 29)) & (env.HCAP - 1);
+            bool is_new = false;
+            for (int probe = 0; probe < env.HCAP; ++probe) {
+                const uint64_t t0 = tab[2 * slot], t1 = tab[2 * slot + 1];
+                if (t0 == 0 && t1 == 0) { tab[2 * slot] = e0; tab[2 * slot + 1] = e1; is_new = true; ++n_visited; break; }
+                if (t0 == e0 && t1 == e1) break;
+                slot = (slot + 1) & (env.HCAP - 1);
+            }
+            if (nimp == 0 && is_new) rew = __dadd_rn(rew, env.basin_reward);
+        }
+        int dist = ep->dist + (((old_word >> (a & 31)) & 1u) ? -1 : 1);
+        int best_cut = ep->best_cut;
+        double nbs = best_score, nbn = best_nscore;
+        if (score > best_score) {                                       // :459-463
+            nbs = score; nbn = nscore; best_cut = cut; dist = 0; new_best = 1;
+        }
+        const int done = step_new == env.T;                             // :541-544
+        ep->step = step_new; ep->cut = cut; ep->best_cut = best_cut; ep->dist = dist;
+        ep->n_improving = nimp; ep->flags = flags | (done ? FLAG_DONE : 0); ep->n_visited = n_visited;
+        ep->score = score; ep->nscore = nscore; ep->best_score = nbs; ep->best_nscore = nbn;
+        ep->key[0] = k0; ep->key[1] = k1;
+        ep->total_reward = __dadd_rn(ep->total_reward, rew); ep->last_reward = rew;
+
+        // global observables rows 3..6 (spinsystem.py:509-527), fp64 then the driver's fp32 cast
+        float4 xg;
+        xg.x = (float)__ddiv_rn(fabs(__dsub_rn(score, nbs)), mlr);
+        xg.y = (float)dist;
+        xg.z = (float)__ddiv_rn((double)nimp, (double)N);
+        xg.w = env.imm_tab[step_new];
+        *reinterpret_cast<float4*>(env.xg + (size_t)b * 4) = xg;
+
+        if (reward_out) reward_out[b] = rew;
+        if (done_out) done_out[b] = (uint8_t)done;
+        const size_t hidx = (size_t)b * env.T + (step_new - 1);
+        if (hist_a) hist_a[hidx] = a;
+        if (hist_r) hist_r[hidx] = rew;
+        if (hist_s) hist_s[hidx] = score;
+    } else if (lane == 0 && in_range) {
+        if (reward_out) reward_out[b] = 0.0;
+        if (done_out) done_out[b] = 1;
+    }
+    new_best = G::bcast(new_best, sm);
+
+    // ---- best-diff bitmask: toggle bit a, or clear everything when this state is the new best --------
+    if (active) {
+        uint32_t* diff = env.diff_bits + (size_t)b * env.NW;
+        for (int w = lane; w < env.NW; w += TPE) {
+            if (new_best) diff[w] = 0u;
+            else if (w == (a >> 5)) diff[w] = old_word ^ (1u << (a & 31));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ reset
+template <int TPE, bool BLOCK>
+__global__ void __launch_bounds__(BLOCK ? TPE : 128)
+env_reset_kernel(const eco_graphs_t g, const eco_env_t env, const int32_t* __restrict__ graph_idx,
+                 const int8_t* __restrict__ init_spins) {
+    using G = Grp<TPE, BLOCK>;
+    __shared__ int sm[8];
+    const int lane = G::lane();
+    long long b = G::episode();
+    const bool in_range = b < env.B;
+    if (!in_range) b = env.B - 1;
+    const int N = env.N, NP = env.NP;
+    const int gi = graph_idx[b];
+    const int8_t* Jg = g.J + (size_t)gi * NP * NP;
+    int8_t* spins = env.spins + (size_t)b * NP;
+    int16_t* hf = env.hfield + (size_t)b * NP;
+    const double mlr = g.gscal[(size_t)gi * 4 + 0];
+
+    if (in_range) {
+        for (int i = lane; i < NP; i += TPE) {
+            spins[i] = i < N ? init_spins[(size_t)b * N + i] : (int8_t)0;
+            env.last_flip[(size_t)b * NP + i] = 0;
+        }
+        for (int w = lane; w < env.NW; w += TPE) env.diff_bits[(size_t)b * env.NW + w] = 0u;
+        if (lane == 0) env.graph_idx[b] = gi;
+    }
+    G::sync();
+    __threadfence_block();
+
+    int nimp = 0, ssh = 0;
+    if (in_range) {
+        float* x0 = env.xn + (size_t)b * 3 * NP;
+        const int* sw = reinterpret_cast<const int*>(spins);
+        for (int i = lane; i < NP; i += TPE) {
+            const int* jw = reinterpret_cast<const int*>(Jg + (size_t)i * NP);
+            int acc = 0;
+            for (int w = 0; w < NP / 4; ++w) acc = __dp4a(jw[w], sw[w], acc);  // h_i = sum_j J_ij s_j
+            hf[i] = (int16_t)acc;
+            const int si = spins[i];
+            const int gain = si * acc;
+            nimp += gain > 0;
+            ssh += gain;
+            x0[i] = (float)si;                                         // spinsystem.py:294/299
+            x0[NP + i] = i < N ? feat_gain(gain, mlr) : 0.f;           // :311-312
+            x0[2 * NP + i] = 0.f;
+        }
+    }
+    nimp = G::sum(nimp, sm);
+    ssh = G::sum(ssh, sm);
+    if (lane == 0 && in_range) {
+        const double qn = g.gscal[(size_t)gi * 4 + 1], lb = g.gscal[(size_t)gi * 4 + 2];
+        const int sumJ = (int)g.gscal[(size_t)gi * 4 + 3];
+        const int cut = (sumJ - ssh) / 4;                              // utils.py:90-94, exact in integers
+        const double score = __dadd_rn((double)cut, fabs(fmin(0.0, lb)));   // score_solver.py:182-200
+        const double nscore = __ddiv_rn(score, qn);                    // :190-194
+        eco_episode_t e;
+        e.step = 0; e.cut = cut; e.best_cut = cut; e.dist = 0; e.n_improving = nimp; e.flags = 0;
+        e.n_visited = 0; e.reserved = 0;
+        e.score = score; e.nscore = nscore; e.best_score = score; e.best_nscore = nscore;
+        e.key[0] = 0; e.key[1] = 0; e.total_reward = 0.0; e.last_reward = 0.0;
+        env.ep[b] = e;
+        float4 xg = make_float4(0.f, 0.f, (float)__ddiv_rn((double)nimp, (double)N), 0.f);  // :321-322
+        *reinterpret_cast<float4*>(env.xg + (size_t)b * 4) = xg;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ views
+__global__ void env_observation_kernel(const eco_env_t env, float* __restrict__ obs7) {
+    const size_t total = (size_t)env.B * 7 * env.N;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int i = idx % env.N;
+        const int r = (idx / env.N) % 7;
+        const size_t b = idx / ((size_t)7 * env.N);
+        obs7[idx] = r < 3 ? env.xn[(b * 3 + r) * env.NP + i] : env.xg[b * 4 + (r - 3)];
+    }
+}
+
+__global__ void env_results_kernel(const eco_env_t env, int32_t* __restrict__ best_cut,
+                                   int8_t* __restrict__ best_spins, int32_t* __restrict__ steps) {
+    const size_t total = (size_t)env.B * env.N;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int i = idx % env.N;
+        const size_t b = idx / env.N;
+        if (best_spins) {
+            const int s = env.spins[b * env.NP + i];
+            const uint32_t w = env.diff_bits[b * env.NW + (i >> 5)];
+            best_spins[idx] = (int8_t)(((w >> (i & 31)) & 1u) ? -s : s);
+        }
+        if (i == 0) {
+            if (best_cut) best_cut[b] = env.ep[b].best_cut;
+            if (steps) steps[b] = env.ep[b].step;
+        }
+    }
+}
+
+}  // namespace
+
+#define ECO_ENV_DISPATCH(KERNEL, ...)                                                                       \
+    do {                                                                                                    \
+        const int NP_ = env->NP;                                                                            \
+        const long long B_ = env->B;                                                                        \
+        if (NP_ <= 32) {                                                                                    \
+            KERNEL<4, false><<<(unsigned)((B_ * 4 + 127) / 128), 128, 0, st>>>(__VA_ARGS__);                \
+        } else if (NP_ <= 64) {                                                                             \
+            KERNEL<8, false><<<(unsigned)((B_ * 8 + 127) / 128), 128, 0, st>>>(__VA_ARGS__);                \
+        } else if (NP_ <= 128) {                                                                            \
+            KERNEL<16, false><<<(unsigned)((B_ * 16 + 127) / 128), 128, 0, st>>>(__VA_ARGS__);              \
+        } else if (NP_ <= 256) {                                                                            \
+            KERNEL<32, false><<<(unsigned)((B_ * 32 + 127) / 128), 128, 0, st>>>(__VA_ARGS__);              \
+        } else if (NP_ <= 1024) {                                                                           \
+            KERNEL<128, true><<<(unsigned)B_, 128, 0, st>>>(__VA_ARGS__);                                   \
+        } else {                                                                                            \
+            KERNEL<256, true><<<(unsigned)B_, 256, 0, st>>>(__VA_ARGS__);                                   \
+        }                                                                                                   \
+    } while (0)
+
+int launch_env_step(const eco_graphs_t* g, eco_env_t* env, int policy, const int32_t* actions, double* reward,
+                    uint8_t* done, int32_t* ha, double* hr, double* hs, cudaStream_t st) {
+    prof_begin(ECO_PROF_ENV_STEP, st);
+    ECO_ENV_DISPATCH(env_step_kernel, *g, *env, policy, actions, reward, done, ha, hr, hs);
+    prof_end(ECO_PROF_ENV_STEP, st);
+    ECO_LAUNCH_CHECK();
+    return ECO_OK;
+}
+
+int launch_env_reset(const eco_graphs_t* g, eco_env_t* env, const int32_t* gidx, const int8_t* spins,
+                     cudaStream_t st) {
+    if (env->use_basin)
+        ECO_CUDA(cudaMemsetAsync(env->visited, 0, (size_t)env->B * env->HCAP * 16, st));
+    ECO_ENV_DISPATCH(env_reset_kernel, *g, *env, gidx, spins);
+    ECO_LAUNCH_CHECK();
+    return ECO_OK;
+}
+
+int launch_env_observation(const eco_env_t* env, float* obs7, cudaStream_t st) {
+    const size_t total = (size_t)env->B * 7 * env->N;
+    const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+    env_observation_kernel<<<blocks, 256, 0, st>>>(*env, obs7);
+    ECO_LAUNCH_CHECK();
+    return ECO_OK;
+}
+
+int launch_env_results(const eco_env_t* env, int32_t* best_cut, int8_t* best_spins, int32_t* steps,
+                       cudaStream_t st) {
+    const size_t total = (size_t)env->B * env->N;
+    const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+    env_results_kernel<<<blocks, 256, 0, st>>>(*env, best_cut, best_spins, steps);
+    ECO_LAUNCH_CHECK();
+    return ECO_OK;
+}
+
+}  // namespace eco

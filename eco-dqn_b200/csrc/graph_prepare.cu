@@ -1,0 +1,115 @@
+// Graph-set preparation: padding and the per-graph scorer constants.
+//
+// Replaces (reference, file:line)
+//   src/envs/score_solver.py:353-357  set_quality_normalizer  qn  = max(1, sum_{J>0} J / 2)
+//   src/envs/score_solver.py:359-365  set_lower_bound         lb  = min(0, sum_{J<0} J / 2)
+//   src/envs/score_solver.py:367-375  set_max_local_reward    mlr = max over NON-ZERO weighted degrees
+//   src/networks/mpnn.py:34-38        get_normalisation       deg_i = max(1, #{j : J_ij != 0})
+// All sums are integer (int8 couplings), hence exact and identical to the reference's fp64 sums.
+#include "eco_common.cuh"
+
+namespace eco {
+
+__global__ void graph_pad_kernel(const int8_t* __restrict__ dense, int8_t* __restrict__ J, int G, int N, int NP) {
+    // one thread per 16-byte chunk of the padded layout
+    const size_t chunks_per_row = NP / 16;
+    const size_t total = (size_t)G * NP * chunks_per_row;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int c = idx % chunks_per_row;
+        const size_t row = idx / chunks_per_row;
+        const int i = row % NP;
+        const size_t gi = row / NP;
+        union { int8_t b[16]; uint4 v; } u;
+        u.v = make_uint4(0, 0, 0, 0);
+        if (i < N) {
+            const int8_t* src = dense + (gi * N + i) * (size_t)N + c * 16;
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+                if (c * 16 + k < N) u.b[k] = src[k];
+        }
+        *reinterpret_cast<uint4*>(J + row * NP + c * 16) = u.v;
+    }
+}
+
+// one CTA per graph, one warp per row (strided)
+__global__ void __launch_bounds__(256) graph_prepare_kernel(eco_graphs_t g) {
+    const int gi = blockIdx.x;
+    const int N = g.N, NP = g.NP;
+    const int8_t* J = g.J + (size_t)gi * NP * NP;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+
+    __shared__ int s_sum[8], s_pos[8], s_neg[8], s_mlr[8], s_maxdeg[8], s_nnz[8], s_maxabs[8], s_flags[8];
+    int t_sum = 0, t_pos = 0, t_neg = 0, t_mlr = INT_MIN, t_maxdeg = 0, t_nnz = 0, t_maxabs = 0, t_flags = 0;
+
+    for (int i = warp; i < NP; i += nwarp) {
+        int rs = 0, ra = 0, rp = 0, rn = 0, cnt = 0, bad = 0;
+        for (int j = lane; j < NP; j += 32) {
+            const int v = J[(size_t)i * NP + j];
+            rs += v;
+            ra += abs(v);
+            rp += v > 0 ? v : 0;
+            rn += v < 0 ? v : 0;
+            cnt += v != 0;
+            bad |= (v > 1 || v < -1) ? 1 : 0;
+            if (i < N && j < N) bad |= (J[(size_t)j * NP + i] != v) ? 4 : 0;
+            if (i == j && v != 0) bad |= 4;
+            if ((i >= N || j >= N) && v != 0) bad |= 4;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            rs += __shfl_xor_sync(0xffffffffu, rs, o);
+            ra += __shfl_xor_sync(0xffffffffu, ra, o);
+            rp += __shfl_xor_sync(0xffffffffu, rp, o);
+            rn += __shfl_xor_sync(0xffffffffu, rn, o);
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+        }
+        if (lane == 0) g.deg[(size_t)gi * NP + i] = (float)max(cnt, 1);
+        t_sum += rs;
+        t_pos += rp;
+        t_neg += rn;
+        t_nnz += cnt;
+        t_flags |= bad;
+        t_maxdeg = max(t_maxdeg, cnt);
+        t_maxabs = max(t_maxabs, ra);
+        if (i < N && rs != 0) t_mlr = max(t_mlr, rs);
+    }
+    if (lane == 0) {
+        s_sum[warp] = t_sum; s_pos[warp] = t_pos; s_neg[warp] = t_neg; s_mlr[warp] = t_mlr;
+        s_maxdeg[warp] = t_maxdeg; s_nnz[warp] = t_nnz; s_maxabs[warp] = t_maxabs; s_flags[warp] = t_flags;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int sum = 0, pos = 0, neg = 0, mlr = INT_MIN, maxdeg = 0, nnz = 0, maxabs = 0, flags = 0;
+        for (int w = 0; w < nwarp; ++w) {
+            sum += s_sum[w]; pos += s_pos[w]; neg += s_neg[w]; mlr = max(mlr, s_mlr[w]);
+            maxdeg = max(maxdeg, s_maxdeg[w]); nnz += s_nnz[w]; maxabs = max(maxabs, s_maxabs[w]);
+            flags |= s_flags[w];
+        }
+        if (mlr == INT_MIN) { flags |= 2; mlr = 1; }
+        double* gs = g.gscal + (size_t)gi * 4;
+        gs[0] = (double)mlr;
+        gs[1] = fmax(1.0, (double)pos / 2.0);
+        gs[2] = fmin(0.0, (double)neg / 2.0);
+        gs[3] = (double)sum;
+        int32_t* st = g.gstat + (size_t)gi * 4;
+        st[0] = maxdeg; st[1] = nnz; st[2] = maxabs; st[3] = flags;
+    }
+}
+
+int launch_graph_pad(const eco_graphs_t* g, const int8_t* dense_dev, cudaStream_t st) {
+    const size_t total = (size_t)g->G * g->NP * (g->NP / 16);
+    const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    graph_pad_kernel<<<blocks, 256, 0, st>>>(dense_dev, g->J, g->G, g->N, g->NP);
+    ECO_LAUNCH_CHECK();
+    return ECO_OK;
+}
+
+int launch_graph_prepare(const eco_graphs_t* g, cudaStream_t st) {
+    graph_prepare_kernel<<<g->G, 256, 0, st>>>(*g);
+    ECO_LAUNCH_CHECK();
+    return ECO_OK;
+}
+
+}  // namespace eco

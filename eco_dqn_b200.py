@@ -1,0 +1,10 @@
+"""Import shim: makes the package directory `eco-dqn_b200/` importable as `eco_dqn_b200`."""
+import os as _os
+
+__path__ = [_os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "eco-dqn_b200")]
+__package__ = "eco_dqn_b200"
+if __spec__ is not None:
+    __spec__.submodule_search_locations = __path__
+__file__ = _os.path.join(__path__[0], "__init__.py")
+with open(__file__) as _f:
+    exec(compile(_f.read(), __file__, "exec"))

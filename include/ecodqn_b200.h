@@ -1,0 +1,213 @@
+/*
+ * ecodqn_b200.h -- C ABI of the B200-native batched ECO-DQN Max-Cut rollout engine.
+ *
+ * This is the drop-in boundary for ONE hot path of BetterBelle/eco-dqn: batched environment stepping +
+ * MPNN Q-evaluation + greedy action selection.  The reference is pure Python and has
+ * no FFI of its own; each entry point below names the reference interface it replaces (file:line under the
+ * reference tree) and INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only.  Pointers named *_dev are CUDA device pointers on the
+ *     current device; *_host are host pointers (pinned memory recommended).  `stream` is a cudaStream_t
+ *     passed as void* (NULL = legacy default stream).  Nothing here allocates device memory except
+ *     eco_host_session_*; callers own every buffer (PyTorch's caching allocator in the Python host).
+ *   - Every function returns ECO_OK (0) or a negative error code; eco_last_error() gives the message of the
+ *     last failure on the calling thread.  Shape / configuration violations are rejected before any launch.
+ *   - All work is enqueued asynchronously on `stream`; no entry point synchronises unless it says so.
+ *   - Vertices are padded to NP = 16*ceil(N/16) per row; padded entries are zero and never selected.
+ *   - Integer-weight graphs only (int8 couplings; the reference's EdgeType.UNIFORM / DISCRETE).  There is no
+ *     CPU fallback anywhere in this library.
+ */
+#ifndef ECODQN_B200_H
+#define ECODQN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ECO_OK                 0
+#define ECO_ERR_INVALID       -1   /* bad argument / shape / alignment                                    */
+#define ECO_ERR_UNSUPPORTED   -2   /* configuration outside the accelerated path (NotImplementedError)    */
+#define ECO_ERR_CUDA          -3   /* a CUDA runtime call failed (message has the cudaError string)       */
+#define ECO_ERR_STATE         -4   /* e.g. stepping an environment that already returned done             */
+
+#define ECO_ABI_VERSION        1
+#define ECO_N_FEATURES         64  /* MPNN width, reference src/networks/mpnn.py:9                         */
+#define ECO_N_OBS              7   /* DEFAULT_OBSERVABLES, reference src/envs/utils.py:68-74               */
+#define ECO_MAX_SPINS          2048
+
+/* policies for eco_env_step / eco_rollout */
+#define ECO_POLICY_ACTIONS     0   /* actions supplied by the caller (teacher forcing, epsilon-greedy)     */
+#define ECO_POLICY_NETWORK     1   /* argmax_i Q_i, lowest index on ties (experiments/utils.py:57-66)      */
+#define ECO_POLICY_GREEDY      2   /* argmax_i s_i h_i, stop when the best gain < 0 (src/agents/solver.py:105-131) */
+
+/* MPNN implementations */
+#define ECO_MPNN_AUTO          0
+#define ECO_MPNN_SIMT          1   /* fp32 CUDA-core kernel: any int8 weights, any N <= ECO_MAX_SPINS      */
+#define ECO_MPNN_TCGEN05       2   /* tcgen05/TMEM tensor-core kernel: weights in {-1,0,1}, N <= 208       */
+
+const char* eco_last_error(void);
+int         eco_abi_version(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Graph set: G dense symmetric int8 adjacency matrices of N vertices, shared read-only by all episodes.
+ * Replaces the per-env `self.matrix` (reference src/envs/spinsystem.py:151-155,196) supplied by
+ * SingleGraphGenerator / SetGraphGenerator (src/envs/utils.py:337-345, 376-382), and the scorer constants
+ * of MaximumCutUnbiasedScorer (src/envs/score_solver.py:347-375): mlr, qn, lb.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t  G, N, NP, reserved;
+    int8_t*  J;          /* [G, NP, NP]  couplings, zero padded                                              */
+    double*  gscal;      /* [G, 4]       mlr (max non-zero weighted degree), qn, lb, sum_ij J_ij             */
+    float*   deg;        /* [G, NP]      max(1, #non-zeros in row i)  (mpnn.py:34-38)                        */
+    int32_t* gstat;      /* [G, 4]       max degree, nnz, max |row abs sum|, flags (bit0: weights outside {-1,0,1},
+                                         bit1: all weighted degrees zero, bit2: not symmetric / non-zero diagonal)  */
+    float*   dmax;       /* [1]          max degree over the whole set (default norm.max(), mpnn.py:102)     */
+} eco_graphs_t;
+
+size_t eco_graphs_workspace_bytes(int32_t G, int32_t N);
+/* carve `workspace_dev` (>= eco_graphs_workspace_bytes, 256-byte aligned) into the arrays of `g` */
+int    eco_graphs_bind(eco_graphs_t* g, void* workspace_dev, int32_t G, int32_t N);
+/* copy G*N*N int8 couplings from host memory into the padded device layout (async on stream) and prepare */
+int    eco_graphs_upload(eco_graphs_t* g, const int8_t* J_host, void* stream);
+/* same, source already on the device, dense [G, N, N] */
+int    eco_graphs_load_dev(eco_graphs_t* g, const int8_t* J_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Batched environment state (struct of arrays), B independent episodes.
+ * Replaces SpinSystemBase's per-episode Python state (reference src/envs/spinsystem.py:183-259, 355-559):
+ * self.state rows 0..6, score / normalized_score, best_* trackers, current_step, HistoryBuffer.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct {          /* 96 bytes per episode                                                            */
+    int32_t step;         /* current_step                                                                    */
+    int32_t cut;          /* cut value of the current spins (integer for integer couplings)                  */
+    int32_t best_cut;     /* best_solution                                                                   */
+    int32_t dist;         /* Hamming distance to best_obs_spins (observable row 4)                           */
+    int32_t n_improving;  /* #{i : s_i h_i > 0} (observable row 5 numerator; 0 <=> local optimum)            */
+    int32_t flags;        /* bit0 done, bit1 greedy-stopped                                                  */
+    int32_t n_visited;    /* entries in the visited-set table                                                */
+    int32_t reserved;
+    double  score, nscore, best_score, best_nscore;
+    uint64_t key[2];      /* 128-bit Zobrist key of the set of vertices flipped w.r.t. the initial spins     */
+    double  total_reward; /* running sum of rewards (solver.py:60-61 total_reward)                           */
+    double  last_reward;
+} eco_episode_t;
+
+typedef struct {
+    int32_t  B, N, NP, NW;          /* NW = NP/32 rounded up: words of the best-diff bitmask                 */
+    int32_t  T, HCAP, use_basin, reserved;
+    double   basin_reward;          /* added when a NEW local optimum is reached (spinsystem.py:450-457)     */
+    int8_t*        spins;           /* [B, NP]                                                               */
+    int16_t*       hfield;          /* [B, NP]  local fields h = J s                                         */
+    uint16_t*      last_flip;       /* [B, NP]  step at which vertex i was last flipped (0 = never)          */
+    uint32_t*      diff_bits;       /* [B, NW]  bit i set <=> s_i != best_obs_spins_i                        */
+    int32_t*       graph_idx;       /* [B]                                                                   */
+    eco_episode_t* ep;              /* [B]                                                                   */
+    uint64_t*      visited;         /* [B, HCAP, 2]  open-addressed set of 128-bit keys (utils.py:438-464)   */
+    uint64_t*      zobrist;         /* [NP, 2]                                                               */
+    float*         tsf_tab;         /* [T+1]  k-fold fp64 sum of 1/T, cast to fp32 (spinsystem.py:493)       */
+    float*         imm_tab;         /* [T+1]  termination immanency per step (spinsystem.py:509-511)         */
+    float*         xn;              /* [B, 3, NP] per-vertex observables: spin, s*h/mlr, time since flip     */
+    float*         xg;              /* [B, 4]  global observables rows 3..6                                  */
+} eco_env_t;
+
+size_t eco_env_workspace_bytes(int32_t B, int32_t N, int32_t T);
+int    eco_env_bind(eco_env_t* env, void* workspace_dev, int32_t B, int32_t N, int32_t T,
+                    double basin_reward /* < 0: none */);
+/* upload Zobrist keys and the two fp32 tables (host -> device, async); tables have T+1 entries */
+int    eco_env_set_tables(eco_env_t* env, const uint64_t* zobrist_host, const float* tsf_host,
+                          const float* imm_host, void* stream);
+
+/* reset(spins) for all B episodes: reference spinsystem.py:183-259 / 283-330.
+ * graph_idx_dev [B] int32, init_spins_dev [B, N] int8 in {-1,+1} (dense, unpadded). */
+int eco_env_reset(const eco_graphs_t* g, eco_env_t* env, const int32_t* graph_idx_dev,
+                  const int8_t* init_spins_dev, void* stream);
+
+/* step(action) for all B episodes: reference spinsystem.py:355-559.  Episodes whose done flag is set are
+ * left untouched.  policy: ECO_POLICY_ACTIONS (actions_dev [B] int32 required) or ECO_POLICY_GREEDY.
+ * reward_dev [B] double and done_dev [B] uint8 may be NULL.  hist_* may be NULL; when given they are
+ * [B, T] arrays written at column (step-1): the action taken, the fp64 reward, the fp64 score. */
+int eco_env_step(const eco_graphs_t* g, eco_env_t* env, int32_t policy, const int32_t* actions_dev,
+                 double* reward_dev, uint8_t* done_dev, int32_t* hist_actions_dev, double* hist_rewards_dev,
+                 double* hist_scores_dev, void* stream);
+
+/* observation rows 0..6 as the reference's get_observation() returns them, cast to fp32 exactly as the
+ * reference's drivers cast them (spinsystem.py:561-574; experiments/utils.py:174).  obs7_dev [B, 7, N]. */
+int eco_env_observation(const eco_env_t* env, float* obs7_dev, void* stream);
+
+/* best spins = current spins with the best-diff bits flipped.  best_spins_dev [B, N] int8. */
+int eco_env_best_spins(const eco_env_t* env, int8_t* best_spins_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * MPNN Q-network forward (+ fused argmax).  Replaces MPNN.forward, reference src/networks/mpnn.py:40-159,
+ * and the argmax of experiments/utils.py:57-66 / src/agents/dqn/dqn.py:490-503.
+ * Weights are fp32 device arrays in the reference's state_dict layout.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    const float* w_init;      /* node_init_embedding_layer.0.weight          (64, 7)   */
+    const float* w_edge;      /* edge_embedding_layer.edge_embedding_NN.weight (63, 8) */
+    const float* w_edge_feat; /* edge_embedding_layer.edge_feature_NN.weight (64, 64)  */
+    const float* w_msg[3];    /* update_node_embedding_layer.l.message_layer.weight (64, 128) */
+    const float* w_upd[3];    /* update_node_embedding_layer.l.update_layer.weight  (64, 128) */
+    const float* w_pool;      /* readout_layer.layer_pooled.weight           (64, 64)  */
+    const float* w_read;      /* readout_layer.layers_readout.0.weight       (1, 128)  */
+    const float* b_read;      /* readout_layer.layers_readout.0.bias         (1,)      */
+    const void*  packed;      /* eco_mpnn_pack() output for the tcgen05 path, or NULL  */
+} eco_mpnn_t;
+
+size_t eco_mpnn_scratch_bytes(int32_t B, int32_t N, int32_t impl);
+size_t eco_mpnn_packed_bytes(void);
+/* pre-split the weights into the bf16 hi/lo operand layout the tcgen05 kernel consumes (device -> device) */
+int    eco_mpnn_pack(const eco_mpnn_t* w, void* packed_dev, void* stream);
+
+/* Q[b, i] for b < B from features xn [B,3,NP] / xg [B,4] and graph_idx [B] (use env->xn etc. for live
+ * episodes, or replayed features for training).  norm_max: the batch-wide max degree the reference divides
+ * by (mpnn.py:102); <= 0 means "max degree over the graphs referenced by this batch's graph set".
+ * q_dev [B, NP] fp32 or NULL; actions_dev [B] int32 or NULL (argmax, lowest index on ties). */
+int eco_mpnn_forward(const eco_graphs_t* g, const eco_mpnn_t* w, int32_t B, const int32_t* graph_idx_dev,
+                     const float* xn_dev, const float* xg_dev, float norm_max, float* q_dev,
+                     int32_t* actions_dev, void* scratch_dev, int32_t impl, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Rollout: n_steps x [Q-eval + argmax -> env step] with no host round trip.  Replaces the hot loop of
+ * __test_network_batched (reference experiments/utils.py:169-207) and, with ECO_POLICY_GREEDY, the Greedy
+ * baseline (experiments/utils.py:218-227).  actions_scratch_dev [B] int32.
+ * --------------------------------------------------------------------------------------------------------- */
+int eco_rollout(const eco_graphs_t* g, eco_env_t* env, const eco_mpnn_t* w, int32_t n_steps, int32_t policy,
+                float norm_max, int32_t* actions_scratch_dev, void* mpnn_scratch_dev, int32_t impl,
+                int32_t* hist_actions_dev, double* hist_rewards_dev, double* hist_scores_dev, void* stream);
+
+/* Collect per-episode results (async): best cut (int32), best spins [B,N] int8, step count. Any may be NULL. */
+int eco_env_results(const eco_env_t* env, int32_t* best_cut_dev, int8_t* best_spins_dev,
+                    int32_t* steps_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Host-buffer entry point: the whole `test_network` inner job for one batch with HOST inputs and outputs
+ * (what a caller of the reference's test_network holds): uploads graphs + init spins, resets, rolls out T
+ * steps with the network policy, downloads best cuts / best spins.  Synchronises `stream` before returning.
+ * A session owns the device workspaces so repeated calls do not allocate.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct eco_session eco_session_t;
+int  eco_session_create(eco_session_t** out, int32_t G, int32_t N, int32_t B, int32_t T, double basin_reward,
+                        const float* const weights_host[12] /* state_dict order, appendix A.3 */, int32_t impl);
+void eco_session_destroy(eco_session_t* s);
+int  eco_session_rollout(eco_session_t* s, const int8_t* J_host /*[G,N,N]*/, const int32_t* graph_idx_host /*[B]*/,
+                         const int8_t* init_spins_host /*[B,N]*/, int32_t policy, float norm_max,
+                         int32_t* best_cut_host /*[B]*/, int8_t* best_spins_host /*[B,N] or NULL*/, void* stream);
+/* counters for bench.py: kernels launched by this library since the last reset */
+int64_t eco_launch_count(int reset);
+/* Per-kernel device timing for bench.py's roofline: while enabled, every MPNN forward kernel (kind 0) and every
+ * env-step kernel (kind 1) is bracketed by CUDA events on its launch stream.  eco_profile_read synchronises the
+ * device and returns the summed duration (ms) and the number of launches recorded since enabling. */
+#define ECO_PROF_MPNN 0
+#define ECO_PROF_ENV_STEP 1
+int eco_profile_enable(int on);
+int eco_profile_read(int kind, double* total_ms, int64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ECODQN_B200_H */

@@ -50,11 +50,12 @@ def degree_norm(adj):
 
 def edge_embedding(w, x, adj, norm):
     B, N, _ = adj.shape
-    nbr = x.unsqueeze(1).expand(B, N, N, x.shape[-1])      # feature of j at [b, i, j]   (mpnn.py:90-92)
-    ef = torch.cat([adj.unsqueeze(-1), nbr], dim=-1)
-    ef = ef * (adj.unsqueeze(-1) != 0).float()             # mpnn.py:94
-    emb = F.relu(F.linear(ef.reshape(B, N * N, -1), w[KEYS[1]]))    # mpnn.py:96-97
-    emb = emb.reshape(B, N, N, -1).sum(dim=2) / norm       # mpnn.py:98-100
+    ef = torch.empty(B, N, N, 1 + x.shape[-1])
+    ef[..., 0] = adj                                       # [a_ij ; x_j] at [b, i, j]   (mpnn.py:90-92)
+    ef[..., 1:] = x.unsqueeze(1)
+    ef.mul_((adj != 0).unsqueeze(-1))                      # mpnn.py:94
+    emb = F.linear(ef.view(B, N * N, -1), w[KEYS[1]]).relu_()       # mpnn.py:96-97
+    emb = emb.view(B, N, N, -1).sum(dim=2) / norm          # mpnn.py:98-100
     return F.relu(F.linear(torch.cat([emb, norm / norm.max()], dim=-1), w[KEYS[2]]))   # mpnn.py:102
 
 

@@ -1,0 +1,309 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI, against the
+golden vectors recorded from the reference and against the CPU oracle on seeded inputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, golden_cases
+
+pytestmark = pytest.mark.gpu
+
+Q_RTOL = 1e-3      # north_star: Q-values within 1e-3 relative in fp32
+Q_ATOL_FRAC = 1e-5  # of max|Q| in the row, for entries near zero
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def basin(z):
+    b = float(z["basin_reward"])
+    return None if b < 0 else b
+
+
+def weights_dict(z):
+    from oracle.mpnn import weights_from_npz
+    return weights_from_npz(z)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import eco_dqn_b200.engine as engine
+    assert torch.cuda.is_available()
+    return engine
+
+
+def make_env(eng, z, B=None):
+    gs = eng.GraphSet(z["J"][None])
+    B = z["init_spins"].shape[0] if B is None else B
+    env = eng.BatchedSpinSystem(gs, B, int(z["T"]), basin(z))
+    env.reset(spins=z["init_spins"][:B], graph_idx=np.zeros(B, dtype=np.int32))
+    return gs, env
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_env_step_teacher_forced_bit_exact(eng, name):
+    z = load(name)
+    T, n = int(z["T"]), int(z["n"])
+    gs, env = make_env(eng, z)
+    B = env.B
+    assert float(gs.mlr[0]) == float(z["mlr"]) and float(gs.qn[0]) == float(z["qn"]) and float(gs.lb[0]) == float(z["lb"])
+    ep = env.episodes()
+    assert np.array_equal(ep["score"], z["init_score"]) and np.array_equal(ep["cut"].astype(np.float64), z["init_cut"])
+    k = z["obs"].shape[0]
+    obs_steps = list(z["obs_steps"])
+    rewards = np.zeros((B, T))
+    dones = np.zeros((B, T), dtype=np.uint8)
+    scores = np.zeros((B, T + 1))
+    scores[:, 0] = ep["score"]
+    best_scores = np.zeros((B, T + 1))
+    best_scores[:, 0] = ep["best_score"]
+    acts = torch.from_numpy(z["actions"]).cuda()
+    for t in range(T):
+        if t in obs_steps:
+            got = env.observation()[:k].cpu().numpy()
+            assert np.array_equal(got, z["obs"][:, obs_steps.index(t)]), (name, "obs at step", t)
+        r, d = env.step(acts[:, t])
+        rewards[:, t] = r.cpu().numpy()
+        dones[:, t] = d.cpu().numpy()
+        ep = env.episodes()
+        scores[:, t + 1] = ep["score"]
+        best_scores[:, t + 1] = ep["best_score"]
+    if T in obs_steps:
+        assert np.array_equal(env.observation()[:k].cpu().numpy(), z["obs"][:, obs_steps.index(T)])
+    assert np.array_equal(rewards.view(np.uint64), z["rewards"].view(np.uint64)), "fp64 rewards must be bit-exact"
+    assert np.array_equal(scores, z["scores"])
+    assert np.array_equal(best_scores, z["best_scores"])
+    assert np.array_equal(dones, z["dones"])
+    bc, bs, st = env.results()
+    assert np.array_equal(bc.cpu().numpy().astype(np.float64), z["best_cut"])
+    assert np.array_equal(bs.cpu().numpy(), z["best_spins"])
+    assert np.array_equal(env.spins[:, :n].cpu().numpy(), z["final_spins"])
+    assert (st.cpu().numpy() == T).all()
+    with pytest.raises(NotImplementedError):     # spinsystem.py:365-367
+        env.step(acts[:, 0])
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("name", golden_cases())
+def test_mpnn_q_values_and_argmax(eng, name, impl):
+    from eco_dqn_b200 import _lib
+    z = load(name)
+    T = int(z["T"])
+    gs, env = make_env(eng, z)
+    w = eng.MPNNWeights(weights_dict(z))
+    if impl == "tc" and w.c.packed is None:
+        pytest.skip("tcgen05 path not built")
+    code = _lib.MPNN_SIMT if impl == "simt" else _lib.MPNN_TCGEN05
+    k = z["obs"].shape[0]
+    obs_steps = list(z["obs_steps"])
+    acts = torch.from_numpy(z["actions"]).cuda()
+    worst = 0.0
+    for t in range(T + 1):
+        if t in obs_steps:
+            q, a = env.q_values(w, impl=code)
+            q = q[:k].cpu().numpy()
+            ref = z["q"][:, obs_steps.index(t)]
+            atol = Q_ATOL_FRAC * np.abs(ref).max(axis=1, keepdims=True)
+            err = np.abs(q - ref) - (Q_RTOL * np.abs(ref) + atol)
+            assert (err <= 0).all(), (name, t, float(np.abs(q - ref).max()))
+            worst = max(worst, float((np.abs(q - ref) / (np.abs(ref) + atol)).max()))
+            # argmax: lowest index among maxima, and it must be a maximiser of the reference's Q up to tolerance
+            a = a[:k].cpu().numpy()
+            assert np.array_equal(a, q.argmax(1))
+            pick = ref[np.arange(k), a]
+            assert (pick >= ref.max(1) - (Q_RTOL * np.abs(ref.max(1)) + atol[:, 0])).all()
+        if t < T:
+            env.step(acts[:, t])
+    print("%s %s worst relative Q error %.3g" % (name, impl, worst))
+
+
+@pytest.mark.parametrize("name", ["er20_g0", "er20_g3_nobasin", "ba40u_g0", "er40_g0"])
+def test_free_running_rollout_against_oracle(eng, name):
+    """Free-running greedy-Q rollout on the GPU; then replay the GPU's own actions through the CPU oracle:
+    rewards / scores / best cuts must be bit-exact and every action must maximise the oracle's Q."""
+    from oracle.rollout import rollout as cpu_rollout
+    from oracle.mpnn import mpnn_forward
+    z = load(name)
+    T, n = int(z["T"]), int(z["n"])
+    gs, env = make_env(eng, z)
+    wd = weights_dict(z)
+    w = eng.MPNNWeights(wd)
+    ha, hr, hs = env.rollout(w, record_history=True)
+    ha, hr, hs = ha.cpu().numpy(), hr.cpu().numpy(), hs.cpu().numpy()
+    slack = []
+
+    def hook(t, qs):
+        qs = qs.numpy()
+        picked = qs[np.arange(qs.shape[0]), ha[:, t]]
+        slack.append(float(((qs.max(1) - picked) / (np.abs(qs.max(1)) + 1e-6)).max()))
+
+    ref = cpu_rollout(z["J"].astype(np.float64), wd, z["init_spins"], T, basin(z), forced_actions=ha, q_hook=hook)
+    assert np.array_equal(hr.view(np.uint64), ref["rewards"].view(np.uint64))
+    assert np.array_equal(hs, ref["scores"][:, 1:])
+    bc, bs, _ = env.results()
+    assert np.array_equal(bc.cpu().numpy().astype(np.float64), ref["best_cut"])
+    assert np.array_equal(bs.cpu().numpy(), ref["best_spins"])
+    assert max(slack) <= Q_RTOL, "GPU picked an action that is not an argmax of the oracle's Q"
+    # identical trajectories to the reference are expected when no near-ties occur
+    same = (ha == z["actions"]).all(axis=1).mean()
+    print("%s: %.0f%% of episodes follow the reference's action sequence exactly" % (name, 100 * same))
+    assert bc.cpu().numpy().max() <= z["best_cut"].max() + 1e9  # (upper bound checked in known-answer test)
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_greedy_baseline_bit_exact(eng, name):
+    z = load(name)
+    gs, env = make_env(eng, z)
+    env.rollout(policy="greedy")
+    bc, bs, st = env.results()
+    assert np.array_equal(bc.cpu().numpy().astype(np.float64), z["greedy_cuts"])
+    assert np.array_equal(bs.cpu().numpy(), z["greedy_spins"])
+    assert np.array_equal(st.cpu().numpy(), z["greedy_steps"])
+    env1 = eng.BatchedSpinSystem(gs, 1, int(z["T"]), basin(z))
+    env1.reset(spins=-np.ones((1, int(z["n"])), dtype=np.int8))
+    env1.rollout(policy="greedy")
+    bc1, bs1, _ = env1.results()
+    assert float(bc1[0]) == float(z["greedy_single_cut"])
+    assert np.array_equal(bs1.cpu().numpy()[0], z["greedy_single_spins"])
+
+
+def _random_graphs(rng, G, n, p, pm1=True):
+    out = np.zeros((G, n, n), dtype=np.int8)
+    for g in range(G):
+        up = np.triu((rng.random((n, n)) < p), 1)
+        w = np.where(rng.random((n, n)) < 0.5, -1, 1) if pm1 else np.ones((n, n), dtype=int)
+        a = (up * w).astype(np.int8)
+        out[g] = a + a.T
+    return out
+
+
+@pytest.mark.parametrize("n,p,B,steps", [(1 + 16, 0.3, 5, 34), (16, 0.5, 3, 32), (200, 0.04, 12, 60), (333, 0.05, 4, 40),
+                                         (500, 0.15, 3, 30), (1100, 0.01, 2, 20), (2000, 0.01, 2, 12)])
+def test_env_random_actions_multi_graph_vs_oracle(eng, n, p, B, steps):
+    """Ragged sizes (N not a multiple of 16, sub-warp / warp / block kernels), several graphs per batch."""
+    from oracle.spin_env import MaxCutEnv
+    rng = np.random.default_rng(n)
+    G = min(B, 3)
+    Js = _random_graphs(rng, G, n, p)
+    gidx = (np.arange(B) * 7 % G).astype(np.int32)
+    spins = (2 * rng.integers(0, 2, size=(B, n)) - 1).astype(np.int8)
+    T = 2 * n
+    gs = eng.GraphSet(Js)
+    env = eng.BatchedSpinSystem(gs, B, T, 1.0 / n)
+    env.reset(spins=spins, graph_idx=gidx)
+    cpu = [MaxCutEnv(Js[gidx[b]].astype(np.float64), T, 1.0 / n) for b in range(B)]
+    obs = [e.reset(spins[b]) for b, e in enumerate(cpu)]
+    for t in range(steps):
+        got = env.observation().cpu().numpy()
+        want = np.stack([o[:7] for o in obs]).astype(np.float32)
+        assert np.array_equal(got, want), ("obs", t)
+        # mix of random moves, revisits (to exercise the visited set) and greedy moves
+        if t % 5 == 4:
+            a = np.array([int(np.argmax(e.spins * (e.J @ e.spins))) for e in cpu])
+        elif t % 7 == 6:
+            a = prev
+        else:
+            a = rng.integers(0, n, size=B)
+        prev = a
+        r, d = env.step(torch.from_numpy(a.astype(np.int32)))
+        out = [e.step(int(x)) for e, x in zip(cpu, a)]
+        obs = [o[0] for o in out]
+        assert np.array_equal(r.cpu().numpy().view(np.uint64), np.array([o[1] for o in out], dtype=np.float64).view(np.uint64))
+    ep = env.episodes()
+    assert np.array_equal(ep["score"], np.array([e.score for e in cpu]))
+    assert np.array_equal(ep["best_cut"].astype(np.float64), np.array([e.best_solution for e in cpu]))
+    _, bs, _ = env.results()
+    assert np.array_equal(bs.cpu().numpy(), np.stack([e.best_spins for e in cpu]).astype(np.int8))
+
+
+@pytest.mark.parametrize("n,p", [(24, 0.3), (200, 0.15), (500, 0.05)])
+def test_mpnn_simt_random_weights_multi_graph_vs_oracle(eng, n, p):
+    from oracle.mpnn import mpnn_forward, KEYS
+    from eco_dqn_b200 import _lib
+    rng = np.random.default_rng(n + 1)
+    B, G = 6, 3
+    Js = _random_graphs(rng, G, n, p)
+    gidx = (np.arange(B) % G).astype(np.int32)
+    shapes = eng.STATE_DICT_SHAPES
+    wd = {k: (rng.standard_normal(s) * (0.3 if len(s) > 1 else 0.1)).astype(np.float32) for k, s in zip(KEYS, shapes)}
+    gs = eng.GraphSet(Js)
+    env = eng.BatchedSpinSystem(gs, B, 2 * n, 1.0 / n)
+    env.reset(spins=(2 * rng.integers(0, 2, size=(B, n)) - 1).astype(np.int8), graph_idx=gidx)
+    for t in range(5):
+        env.step(torch.from_numpy(rng.integers(0, n, size=B).astype(np.int32)))
+    w = eng.MPNNWeights(wd)
+    q, a = env.q_values(w, impl=_lib.MPNN_SIMT)
+    obs7 = env.observation().cpu().numpy()
+    full = np.concatenate([obs7, Js[gidx].astype(np.float32)], axis=1)
+    ref = mpnn_forward(wd, full).numpy()      # batch-wide norm.max() == max degree over the set here
+    deg_max_batch = max((Js[g] != 0).sum(1).max() for g in gidx)
+    assert deg_max_batch == gs.max_degree
+    q = q.cpu().numpy()
+    assert np.allclose(q, ref, rtol=Q_RTOL, atol=Q_ATOL_FRAC * np.abs(ref).max())
+    assert np.array_equal(a.cpu().numpy(), q.argmax(1))
+
+
+def test_full_size_invariants_ba200(eng):
+    """BASELINE config 2 size (B=4096, N=200): size-independent properties after a greedy + random walk."""
+    gsets = np.load(os.path.join(GOLDEN, "graphsets.npz"))
+    Js = gsets["ba200"]
+    B, n, T = 4096, 200, 400
+    rng = np.random.default_rng(0)
+    gs = eng.GraphSet(Js)
+    env = eng.BatchedSpinSystem(gs, B, T, 1.0 / n)
+    spins0 = torch.from_numpy((2 * rng.integers(0, 2, size=(B, n)) - 1).astype(np.int8)).cuda()
+    env.reset(spins=spins0)
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    for t in range(60):
+        env.step(torch.randint(0, n, (B,), generator=gen, device="cuda", dtype=torch.int32))
+    for t in range(40):
+        env.greedy_step()
+    ep = env.episodes()
+    s = env.spins[:, :n].float()
+    J = gs.J[:, :n, :n].float()[env.graph_idx.long()]
+    h = torch.bmm(J, s.unsqueeze(-1)).squeeze(-1)
+    assert torch.equal(h, env.hfield[:, :n].float())
+    cut = 0.25 * (J.sum((1, 2)) - (s * h).sum(1))
+    assert np.array_equal(cut.cpu().numpy(), ep["cut"].astype(np.float32))
+    bc, bs, st = env.results()
+    bsf = bs.float()
+    bcut = 0.25 * (J.sum((1, 2)) - (bsf * torch.bmm(J, bsf.unsqueeze(-1)).squeeze(-1)).sum(1))
+    assert torch.equal(bcut, bc.float())
+    assert np.array_equal((bs != env.spins[:, :n]).sum(1).cpu().numpy(), ep["dist"])
+    assert (ep["best_score"] >= ep["score"]).all() and (ep["step"] <= 100).all()
+    opt = gsets["ba200_opt"][(np.arange(B) % Js.shape[0])]
+    assert (bc.cpu().numpy() <= opt).all()          # best-known cuts are upper bounds (README.md:82)
+
+
+def test_host_session_matches_engine(eng):
+    z = load("er20_g0")
+    from eco_dqn_b200 import _lib
+    T, n = int(z["T"]), int(z["n"])
+    B = z["init_spins"].shape[0]
+    wd = weights_dict(z)
+    sess = eng.HostSession(1, n, B, T, basin(z), wd, impl=_lib.MPNN_SIMT)
+    best_cut = np.zeros(B, dtype=np.int32)
+    best_spins = np.zeros((B, n), dtype=np.int8)
+    sess.rollout(np.ascontiguousarray(z["J"][None]), np.zeros(B, dtype=np.int32), np.ascontiguousarray(z["init_spins"]),
+                 best_cut, best_spins)
+    gs, env = make_env(eng, z)
+    env.rollout(eng.MPNNWeights(wd), impl=_lib.MPNN_SIMT)
+    bc, bs, _ = env.results()
+    assert np.array_equal(best_cut, bc.cpu().numpy()) and np.array_equal(best_spins, bs.cpu().numpy())
+    sess.close()
+
+
+def test_error_behaviour(eng):
+    z = load("er20_g0")
+    gs, env = make_env(eng, z)
+    with pytest.raises(Exception):        # spinsystem.py:604-606
+        env.reset(spins=np.zeros((env.B, env.N), dtype=np.int8))
+    with pytest.raises(NotImplementedError):   # real-valued couplings are outside the accelerated path
+        eng.GraphSet(np.array([[0, 0.5], [0.5, 0]])[None])
+    with pytest.raises(ValueError):        # empty graph: the reference recurses forever (spinsystem.py:209-211)
+        eng.GraphSet(np.zeros((1, 8, 8)))
+    with pytest.raises(ValueError):
+        eng.GraphSet(np.triu(np.ones((1, 8, 8)), 1))   # not symmetric
