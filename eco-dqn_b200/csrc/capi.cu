@@ -339,6 +339,7 @@ struct eco_session {
     eco_env_t env;
     eco_mpnn_t w;
     void *ws_graphs = nullptr, *ws_env = nullptr, *ws_w = nullptr, *ws_scratch = nullptr, *ws_io = nullptr;
+    void* packed_buf = nullptr;
     int8_t *d_Jdense, *d_spins, *d_best_spins;
     int32_t *d_gidx, *d_act, *d_best_cut;
 };
@@ -402,12 +403,7 @@ int eco_session_create(eco_session_t** out, int32_t G, int32_t N, int32_t B, int
     for (int l = 0; l < 3; ++l) { s->w.w_msg[l] = ptrs[3 + 2 * l]; s->w.w_upd[l] = ptrs[4 + 2 * l]; }
     s->w.w_pool = ptrs[9]; s->w.w_read = ptrs[10]; s->w.b_read = ptrs[11];
     s->w.packed = nullptr;
-    if (impl != ECO_MPNN_SIMT && eco_mpnn_packed_bytes() > 0 && mpnn_tc_supported(&s->graphs)) {
-        void* packed = (void*)(((uintptr_t)wd + 255) & ~(uintptr_t)255);
-        rc = eco_mpnn_pack(&s->w, packed, nullptr);
-        if (rc) { eco_session_destroy(s); return rc; }
-        s->w.packed = packed;
-    }
+    s->packed_buf = (void*)(((uintptr_t)wd + 255) & ~(uintptr_t)255);
 
     // tables: Zobrist keys (splitmix64), time-since-flip and immanency tables in the reference's fp64 arithmetic
     std::vector<uint64_t> zob((size_t)s->env.NP * 2);
@@ -447,6 +443,20 @@ int eco_session_rollout(eco_session_t* s, const int8_t* J_host, const int32_t* g
         ECO_CUDA(cudaMemcpyAsync(s->d_Jdense, J_host, (size_t)s->G * s->N * s->N, cudaMemcpyHostToDevice, st));
         rc = eco_graphs_load_dev(&s->graphs, s->d_Jdense, stream);
         if (rc) return rc;
+        // graph flags decide whether the tcgen05 path (couplings in {-1,0,1}) may be used
+        std::vector<int32_t> stat((size_t)s->G * 4);
+        ECO_CUDA(cudaMemcpyAsync(stat.data(), s->graphs.gstat, stat.size() * 4, cudaMemcpyDeviceToHost, st));
+        ECO_CUDA(cudaStreamSynchronize(st));
+        int flags = 0;
+        for (int i = 0; i < s->G; ++i) flags |= stat[(size_t)i * 4 + 3];
+        ECO_CHECK_ARG(!(flags & 6), ECO_ERR_INVALID,
+                      "eco_session_rollout: a graph is not symmetric with zero diagonal, or has no non-zero degree");
+        s->graphs.reserved = (flags & 1) ? 0 : 1;
+        if (s->impl != ECO_MPNN_SIMT && !s->w.packed && eco_mpnn_packed_bytes() > 0) {
+            rc = eco_mpnn_pack(&s->w, s->packed_buf, stream);
+            if (rc) return rc;
+            s->w.packed = s->packed_buf;
+        }
     }
     ECO_CUDA(cudaMemcpyAsync(s->d_gidx, gidx_host, (size_t)s->B * 4, cudaMemcpyHostToDevice, st));
     ECO_CUDA(cudaMemcpyAsync(s->d_spins, spins_host, (size_t)s->B * s->N, cudaMemcpyHostToDevice, st));

@@ -118,12 +118,15 @@ env_step_kernel(const eco_graphs_t g, const eco_env_t env, const int policy, con
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const int i = c * 8 + k;
-                if (i < N) best = max(best, ((s.b[k] * h.h[k] + 32768) << 16) | (0xFFFF - i));
+                // key = (gain + 32768) : (65535 - i) as an unsigned pair, biased so that signed max orders it
+                if (i < N)
+                    best = max(best, (int)((((uint32_t)(s.b[k] * h.h[k] + 32768) << 16) | (uint32_t)(0xFFFF - i)) ^ 0x80000000u));
             }
         }
         best = G::maxv(best, sm);
-        a = 0xFFFF - (best & 0xFFFF);
-        if (active && ((best >> 16) - 32768) < 0) {  // solver.py:124: stop only if the best gain is < 0
+        const uint32_t ukey = (uint32_t)best ^ 0x80000000u;
+        a = 0xFFFF - (int)(ukey & 0xFFFFu);
+        if (active && ((int)(ukey >> 16) - 32768) < 0) {  // solver.py:124: stop only if the best gain is < 0
             active = false;
             if (lane == 0) ep->flags = flags | FLAG_STOPPED;
         }

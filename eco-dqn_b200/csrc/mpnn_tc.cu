@@ -1,17 +1,541 @@
-// Kernel family 2b placeholder: tcgen05 MPNN forward (filled in by the next milestone).
+// Kernel family 2b: MPNN Q-network forward + argmax on the 5th-gen tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// Replaces (reference, file:line) src/networks/mpnn.py:40-159 (MPNN.forward and its three layer classes) and
+// the argmax of experiments/utils.py:57-66, for graphs with couplings in {-1,0,+1} and N <= 208.
+//
+// One persistent CTA per SM runs whole episodes; every activation stays on chip between the layers:
+//
+//   orientation   D^T[feature, vertex] = W[feature, k] * X^T[k, vertex]   (linears:   A-operand = weights, TMEM)
+//                 D^T[feature, vertex] = H^T[feature, j] * A[j, vertex]   (aggregate: B-operand = adjacency, smem)
+//   precision     fp32-accurate on bf16 tensor cores: every activation / weight x is stored as hi = bf16(x),
+//                 lo = bf16(x - hi).  hi and lo rows are STACKED in the M dimension (128 = 64 features x {hi,lo}),
+//                 so one M=128 MMA chain yields both partial products and the split costs no extra instructions for
+//                 the aggregation (A in {-1,0,1} is exact) and 2 chains (4 products) for the linears.
+//                 Stacked row order r = 32q + 16s + t  <->  feature 16q + t, s in {hi, lo}: the two halves of a
+//                 feature sit in the same TMEM lane quadrant, so one warp adds them after two 16x256b loads.
+//   smem          adjacency bf16 (N x N, K-major core matrices), H^T and E^T stacked hi/lo (one copy serves as
+//                 K-major A-operand of the aggregation AND MN-major B-operand of the linears), one 80-vertex
+//                 chunk buffer.  No swizzle: 8x16-byte core matrices, written conflict-free by the epilogues.
+//   TMEM          cols 0..207 aggregation accumulator, 208..287 linear accumulator, 288.. weight A-operands
+//                 (tcgen05.st from registers, straight from L2); the edge-stage A-operands S = R+ + R-,
+//                 D = R+ - R- live in TMEM too (g = (|A| S + A D) / (2 deg), SURVEY.md section 7 identity).
+//   edge stage    ReLU(W_e [a_ij ; x_j]) = ReLU(a_ij w0 + P_j): two dense N x N contractions instead of the
+//                 reference's [B,N,N,63] intermediate.
+#include <cuda_bf16.h>
+
 #include "eco_common.cuh"
+#include "tc_prims.cuh"
 
 namespace eco {
-bool mpnn_tc_supported(const eco_graphs_t*) { return false; }
-size_t mpnn_tc_scratch_bytes(int, int) { return 0; }
-size_t mpnn_tc_packed_bytes() { return 0; }
-int launch_mpnn_pack(const eco_mpnn_t*, void*, cudaStream_t) {
-    set_error("tcgen05 MPNN path not built");
-    return ECO_ERR_UNSUPPORTED;
+namespace {
+
+using namespace tc;
+
+constexpr int NPMAX = 208;
+constexpr int CHUNK = 80;        // vertices per linear-layer chunk (accumulator columns)
+constexpr int THREADS = 256;
+
+// ---- TMEM column map -------------------------------------------------------------------------------------
+constexpr uint32_t T_ACC0 = 0;       // 208 cols: aggregation / edge accumulator
+constexpr uint32_t T_ACC1 = 208;     // 80 cols: linear accumulator (chunk relative)
+constexpr uint32_t T_WM = 288;       // 64 cols: message weights (128 stacked rows x 128 k, bf16 pairs)
+constexpr uint32_t T_WU = 352;       // 64 cols: update weights
+constexpr uint32_t T_WEF = 416;      // 32 cols: edge-feature weights (k = 64)
+constexpr uint32_t T_S = 208;        // 104 cols: edge-stage A-operand S   (dead before ACC1 / weights are live)
+constexpr uint32_t T_D = 312;        // 104 cols: edge-stage A-operand D
+
+// ---- shared memory map (bytes) -----------------------------------------------------------------------------
+constexpr int SM_A = 0;                                  // adjacency, bf16, up to 208 x 208
+constexpr int SM_H = SM_A + NPMAX * NPMAX * 2;           // H^T stacked [128][208]
+constexpr int SM_E = SM_H + 128 * NPMAX * 2;             // E^T stacked
+constexpr int SM_T = SM_E + 128 * NPMAX * 2;             // chunk buffer [128][80]
+constexpr int SM_ABS = SM_H;                             // |A| overlays H and E during the edge stage
+constexpr int SM_XF = SM_T + 128 * CHUNK * 2;            // float xf[7][208]
+constexpr int SM_DEG = SM_XF + 7 * NPMAX * 4;            // float deg[208]
+constexpr int SM_QP = SM_DEG + NPMAX * 4;                // float qpart[4][208]
+constexpr int SM_PP = SM_QP + 4 * NPMAX * 4;             // float ppart[2][64]
+constexpr int SM_WI = SM_PP + 2 * 64 * 4;                // float w_init[64*7]
+constexpr int SM_WE = SM_WI + 64 * 7 * 4;                // float w_edge[64*8] (row 63 zero)
+constexpr int SM_WR = SM_WE + 64 * 8 * 4;                // float w_read[128]
+constexpr int SM_MISC = SM_WR + 128 * 4;                 // float pooled[64], c0, reductions
+constexpr int SM_TOTAL = SM_MISC + 64 * 4 + 64 + 8 * 8 + 8 * 8;
+static_assert(NPMAX * NPMAX * 2 <= 2 * 128 * NPMAX * 2, "|A| must fit in the H+E region");
+static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
+
+// packed weights (uint32 words): [128 stacked rows][k/2] per matrix
+constexpr int PK_WEF = 0;                    // 128 x 32
+constexpr int PK_WM = PK_WEF + 128 * 32;     // 3 x 128 x 64
+constexpr int PK_WU = PK_WM + 3 * 128 * 64;  // 3 x 128 x 64
+constexpr int PK_WORDS = PK_WU + 3 * 128 * 64;
+
+__device__ __forceinline__ uint16_t bf16_bits(float x) { return __bfloat16_as_ushort(__float2bfloat16_rn(x)); }
+
+__global__ void mpnn_pack_kernel(const eco_mpnn_t w, uint32_t* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= PK_WORDS) return;
+    const float* src;
+    int kw, rel;   // words per row, index within the matrix
+    if (idx < PK_WM) { src = w.w_edge_feat; kw = 32; rel = idx; }
+    else if (idx < PK_WU) { const int l = (idx - PK_WM) / (128 * 64); src = w.w_msg[l]; kw = 64; rel = (idx - PK_WM) % (128 * 64); }
+    else { const int l = (idx - PK_WU) / (128 * 64); src = w.w_upd[l]; kw = 64; rel = (idx - PK_WU) % (128 * 64); }
+    const int r = rel / kw, c = rel % kw;
+    const int f = 16 * (r >> 5) + (r & 15), s = (r >> 4) & 1;
+    const float a = src[f * (2 * kw) + 2 * c], b = src[f * (2 * kw) + 2 * c + 1];
+    uint32_t hi, lo;
+    split2(a, b, hi, lo);
+    out[idx] = s ? lo : hi;
 }
-int launch_mpnn_tc(const eco_graphs_t*, const eco_mpnn_t*, int, const int32_t*, const float*, const float*, float,
-                   float*, int32_t*, void*, cudaStream_t) {
-    set_error("tcgen05 MPNN path not built");
-    return ECO_ERR_UNSUPPORTED;
+
+struct Ctx {
+    unsigned char* smem;
+    uint32_t tmem;
+    uint64_t* bar;
+    uint32_t phase;
+    int tid, warp, lane, q, hw;
+    int N, NP, NB;
+};
+
+__device__ __forceinline__ void stage_sync() {   // operands written (smem via generic proxy, TMEM via tcgen05.st / ld done)
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
 }
+__device__ __forceinline__ void wait_mma(Ctx& c) {
+    mbar_wait(c.bar, c.phase);
+    c.phase ^= 1;
+    tc_fence_after();
+}
+
+// weights: global packed [128][KW] words -> TMEM columns [tcol, tcol + KW); the two warps of a quadrant split the columns
+template <int KW>
+__device__ __forceinline__ void load_weights_tmem(const Ctx& c, const uint32_t* __restrict__ pk, uint32_t tcol) {
+    const int r = 32 * c.q + c.lane;
+    const uint4* src = reinterpret_cast<const uint4*>(pk + (size_t)r * KW + c.hw * (KW / 2));
+#pragma unroll
+    for (int i = 0; i < KW / 16; ++i) {
+        const uint4 a = src[2 * i], b = src[2 * i + 1];
+        const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        tmem_st_32x32b_x8(tmem_addr(c.tmem, 32 * c.q, tcol + c.hw * (KW / 2) + 8 * i), v);
+    }
+}
+
+// Generic epilogue over accumulator columns [col0, col0 + width) of `acc` (width % 16 == 0).  For every 16-column
+// block the warp owns, loads the hi-row and lo-row halves of its quadrant, adds them and calls
+//   fn(blk_col /*first column of the block, relative to col0*/, v[8])
+// where v[i] belongs to feature 16q + lane/4 + 8*((i>>1)&1) and column blk_col + 8*(i>>2) + 2*(lane&3) + (i&1).
+template <class Fn>
+__device__ __forceinline__ void epilogue(const Ctx& c, uint32_t acc, int col0, int width, Fn fn) {
+    for (int blk = c.hw; blk < width / 16; blk += 2) {
+        uint32_t vh[8], vl[8];
+        tmem_ld_16x256b_x2(tmem_addr(c.tmem, 32 * c.q, acc + col0 + 16 * blk), vh);
+        tmem_ld_16x256b_x2(tmem_addr(c.tmem, 32 * c.q + 16, acc + col0 + 16 * blk), vl);
+        tmem_ld_wait();
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(vh[i]) + __uint_as_float(vl[i]);
+        fn(16 * blk, v);
+    }
+}
+
+// Store the 8 epilogue values of a 16-column block into a stacked hi/lo buffer (core(rb, cb) at (cb*16 + rb)*128).
+// `node0` = buffer-relative vertex index of the block's first column.
+__device__ __forceinline__ void store_block(const Ctx& c, unsigned char* buf, int node0, const float (&v)[8]) {
+    const int rowoff = 16 * (c.lane >> 2) + 4 * (c.lane & 3);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {          // columns +0 / +8
+        const int cb = (node0 >> 3) + half;
+#pragma unroll
+        for (int fr = 0; fr < 2; ++fr) {            // feature rows lane/4 and lane/4 + 8
+            uint32_t hi, lo;
+            split2(v[4 * half + 2 * fr], v[4 * half + 2 * fr + 1], hi, lo);
+            unsigned char* p = buf + ((cb * 16 + 4 * c.q + fr) * 128) + rowoff;
+            *reinterpret_cast<uint32_t*>(p) = hi;             // rb = 4q + fr      (hi rows)
+            *reinterpret_cast<uint32_t*>(p + 2 * 128) = lo;   // rb = 4q + 2 + fr  (lo rows)
+        }
+    }
+}
+
+// B-operand descriptor of a stacked buffer used MN-major: k-step kq (features 16kq..16kq+15), split s, first vertex group cb0
+__device__ __forceinline__ uint64_t bdesc_stacked(const unsigned char* buf, int cb0, int kq, int s) {
+    return smem_desc(smem_u32(buf) + (cb0 * 16 + 4 * kq + 2 * s) * 128, /*LBO (k groups)*/ 128, /*SBO (vertex groups)*/ 2048);
+}
+
+// One linear layer on a chunk: acc1 = W[:, 0:64] * X0 + W[:, 64:128] * X1 (X1 optional), X given as stacked buffers.
+__device__ __forceinline__ void issue_linear(const Ctx& c, uint32_t tw, const unsigned char* x0, int cb0_0,
+                                             const unsigned char* x1, int cb0_1, int width) {
+    const uint32_t idesc = instr_desc_bf16(128, width, false, true);
+    bool acc = false;
+#pragma unroll
+    for (int part = 0; part < 2; ++part) {
+        const unsigned char* x = part ? x1 : x0;
+        if (x == nullptr) continue;
+        const int cb0 = part ? cb0_1 : cb0_0;
+#pragma unroll
+        for (int kq = 0; kq < 4; ++kq)
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                mma_ts(c.tmem + T_ACC1, c.tmem + tw + 32 * part + 8 * kq, bdesc_stacked(x, cb0, kq, s), idesc, acc);
+                acc = true;
+            }
+    }
+    mma_commit(c.bar);
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int32_t* __restrict__ graph_idx,
+               const float* __restrict__ xn, const float* __restrict__ xg, const float norm_max,
+               float* __restrict__ q_out, int32_t* __restrict__ act_out) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t bar_s;
+    __shared__ uint32_t tmem_base_s;
+    Ctx c;
+    c.smem = smem; c.bar = &bar_s; c.phase = 0;
+    c.tid = threadIdx.x; c.warp = c.tid >> 5; c.lane = c.tid & 31; c.q = c.warp & 3; c.hw = c.warp >> 2;
+    c.N = g.N; c.NP = g.NP; c.NB = g.NP >> 3;
+    const int N = c.N, NP = c.NP, NB = c.NB;
+
+    float* xf = reinterpret_cast<float*>(smem + SM_XF);
+    float* sdeg = reinterpret_cast<float*>(smem + SM_DEG);
+    float* qpart = reinterpret_cast<float*>(smem + SM_QP);
+    float* ppart = reinterpret_cast<float*>(smem + SM_PP);
+    float* s_winit = reinterpret_cast<float*>(smem + SM_WI);
+    float* s_wedge = reinterpret_cast<float*>(smem + SM_WE);
+    float* s_wread = reinterpret_cast<float*>(smem + SM_WR);
+    float* pooled = reinterpret_cast<float*>(smem + SM_MISC);
+    float* s_c0 = pooled + 64;
+    float* red_val = pooled + 64 + 16;
+    int* red_idx = reinterpret_cast<int*>(pooled + 64 + 32);
+    unsigned char* sA = smem + SM_A;
+    unsigned char* sAbs = smem + SM_ABS;
+    unsigned char* sH = smem + SM_H;
+    unsigned char* sE = smem + SM_E;
+    unsigned char* sT = smem + SM_T;
+    const uint32_t* pk = reinterpret_cast<const uint32_t*>(w.packed);
+
+    if (c.warp == 0) tmem_alloc(&tmem_base_s, 512);
+    if (c.tid == 0) { mbar_init(&bar_s, 1); fence_mbar_init(); }
+    for (int i = c.tid; i < 64 * 7; i += THREADS) s_winit[i] = w.w_init[i];
+    for (int i = c.tid; i < 64 * 8; i += THREADS) s_wedge[i] = i < 63 * 8 ? w.w_edge[i] : 0.f;
+    for (int i = c.tid; i < 128; i += THREADS) s_wread[i] = w.w_read[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    c.tmem = tmem_base_s;
+    const float dmax = norm_max > 0.f ? norm_max : *g.dmax;
+    const int nsteps_A = NP >> 4;                         // k-steps over vertices
+
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        const int gi = graph_idx[b];
+        const int8_t* A8 = g.J + (size_t)gi * NP * NP;
+
+        // ================= stage 0: operands of the edge contraction ======================================
+        for (int i = c.tid; i < NP; i += THREADS) {
+            const bool ok = i < N;
+            xf[0 * NPMAX + i] = ok ? xn[((size_t)b * 3 + 0) * NP + i] : 0.f;
+            xf[1 * NPMAX + i] = ok ? xn[((size_t)b * 3 + 1) * NP + i] : 0.f;
+            xf[2 * NPMAX + i] = ok ? xn[((size_t)b * 3 + 2) * NP + i] : 0.f;
+            const float4 gl = *reinterpret_cast<const float4*>(xg + (size_t)b * 4);
+            xf[3 * NPMAX + i] = ok ? gl.x : 0.f;
+            xf[4 * NPMAX + i] = ok ? gl.y : 0.f;
+            xf[5 * NPMAX + i] = ok ? gl.z : 0.f;
+            xf[6 * NPMAX + i] = ok ? gl.w : 0.f;
+            sdeg[i] = g.deg[(size_t)gi * NP + i];
+        }
+        // adjacency int8 -> bf16 A and |A| (K-major B operands): a warp converts 8 rows x 64 bytes per pass
+        {
+            const int nch = NP >> 4;                       // 16-byte chunks per row
+            const int passes_per_rowgroup = (nch + 3) >> 2;
+            for (int it = c.warp; it < NB * passes_per_rowgroup; it += THREADS / 32) {
+                const int ib = it / passes_per_rowgroup, cp = it % passes_per_rowgroup;
+                const int i = ib * 8 + (c.lane & 7), ch = cp * 4 + (c.lane >> 3);
+                if (ch < nch) {
+                    union { uint4 v; int8_t s[16]; } u;
+                    u.v = *reinterpret_cast<const uint4*>(A8 + (size_t)i * NP + ch * 16);
+                    uint32_t wa[8], wb[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int a0 = u.s[2 * k], a1 = u.s[2 * k + 1];
+                        const uint32_t m0 = a0 ? 0x3F80u : 0u, m1 = a1 ? 0x3F80u : 0u;
+                        wb[k] = m0 | (m1 << 16);
+                        wa[k] = (m0 | (a0 < 0 ? 0x8000u : 0u)) | ((m1 | (a1 < 0 ? 0x8000u : 0u)) << 16);
+                    }
+                    const int off0 = ((2 * ch) * NB + ib) * 128 + (c.lane & 7) * 16;
+                    const int off1 = off0 + NB * 128;
+                    *reinterpret_cast<uint4*>(sA + off0) = make_uint4(wa[0], wa[1], wa[2], wa[3]);
+                    *reinterpret_cast<uint4*>(sA + off1) = make_uint4(wa[4], wa[5], wa[6], wa[7]);
+                    *reinterpret_cast<uint4*>(sAbs + off0) = make_uint4(wb[0], wb[1], wb[2], wb[3]);
+                    *reinterpret_cast<uint4*>(sAbs + off1) = make_uint4(wb[4], wb[5], wb[6], wb[7]);
+                }
+            }
+        }
+        load_weights_tmem<32>(c, pk + PK_WEF, T_WEF);
+        __syncthreads();                                   // xf visible
+        // S = R+ + R-, D = R+ - R- with R+- = ReLU(P +- w0), P = W_x x  -> TMEM A operands (mpnn.py:89-100 factorised)
+        {
+            const int fa = 16 * c.q + (c.lane >> 2), fb = fa + 8;
+            float wxa[8], wxb[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { wxa[k] = s_wedge[fa * 8 + k]; wxb[k] = s_wedge[fb * 8 + k]; }
+            for (int blk = c.hw; blk < nsteps_A; blk += 2) {
+                uint32_t sh[4], sl[4], dh[4], dl[4];
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int n0 = 16 * blk + 8 * half + 2 * (c.lane & 3);
+                    float pa0 = 0.f, pa1 = 0.f, pb0 = 0.f, pb1 = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) {
+                        const float2 x = *reinterpret_cast<const float2*>(xf + k * NPMAX + n0);
+                        pa0 = fmaf(wxa[1 + k], x.x, pa0); pa1 = fmaf(wxa[1 + k], x.y, pa1);
+                        pb0 = fmaf(wxb[1 + k], x.x, pb0); pb1 = fmaf(wxb[1 + k], x.y, pb1);
+                    }
+                    const float rpa0 = fmaxf(pa0 + wxa[0], 0.f), rma0 = fmaxf(pa0 - wxa[0], 0.f);
+                    const float rpa1 = fmaxf(pa1 + wxa[0], 0.f), rma1 = fmaxf(pa1 - wxa[0], 0.f);
+                    const float rpb0 = fmaxf(pb0 + wxb[0], 0.f), rmb0 = fmaxf(pb0 - wxb[0], 0.f);
+                    const float rpb1 = fmaxf(pb1 + wxb[0], 0.f), rmb1 = fmaxf(pb1 - wxb[0], 0.f);
+                    split2(rpa0 + rma0, rpa1 + rma1, sh[2 * half + 0], sl[2 * half + 0]);
+                    split2(rpb0 + rmb0, rpb1 + rmb1, sh[2 * half + 1], sl[2 * half + 1]);
+                    split2(rpa0 - rma0, rpa1 - rma1, dh[2 * half + 0], dl[2 * half + 0]);
+                    split2(rpb0 - rmb0, rpb1 - rmb1, dh[2 * half + 1], dl[2 * half + 1]);
+                }
+                tmem_st_16x128b_x2(tmem_addr(c.tmem, 32 * c.q, T_S + 8 * blk), sh);
+                tmem_st_16x128b_x2(tmem_addr(c.tmem, 32 * c.q + 16, T_S + 8 * blk), sl);
+                tmem_st_16x128b_x2(tmem_addr(c.tmem, 32 * c.q, T_D + 8 * blk), dh);
+                tmem_st_16x128b_x2(tmem_addr(c.tmem, 32 * c.q + 16, T_D + 8 * blk), dl);
+            }
+            tmem_st_wait();
+        }
+        stage_sync();
+        if (c.tid == 0) {
+            tc_fence_after();
+            const uint32_t idesc = instr_desc_bf16(128, NP, false, false);
+            for (int ks = 0; ks < nsteps_A; ++ks) {
+                const uint64_t bd_abs = smem_desc(smem_u32(sAbs) + ks * 2 * NB * 128, NB * 128, 128);
+                const uint64_t bd_a = smem_desc(smem_u32(sA) + ks * 2 * NB * 128, NB * 128, 128);
+                mma_ts(c.tmem + T_ACC0, c.tmem + T_S + 8 * ks, bd_abs, idesc, ks > 0);
+                mma_ts(c.tmem + T_ACC0, c.tmem + T_D + 8 * ks, bd_a, idesc, true);
+            }
+            mma_commit(c.bar);
+        }
+        wait_mma(c);
+
+        // ================= stage 1: h0 (CUDA cores), weights of layer 0, edge embeddings e =================
+        load_weights_tmem<64>(c, pk + PK_WM, T_WM);
+        load_weights_tmem<64>(c, pk + PK_WU, T_WU);
+        for (int blk = c.warp; blk < 8 * NB; blk += THREADS / 32) {      // (8-feature group, 8-vertex group) tiles
+            const int g8 = blk % 8, cb = blk / 8;
+            const int f = 8 * g8 + (c.lane >> 2), n0 = 8 * cb + 2 * (c.lane & 3);
+            float h0 = 0.f, h1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                const float2 x = *reinterpret_cast<const float2*>(xf + k * NPMAX + n0);
+                const float wk = s_winit[f * 7 + k];
+                h0 = fmaf(wk, x.x, h0); h1 = fmaf(wk, x.y, h1);
+            }
+            uint32_t hi, lo;
+            split2(fmaxf(h0, 0.f), fmaxf(h1, 0.f), hi, lo);
+            const int rb = 4 * (g8 >> 1) + (g8 & 1);
+            unsigned char* p = sH + (cb * 16 + rb) * 128 + 16 * (c.lane >> 2) + 4 * (c.lane & 3);
+            *reinterpret_cast<uint32_t*>(p) = hi;
+            *reinterpret_cast<uint32_t*>(p + 2 * 128) = lo;
+        }
+        tmem_st_wait();
+        for (int c0 = 0; c0 < NP; c0 += CHUNK) {
+            const int width = min(CHUNK, NP - c0);
+            // g = (S|A| + D A) / (2 deg); feature 63 = deg / deg_max   (mpnn.py:100-102)
+            epilogue(c, T_ACC0, c0, width, [&](int bc, float (&v)[8]) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int n = c0 + bc + 8 * (i >> 2) + 2 * (c.lane & 3) + (i & 1);
+                    const int f = 16 * c.q + (c.lane >> 2) + 8 * ((i >> 1) & 1);
+                    const float d = sdeg[n];
+                    v[i] = f == 63 ? d / dmax : (0.5f * v[i]) / d;
+                }
+                store_block(c, sT, bc, v);
+            });
+            stage_sync();
+            if (c.tid == 0) {
+                tc_fence_after();
+                const uint32_t idesc = instr_desc_bf16(128, width, false, true);
+                bool acc = false;
+#pragma unroll
+                for (int kq = 0; kq < 4; ++kq)
+#pragma unroll
+                    for (int s = 0; s < 2; ++s) {
+                        mma_ts(c.tmem + T_ACC1, c.tmem + T_WEF + 8 * kq, bdesc_stacked(sT, 0, kq, s), idesc, acc);
+                        acc = true;
+                    }
+                mma_commit(c.bar);
+            }
+            wait_mma(c);
+            epilogue(c, T_ACC1, 0, width, [&](int bc, float (&v)[8]) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+                store_block(c, sE, c0 + bc, v);
+            });
+        }
+
+        // ================= stage 2: three message-passing layers (mpnn.py:114-120) ==========================
+        float pool_a = 0.f, pool_b = 0.f;       // readout partials (last layer)
+        for (int i = c.tid; i < 4 * NPMAX; i += THREADS) qpart[i] = 0.f;
+        for (int l = 0; l < 3; ++l) {
+            stage_sync();
+            if (c.tid == 0) {                   // agg^T = H^T A  (both hi and lo rows in one M=128 chain)
+                tc_fence_after();
+                const uint32_t idesc = instr_desc_bf16(128, NP, false, false);
+                for (int ks = 0; ks < nsteps_A; ++ks) {
+                    const uint64_t ad = smem_desc(smem_u32(sH) + ks * 2 * 2048, 2048, 128);
+                    const uint64_t bd = smem_desc(smem_u32(sA) + ks * 2 * NB * 128, NB * 128, 128);
+                    mma_ss(c.tmem + T_ACC0, ad, bd, idesc, ks > 0);
+                }
+                mma_commit(c.bar);
+            }
+            wait_mma(c);
+            for (int c0 = 0; c0 < NP; c0 += CHUNK) {
+                const int width = min(CHUNK, NP - c0);
+                epilogue(c, T_ACC0, c0, width, [&](int bc, float (&v)[8]) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = v[i] / sdeg[c0 + bc + 8 * (i >> 2) + 2 * (c.lane & 3) + (i & 1)];
+                    store_block(c, sT, bc, v);
+                });
+                stage_sync();
+                if (c.tid == 0) { tc_fence_after(); issue_linear(c, T_WM, sT, 0, sE, c0 >> 3, width); }   // m = W_m [agg ; e]
+                wait_mma(c);
+                epilogue(c, T_ACC1, 0, width, [&](int bc, float (&v)[8]) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+                    store_block(c, sT, bc, v);
+                });
+                stage_sync();
+                if (c.tid == 0) { tc_fence_after(); issue_linear(c, T_WU, sH, c0 >> 3, sT, 0, width); }   // h' = W_u [h ; m]
+                wait_mma(c);
+                if (l < 2) {
+                    epilogue(c, T_ACC1, 0, width, [&](int bc, float (&v)[8]) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+                        store_block(c, sH, c0 + bc, v);
+                    });
+                } else {
+                    // readout partials straight from the fp32 registers (mpnn.py:143-159)
+                    const int fa = 16 * c.q + (c.lane >> 2);
+                    const float wa = s_wread[64 + fa], wb = s_wread[64 + fa + 8];
+                    epilogue(c, T_ACC1, 0, width, [&](int bc, float (&v)[8]) {
+                        float qv[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {     // j: columns {0,1,8,9} + 2(lane&3)
+                            const int ia = 4 * (j >> 1) + (j & 1), ib = ia + 2;
+                            const int n = c0 + bc + 8 * (j >> 1) + 2 * (c.lane & 3) + (j & 1);
+                            const float ha = fmaxf(v[ia], 0.f), hb = fmaxf(v[ib], 0.f);
+                            if (n < N) { pool_a += ha; pool_b += hb; }
+                            qv[j] = fmaf(wa, ha, wb * hb);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            qv[j] += __shfl_xor_sync(0xffffffffu, qv[j], 4);
+                            qv[j] += __shfl_xor_sync(0xffffffffu, qv[j], 8);
+                            qv[j] += __shfl_xor_sync(0xffffffffu, qv[j], 16);
+                        }
+                        if ((c.lane >> 2) == 0) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                qpart[c.q * NPMAX + c0 + bc + 8 * (j >> 1) + 2 * (c.lane & 3) + (j & 1)] = qv[j];
+                        }
+                    });
+                }
+            }
+            if (l < 2) {
+                load_weights_tmem<64>(c, pk + PK_WM + (l + 1) * 128 * 64, T_WM);
+                load_weights_tmem<64>(c, pk + PK_WU + (l + 1) * 128 * 64, T_WU);
+                tmem_st_wait();
+            }
+        }
+
+        // ================= stage 3: readout + argmax ========================================================
+        pool_a += __shfl_xor_sync(0xffffffffu, pool_a, 1); pool_a += __shfl_xor_sync(0xffffffffu, pool_a, 2);
+        pool_b += __shfl_xor_sync(0xffffffffu, pool_b, 1); pool_b += __shfl_xor_sync(0xffffffffu, pool_b, 2);
+        if ((c.lane & 3) == 0) {
+            const int fa = 16 * c.q + (c.lane >> 2);
+            ppart[c.hw * 64 + fa] = pool_a;
+            ppart[c.hw * 64 + fa + 8] = pool_b;
+        }
+        __syncthreads();
+        if (c.tid < 64) pooled[c.tid] = (ppart[c.tid] + ppart[64 + c.tid]) / (float)N;
+        __syncthreads();
+        if (c.warp == 0) {
+            float acc = 0.f;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int f = c.lane + 32 * half;
+                float p = 0.f;
+                for (int k = 0; k < 64; ++k) p = fmaf(w.w_pool[f * 64 + k], pooled[k], p);
+                acc = fmaf(s_wread[f], fmaxf(p, 0.f), acc);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (c.lane == 0) *s_c0 = acc + w.b_read[0];
+        }
+        __syncthreads();
+        {
+            float bv = -INFINITY;
+            int bi = 0x7fffffff;
+            if (c.tid < N) {
+                const int i = c.tid;
+                bv = *s_c0 + ((qpart[i] + qpart[NPMAX + i]) + (qpart[2 * NPMAX + i] + qpart[3 * NPMAX + i]));
+                bi = i;
+                if (q_out) q_out[(size_t)b * NP + i] = bv;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (c.lane == 0) { red_val[c.warp] = bv; red_idx[c.warp] = bi; }
+        }
+        __syncthreads();
+        if (c.tid == 0 && act_out) {
+            float bv = red_val[0];
+            int bi = red_idx[0];
+            for (int ww = 1; ww < THREADS / 32; ++ww)
+                if (red_val[ww] > bv || (red_val[ww] == bv && red_idx[ww] < bi)) { bv = red_val[ww]; bi = red_idx[ww]; }
+            act_out[b] = bi;
+        }
+        __syncthreads();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (c.warp == 0) tmem_dealloc(c.tmem, 512);
+}
+
+}  // namespace
+
+bool mpnn_tc_supported(const eco_graphs_t* g) { return g->N <= NPMAX && (g->reserved & 1); }
+size_t mpnn_tc_scratch_bytes(int, int) { return 256; }
+size_t mpnn_tc_packed_bytes() { return (size_t)PK_WORDS * 4; }
+
+int launch_mpnn_pack(const eco_mpnn_t* w, void* packed, cudaStream_t st) {
+    mpnn_pack_kernel<<<(PK_WORDS + 255) / 256, 256, 0, st>>>(*w, (uint32_t*)packed);
+    ECO_LAUNCH_CHECK();
+    return ECO_OK;
+}
+
+int launch_mpnn_tc(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int32_t* gidx, const float* xn,
+                   const float* xg, float norm_max, float* q, int32_t* actions, void*, cudaStream_t st) {
+    static bool attr_set = false;
+    static int n_sm = 148;
+    if (!attr_set) {
+        ECO_CUDA(cudaFuncSetAttribute(mpnn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+        int dev = 0;
+        ECO_CUDA(cudaGetDevice(&dev));
+        ECO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        attr_set = true;
+    }
+    const int grid = B < n_sm ? B : n_sm;
+    prof_begin(ECO_PROF_MPNN, st);
+    mpnn_tc_kernel<<<grid, THREADS, SM_TOTAL, st>>>(*g, *w, B, gidx, xn, xg, norm_max, q, actions);
+    prof_end(ECO_PROF_MPNN, st);
+    ECO_LAUNCH_CHECK();
+    return ECO_OK;
+}
+
 }  // namespace eco

@@ -37,10 +37,11 @@ def rollout(J, weights, init_spins, max_steps, basin_reward=None, forced_actions
             ob = torch.FloatTensor(np.array(obs))          # experiments/utils.py:174
             if record_obs:
                 obs_rec[:, t] = ob[:, :7, :].numpy()
-        if forced_actions is None:
+        if forced_actions is None or q_hook is not None:
             qs = mpnn_forward(w, ob)
             if q_hook is not None:
                 q_hook(t, qs)
+        if forced_actions is None:
             acts = qs.argmax(1, True).squeeze(1).numpy()   # experiments/utils.py:65 (first max on ties)
         else:
             acts = forced_actions[:, t]

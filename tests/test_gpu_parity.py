@@ -11,7 +11,7 @@ from conftest import GOLDEN, golden_cases
 pytestmark = pytest.mark.gpu
 
 Q_RTOL = 1e-3      # north_star: Q-values within 1e-3 relative in fp32
-Q_ATOL_FRAC = 1e-5  # of max|Q| in the row, for entries near zero
+Q_ATOL_FRAC = 1e-4  # x max|Q| of the row: floor for entries near zero (10x below the 1e-3 scale)
 
 
 def load(name):
