@@ -14,13 +14,17 @@
 //                 Stacked row order r = 32q + 16s + t  <->  feature 16q + t, s in {hi, lo}: the two halves of a
 //                 feature sit in the same TMEM lane quadrant, so one warp adds them after two 16x256b loads.
 //   smem          adjacency bf16 (N x N, K-major core matrices), H^T and E^T stacked hi/lo (one copy serves as
-//                 K-major A-operand of the aggregation AND MN-major B-operand of the linears), one 80-vertex
-//                 chunk buffer.  No swizzle: 8x16-byte core matrices, written conflict-free by the epilogues.
-//   TMEM          cols 0..207 aggregation accumulator, 208..287 linear accumulator, 288.. weight A-operands
+//                 K-major A-operand of the aggregation AND MN-major B-operand of the linears), two 48-vertex
+//                 chunk buffers.  No swizzle: 8x16-byte core matrices, written conflict-free by the epilogues.
+//   TMEM          cols 0..207 aggregation accumulator, 208..335 linear accumulators, 336.. weight A-operands
 //                 (tcgen05.st from registers, straight from L2); the edge-stage A-operands S = R+ + R-,
 //                 D = R+ - R- live in TMEM too (g = (|A| S + A D) / (2 deg), SURVEY.md section 7 identity).
 //   edge stage    ReLU(W_e [a_ij ; x_j]) = ReLU(a_ij w0 + P_j): two dense N x N contractions instead of the
 //                 reference's [B,N,N,63] intermediate.
+//   schedule      the 8 warps form two groups of 4 (one warp per TMEM lane quadrant).  The N x N contractions are
+//                 issued once per layer for the whole CTA; the per-vertex linears run on 48-vertex chunks, even
+//                 chunks on group 0 and odd chunks on group 1, each group with its own accumulator columns, chunk
+//                 buffer, mbarrier and named barrier, so one group's MMAs overlap the other group's epilogue.
 #include <cuda_bf16.h>
 
 #include "eco_common.cuh"
@@ -32,27 +36,27 @@ namespace {
 using namespace tc;
 
 constexpr int NPMAX = 208;
-constexpr int CHUNK = 80;        // vertices per linear-layer chunk (accumulator columns)
+constexpr int CHUNK = 48;        // vertices per linear-layer chunk (accumulator columns)
 constexpr int THREADS = 256;
 
 // ---- TMEM column map -------------------------------------------------------------------------------------
 constexpr uint32_t T_ACC0 = 0;       // 208 cols: aggregation / edge accumulator
-constexpr uint32_t T_ACC1 = 208;     // 80 cols: linear accumulator (chunk relative)
-constexpr uint32_t T_WM = 288;       // 64 cols: message weights (128 stacked rows x 128 k, bf16 pairs)
-constexpr uint32_t T_WU = 352;       // 64 cols: update weights
-constexpr uint32_t T_WEF = 416;      // 32 cols: edge-feature weights (k = 64)
-constexpr uint32_t T_S = 208;        // 104 cols: edge-stage A-operand S   (dead before ACC1 / weights are live)
+constexpr uint32_t T_ACC1 = 208;     // 2 x 64 cols: linear accumulators of group 0 / group 1 (chunk relative)
+constexpr uint32_t T_WM = 336;       // 64 cols: message weights (128 stacked rows x 128 k, bf16 pairs)
+constexpr uint32_t T_WU = 400;       // 64 cols: update weights
+constexpr uint32_t T_WEF = 464;      // 32 cols: edge-feature weights (k = 64)
+constexpr uint32_t T_S = 208;        // 104 cols: edge-stage A-operand S   (dead before ACC1 / WM / WU are live)
 constexpr uint32_t T_D = 312;        // 104 cols: edge-stage A-operand D
 
 // ---- shared memory map (bytes) -----------------------------------------------------------------------------
 constexpr int SM_A = 0;                                  // adjacency, bf16, up to 208 x 208
 constexpr int SM_H = SM_A + NPMAX * NPMAX * 2;           // H^T stacked [128][208]
 constexpr int SM_E = SM_H + 128 * NPMAX * 2;             // E^T stacked
-constexpr int SM_T = SM_E + 128 * NPMAX * 2;             // chunk buffer [128][80]
+constexpr int SM_T = SM_E + 128 * NPMAX * 2;             // chunk buffers [2 groups][128][48]
 constexpr int SM_ABS = SM_H;                             // |A| overlays H and E during the edge stage
-constexpr int SM_XF = SM_T + 128 * CHUNK * 2;            // float xf[7][208]
-constexpr int SM_DEG = SM_XF + 7 * NPMAX * 4;            // float deg[208]
-constexpr int SM_QP = SM_DEG + NPMAX * 4;                // float qpart[4][208]
+constexpr int SM_XF = SM_T + 128 * CHUNK * 2;            // float xf[7][208] overlays group 1's chunk buffer (dead by then)
+constexpr int SM_DEG = SM_T + 2 * 128 * CHUNK * 2;       // float rdeg[208] = 1/deg, float fdeg[208] = deg/deg_max
+constexpr int SM_QP = SM_DEG + 2 * NPMAX * 4;            // float qpart[4][208]
 constexpr int SM_PP = SM_QP + 4 * NPMAX * 4;             // float ppart[2][64]
 constexpr int SM_WI = SM_PP + 2 * 64 * 4;                // float w_init[64*7]
 constexpr int SM_WE = SM_WI + 64 * 7 * 4;                // float w_edge[64*8] (row 63 zero)
@@ -60,6 +64,7 @@ constexpr int SM_WR = SM_WE + 64 * 8 * 4;                // float w_read[128]
 constexpr int SM_MISC = SM_WR + 128 * 4;                 // float pooled[64], c0, reductions
 constexpr int SM_TOTAL = SM_MISC + 64 * 4 + 64 + 8 * 8 + 8 * 8;
 static_assert(NPMAX * NPMAX * 2 <= 2 * 128 * NPMAX * 2, "|A| must fit in the H+E region");
+static_assert(7 * NPMAX * 4 <= 128 * CHUNK * 2, "xf must fit in a chunk buffer");
 static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
 
 // packed weights (uint32 words): [128 stacked rows][k/2] per matrix
@@ -89,20 +94,31 @@ __global__ void mpnn_pack_kernel(const eco_mpnn_t w, uint32_t* __restrict__ out)
 struct Ctx {
     unsigned char* smem;
     uint32_t tmem;
-    uint64_t* bar;
-    uint32_t phase;
-    int tid, warp, lane, q, hw;
+    uint64_t* bar_all;     // completion of CTA-wide MMA batches (edge contraction, aggregation)
+    uint64_t* bar_grp;     // completion of this group's linear MMAs
+    uint32_t phase_all, phase_grp;
+    int tid, warp, lane, q, grp;
     int N, NP, NB;
 };
 
-__device__ __forceinline__ void stage_sync() {   // operands written (smem via generic proxy, TMEM via tcgen05.st / ld done)
+__device__ __forceinline__ void cta_stage_sync() {   // operands written by everyone (smem: generic proxy; TMEM: st/ld retired)
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
 }
-__device__ __forceinline__ void wait_mma(Ctx& c) {
-    mbar_wait(c.bar, c.phase);
-    c.phase ^= 1;
+__device__ __forceinline__ void grp_stage_sync(const Ctx& c) {   // same, among the 128 threads of one group
+    fence_proxy_async();
+    tc_fence_before();
+    asm volatile("bar.sync %0, 128;" ::"r"(c.grp + 1) : "memory");
+}
+__device__ __forceinline__ void wait_all(Ctx& c) {
+    mbar_wait(c.bar_all, c.phase_all);
+    c.phase_all ^= 1;
+    tc_fence_after();
+}
+__device__ __forceinline__ void wait_grp(Ctx& c) {
+    mbar_wait(c.bar_grp, c.phase_grp);
+    c.phase_grp ^= 1;
     tc_fence_after();
 }
 
@@ -110,22 +126,24 @@ __device__ __forceinline__ void wait_mma(Ctx& c) {
 template <int KW>
 __device__ __forceinline__ void load_weights_tmem(const Ctx& c, const uint32_t* __restrict__ pk, uint32_t tcol) {
     const int r = 32 * c.q + c.lane;
-    const uint4* src = reinterpret_cast<const uint4*>(pk + (size_t)r * KW + c.hw * (KW / 2));
+    const uint4* src = reinterpret_cast<const uint4*>(pk + (size_t)r * KW + c.grp * (KW / 2));
+    uint4 buf[KW / 8];
+#pragma unroll
+    for (int i = 0; i < KW / 8; ++i) buf[i] = __ldg(src + i);
 #pragma unroll
     for (int i = 0; i < KW / 16; ++i) {
-        const uint4 a = src[2 * i], b = src[2 * i + 1];
+        const uint4 a = buf[2 * i], b = buf[2 * i + 1];
         const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        tmem_st_32x32b_x8(tmem_addr(c.tmem, 32 * c.q, tcol + c.hw * (KW / 2) + 8 * i), v);
+        tmem_st_32x32b_x8(tmem_addr(c.tmem, 32 * c.q, tcol + c.grp * (KW / 2) + 8 * i), v);
     }
 }
 
-// Generic epilogue over accumulator columns [col0, col0 + width) of `acc` (width % 16 == 0).  For every 16-column
-// block the warp owns, loads the hi-row and lo-row halves of its quadrant, adds them and calls
-//   fn(blk_col /*first column of the block, relative to col0*/, v[8])
-// where v[i] belongs to feature 16q + lane/4 + 8*((i>>1)&1) and column blk_col + 8*(i>>2) + 2*(lane&3) + (i&1).
+// Epilogue over accumulator columns [col0, col0 + width) of `acc` (width % 16 == 0) by the warp owning quadrant q of
+// one group: loads the hi-row and lo-row halves, adds them and calls fn(blk_col, v[8]) where v[i] belongs to feature
+// 16q + lane/4 + 8*((i>>1)&1) and column blk_col + 8*(i>>2) + 2*(lane&3) + (i&1)  (blk_col relative to col0).
 template <class Fn>
 __device__ __forceinline__ void epilogue(const Ctx& c, uint32_t acc, int col0, int width, Fn fn) {
-    for (int blk = c.hw; blk < width / 16; blk += 2) {
+    for (int blk = 0; blk < width / 16; ++blk) {
         uint32_t vh[8], vl[8];
         tmem_ld_16x256b_x2(tmem_addr(c.tmem, 32 * c.q, acc + col0 + 16 * blk), vh);
         tmem_ld_16x256b_x2(tmem_addr(c.tmem, 32 * c.q + 16, acc + col0 + 16 * blk), vl);
@@ -155,30 +173,22 @@ __device__ __forceinline__ void store_block(const Ctx& c, unsigned char* buf, in
     }
 }
 
-// B-operand descriptor of a stacked buffer used MN-major: k-step kq (features 16kq..16kq+15), split s, first vertex group cb0
-__device__ __forceinline__ uint64_t bdesc_stacked(const unsigned char* buf, int cb0, int kq, int s) {
-    return smem_desc(smem_u32(buf) + (cb0 * 16 + 4 * kq + 2 * s) * 128, /*LBO (k groups)*/ 128, /*SBO (vertex groups)*/ 2048);
-}
-
-// One linear layer on a chunk: acc1 = W[:, 0:64] * X0 + W[:, 64:128] * X1 (X1 optional), X given as stacked buffers.
-__device__ __forceinline__ void issue_linear(const Ctx& c, uint32_t tw, const unsigned char* x0, int cb0_0,
+// One linear layer on a chunk (single issuing thread): acc = W[:, 0:64] * X0 (+ W[:, 64:128] * X1), X given as stacked
+// buffers used MN-major: k-step kq covers features 16kq..16kq+15, split s selects the hi / lo rows.
+__device__ __forceinline__ void issue_linear(const Ctx& c, uint32_t acc_col, uint32_t tw, const unsigned char* x0, int cb0_0,
                                              const unsigned char* x1, int cb0_1, int width) {
     const uint32_t idesc = instr_desc_bf16(128, width, false, true);
-    bool acc = false;
+    const uint64_t d0 = smem_desc(smem_u32(x0) + cb0_0 * 2048, /*LBO (k groups)*/ 128, /*SBO (vertex groups)*/ 2048);
 #pragma unroll
-    for (int part = 0; part < 2; ++part) {
-        const unsigned char* x = part ? x1 : x0;
-        if (x == nullptr) continue;
-        const int cb0 = part ? cb0_1 : cb0_0;
+    for (int i = 0; i < 8; ++i)     // i = 2*kq + s -> rows 32kq + 16s: 256-byte steps (16 B units in the descriptor)
+        mma_ts(c.tmem + acc_col, c.tmem + tw + 8 * (i >> 1), d0 + (uint64_t)(16 * i), idesc, i > 0);
+    if (x1 != nullptr) {
+        const uint64_t d1 = smem_desc(smem_u32(x1) + cb0_1 * 2048, 128, 2048);
 #pragma unroll
-        for (int kq = 0; kq < 4; ++kq)
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                mma_ts(c.tmem + T_ACC1, c.tmem + tw + 32 * part + 8 * kq, bdesc_stacked(x, cb0, kq, s), idesc, acc);
-                acc = true;
-            }
+        for (int i = 0; i < 8; ++i)
+            mma_ts(c.tmem + acc_col, c.tmem + tw + 32 + 8 * (i >> 1), d1 + (uint64_t)(16 * i), idesc, true);
     }
-    mma_commit(c.bar);
+    mma_commit(c.bar_grp);
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -186,16 +196,19 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                const float* __restrict__ xn, const float* __restrict__ xg, const float norm_max,
                float* __restrict__ q_out, int32_t* __restrict__ act_out) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ uint64_t bar_s;
+    __shared__ uint64_t bars[3];
     __shared__ uint32_t tmem_base_s;
     Ctx c;
-    c.smem = smem; c.bar = &bar_s; c.phase = 0;
-    c.tid = threadIdx.x; c.warp = c.tid >> 5; c.lane = c.tid & 31; c.q = c.warp & 3; c.hw = c.warp >> 2;
+    c.smem = smem; c.phase_all = 0; c.phase_grp = 0;
+    c.tid = threadIdx.x; c.warp = c.tid >> 5; c.lane = c.tid & 31; c.q = c.warp & 3; c.grp = c.warp >> 2;
+    c.bar_all = &bars[0]; c.bar_grp = &bars[1 + c.grp];
     c.N = g.N; c.NP = g.NP; c.NB = g.NP >> 3;
     const int N = c.N, NP = c.NP, NB = c.NB;
+    const bool leader = (c.tid & 127) == 0;
 
     float* xf = reinterpret_cast<float*>(smem + SM_XF);
-    float* sdeg = reinterpret_cast<float*>(smem + SM_DEG);
+    float* rdeg = reinterpret_cast<float*>(smem + SM_DEG);      // 1 / deg
+    float* fdeg = rdeg + NPMAX;                                   // deg / deg_max
     float* qpart = reinterpret_cast<float*>(smem + SM_QP);
     float* ppart = reinterpret_cast<float*>(smem + SM_PP);
     float* s_winit = reinterpret_cast<float*>(smem + SM_WI);
@@ -209,11 +222,12 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     unsigned char* sAbs = smem + SM_ABS;
     unsigned char* sH = smem + SM_H;
     unsigned char* sE = smem + SM_E;
-    unsigned char* sT = smem + SM_T;
+    unsigned char* sT = smem + SM_T + c.grp * (128 * CHUNK * 2);     // this group's chunk buffer
+    const uint32_t acc1 = T_ACC1 + 64 * c.grp;                       // this group's linear accumulator
     const uint32_t* pk = reinterpret_cast<const uint32_t*>(w.packed);
 
     if (c.warp == 0) tmem_alloc(&tmem_base_s, 512);
-    if (c.tid == 0) { mbar_init(&bar_s, 1); fence_mbar_init(); }
+    if (c.tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); fence_mbar_init(); }
     for (int i = c.tid; i < 64 * 7; i += THREADS) s_winit[i] = w.w_init[i];
     for (int i = c.tid; i < 64 * 8; i += THREADS) s_wedge[i] = i < 63 * 8 ? w.w_edge[i] : 0.f;
     for (int i = c.tid; i < 128; i += THREADS) s_wread[i] = w.w_read[i];
@@ -222,11 +236,20 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     tc_fence_after();
     c.tmem = tmem_base_s;
     const float dmax = norm_max > 0.f ? norm_max : *g.dmax;
+    const float rdmax = 1.f / dmax;
     const int nsteps_A = NP >> 4;                         // k-steps over vertices
+    const int nchunks = (NP + CHUNK - 1) / CHUNK;
 
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
         const int gi = graph_idx[b];
         const int8_t* A8 = g.J + (size_t)gi * NP * NP;
+
+        // pull the next episode's adjacency towards L2 while this one computes
+        if (b + (int)gridDim.x < B) {
+            const int8_t* nxt = g.J + (size_t)graph_idx[b + gridDim.x] * NP * NP;
+            for (int off = c.tid * 128; off < NP * NP; off += THREADS * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + off));
+        }
 
         // ================= stage 0: operands of the edge contraction ======================================
         for (int i = c.tid; i < NP; i += THREADS) {
@@ -239,25 +262,40 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             xf[4 * NPMAX + i] = ok ? gl.y : 0.f;
             xf[5 * NPMAX + i] = ok ? gl.z : 0.f;
             xf[6 * NPMAX + i] = ok ? gl.w : 0.f;
-            sdeg[i] = g.deg[(size_t)gi * NP + i];
+            const float d = g.deg[(size_t)gi * NP + i];
+            rdeg[i] = 1.f / d;
+            fdeg[i] = d * rdmax;
         }
-        // adjacency int8 -> bf16 A and |A| (K-major B operands): a warp converts 8 rows x 64 bytes per pass
+        // adjacency int8 -> bf16 A and |A| (K-major B operands): a warp converts 8 rows x 64 bytes per pass;
+        // all of a warp's loads are issued before the first conversion
         {
             const int nch = NP >> 4;                       // 16-byte chunks per row
-            const int passes_per_rowgroup = (nch + 3) >> 2;
-            for (int it = c.warp; it < NB * passes_per_rowgroup; it += THREADS / 32) {
-                const int ib = it / passes_per_rowgroup, cp = it % passes_per_rowgroup;
-                const int i = ib * 8 + (c.lane & 7), ch = cp * 4 + (c.lane >> 3);
-                if (ch < nch) {
+            const int ppr = (nch + 3) >> 2;                // passes per 8-row group
+            const int total = NB * ppr;
+            constexpr int MAXIT = (NPMAX / 8 * 4 + 7) / 8;  // 13 passes per warp at N = 208
+            uint4 raw[MAXIT];
+#pragma unroll
+            for (int k = 0; k < MAXIT; ++k) {
+                const int it = c.warp + 8 * k;
+                const int ib = it / ppr, ch = (it % ppr) * 4 + (c.lane >> 3);
+                raw[k] = make_uint4(0, 0, 0, 0);
+                if (it < total && ch < nch)
+                    raw[k] = *reinterpret_cast<const uint4*>(A8 + (size_t)(ib * 8 + (c.lane & 7)) * NP + ch * 16);
+            }
+#pragma unroll
+            for (int k = 0; k < MAXIT; ++k) {
+                const int it = c.warp + 8 * k;
+                const int ib = it / ppr, ch = (it % ppr) * 4 + (c.lane >> 3);
+                if (it < total && ch < nch) {
                     union { uint4 v; int8_t s[16]; } u;
-                    u.v = *reinterpret_cast<const uint4*>(A8 + (size_t)i * NP + ch * 16);
+                    u.v = raw[k];
                     uint32_t wa[8], wb[8];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const int a0 = u.s[2 * k], a1 = u.s[2 * k + 1];
+                    for (int e = 0; e < 8; ++e) {
+                        const int a0 = u.s[2 * e], a1 = u.s[2 * e + 1];
                         const uint32_t m0 = a0 ? 0x3F80u : 0u, m1 = a1 ? 0x3F80u : 0u;
-                        wb[k] = m0 | (m1 << 16);
-                        wa[k] = (m0 | (a0 < 0 ? 0x8000u : 0u)) | ((m1 | (a1 < 0 ? 0x8000u : 0u)) << 16);
+                        wb[e] = m0 | (m1 << 16);
+                        wa[e] = (m0 | (a0 < 0 ? 0x8000u : 0u)) | ((m1 | (a1 < 0 ? 0x8000u : 0u)) << 16);
                     }
                     const int off0 = ((2 * ch) * NB + ib) * 128 + (c.lane & 7) * 16;
                     const int off1 = off0 + NB * 128;
@@ -276,7 +314,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             float wxa[8], wxb[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) { wxa[k] = s_wedge[fa * 8 + k]; wxb[k] = s_wedge[fb * 8 + k]; }
-            for (int blk = c.hw; blk < nsteps_A; blk += 2) {
+            for (int blk = c.grp; blk < nsteps_A; blk += 2) {
                 uint32_t sh[4], sl[4], dh[4], dl[4];
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
@@ -304,19 +342,20 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             }
             tmem_st_wait();
         }
-        stage_sync();
+        cta_stage_sync();
         if (c.tid == 0) {
             tc_fence_after();
             const uint32_t idesc = instr_desc_bf16(128, NP, false, false);
+            const uint64_t bd_abs = smem_desc(smem_u32(sAbs), NB * 128, 128);
+            const uint64_t bd_a = smem_desc(smem_u32(sA), NB * 128, 128);
+            const uint64_t kstep = (uint64_t)((2 * NB * 128) >> 4);
             for (int ks = 0; ks < nsteps_A; ++ks) {
-                const uint64_t bd_abs = smem_desc(smem_u32(sAbs) + ks * 2 * NB * 128, NB * 128, 128);
-                const uint64_t bd_a = smem_desc(smem_u32(sA) + ks * 2 * NB * 128, NB * 128, 128);
-                mma_ts(c.tmem + T_ACC0, c.tmem + T_S + 8 * ks, bd_abs, idesc, ks > 0);
-                mma_ts(c.tmem + T_ACC0, c.tmem + T_D + 8 * ks, bd_a, idesc, true);
+                mma_ts(c.tmem + T_ACC0, c.tmem + T_S + 8 * ks, bd_abs + ks * kstep, idesc, ks > 0);
+                mma_ts(c.tmem + T_ACC0, c.tmem + T_D + 8 * ks, bd_a + ks * kstep, idesc, true);
             }
-            mma_commit(c.bar);
+            mma_commit(c.bar_all);
         }
-        wait_mma(c);
+        wait_all(c);
 
         // ================= stage 1: h0 (CUDA cores), weights of layer 0, edge embeddings e =================
         load_weights_tmem<64>(c, pk + PK_WM, T_WM);
@@ -338,36 +377,28 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             *reinterpret_cast<uint32_t*>(p) = hi;
             *reinterpret_cast<uint32_t*>(p + 2 * 128) = lo;
         }
+        for (int i = c.tid; i < 4 * NPMAX; i += THREADS) qpart[i] = 0.f;
         tmem_st_wait();
-        for (int c0 = 0; c0 < NP; c0 += CHUNK) {
-            const int width = min(CHUNK, NP - c0);
+        cta_stage_sync();            // xf (overlaying group 1's chunk buffer) is dead from here; weights visible to the MMAs
+        for (int ci = c.grp; ci < nchunks; ci += 2) {
+            const int c0 = ci * CHUNK, width = min(CHUNK, NP - c0);
             // g = (S|A| + D A) / (2 deg); feature 63 = deg / deg_max   (mpnn.py:100-102)
             epilogue(c, T_ACC0, c0, width, [&](int bc, float (&v)[8]) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int n = c0 + bc + 8 * (i >> 2) + 2 * (c.lane & 3) + (i & 1);
                     const int f = 16 * c.q + (c.lane >> 2) + 8 * ((i >> 1) & 1);
-                    const float d = sdeg[n];
-                    v[i] = f == 63 ? d / dmax : (0.5f * v[i]) / d;
+                    v[i] = f == 63 ? fdeg[n] : (0.5f * v[i]) * rdeg[n];
                 }
                 store_block(c, sT, bc, v);
             });
-            stage_sync();
-            if (c.tid == 0) {
+            grp_stage_sync(c);
+            if (leader) {
                 tc_fence_after();
-                const uint32_t idesc = instr_desc_bf16(128, width, false, true);
-                bool acc = false;
-#pragma unroll
-                for (int kq = 0; kq < 4; ++kq)
-#pragma unroll
-                    for (int s = 0; s < 2; ++s) {
-                        mma_ts(c.tmem + T_ACC1, c.tmem + T_WEF + 8 * kq, bdesc_stacked(sT, 0, kq, s), idesc, acc);
-                        acc = true;
-                    }
-                mma_commit(c.bar);
+                issue_linear(c, acc1, T_WEF, sT, 0, nullptr, 0, width);
             }
-            wait_mma(c);
-            epilogue(c, T_ACC1, 0, width, [&](int bc, float (&v)[8]) {
+            wait_grp(c);
+            epilogue(c, acc1, 0, width, [&](int bc, float (&v)[8]) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
                 store_block(c, sE, c0 + bc, v);
@@ -376,40 +407,46 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
 
         // ================= stage 2: three message-passing layers (mpnn.py:114-120) ==========================
         float pool_a = 0.f, pool_b = 0.f;       // readout partials (last layer)
-        for (int i = c.tid; i < 4 * NPMAX; i += THREADS) qpart[i] = 0.f;
         for (int l = 0; l < 3; ++l) {
-            stage_sync();
+            cta_stage_sync();                   // every h / e column of the previous stage is written
             if (c.tid == 0) {                   // agg^T = H^T A  (both hi and lo rows in one M=128 chain)
                 tc_fence_after();
                 const uint32_t idesc = instr_desc_bf16(128, NP, false, false);
-                for (int ks = 0; ks < nsteps_A; ++ks) {
-                    const uint64_t ad = smem_desc(smem_u32(sH) + ks * 2 * 2048, 2048, 128);
-                    const uint64_t bd = smem_desc(smem_u32(sA) + ks * 2 * NB * 128, NB * 128, 128);
-                    mma_ss(c.tmem + T_ACC0, ad, bd, idesc, ks > 0);
-                }
-                mma_commit(c.bar);
+                const uint64_t ad = smem_desc(smem_u32(sH), 2048, 128);
+                const uint64_t bd = smem_desc(smem_u32(sA), NB * 128, 128);
+                const uint64_t bstep = (uint64_t)((2 * NB * 128) >> 4);
+                for (int ks = 0; ks < nsteps_A; ++ks)
+                    mma_ss(c.tmem + T_ACC0, ad + (uint64_t)ks * (4096 >> 4), bd + ks * bstep, idesc, ks > 0);
+                mma_commit(c.bar_all);
             }
-            wait_mma(c);
-            for (int c0 = 0; c0 < NP; c0 += CHUNK) {
-                const int width = min(CHUNK, NP - c0);
+            if (l > 0) {                        // this layer's weights (the previous layer's MMAs all retired)
+                load_weights_tmem<64>(c, pk + PK_WM + l * 128 * 64, T_WM);
+                load_weights_tmem<64>(c, pk + PK_WU + l * 128 * 64, T_WU);
+                tmem_st_wait();
+                tc_fence_before();
+                __syncthreads();
+            }
+            wait_all(c);
+            for (int ci = c.grp; ci < nchunks; ci += 2) {
+                const int c0 = ci * CHUNK, width = min(CHUNK, NP - c0);
                 epilogue(c, T_ACC0, c0, width, [&](int bc, float (&v)[8]) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = v[i] / sdeg[c0 + bc + 8 * (i >> 2) + 2 * (c.lane & 3) + (i & 1)];
+                    for (int i = 0; i < 8; ++i) v[i] = v[i] * rdeg[c0 + bc + 8 * (i >> 2) + 2 * (c.lane & 3) + (i & 1)];
                     store_block(c, sT, bc, v);
                 });
-                stage_sync();
-                if (c.tid == 0) { tc_fence_after(); issue_linear(c, T_WM, sT, 0, sE, c0 >> 3, width); }   // m = W_m [agg ; e]
-                wait_mma(c);
-                epilogue(c, T_ACC1, 0, width, [&](int bc, float (&v)[8]) {
+                grp_stage_sync(c);
+                if (leader) { tc_fence_after(); issue_linear(c, acc1, T_WM, sT, 0, sE, c0 >> 3, width); }   // m = W_m [agg ; e]
+                wait_grp(c);
+                epilogue(c, acc1, 0, width, [&](int bc, float (&v)[8]) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
                     store_block(c, sT, bc, v);
                 });
-                stage_sync();
-                if (c.tid == 0) { tc_fence_after(); issue_linear(c, T_WU, sH, c0 >> 3, sT, 0, width); }   // h' = W_u [h ; m]
-                wait_mma(c);
+                grp_stage_sync(c);
+                if (leader) { tc_fence_after(); issue_linear(c, acc1, T_WU, sH, c0 >> 3, sT, 0, width); }   // h' = W_u [h ; m]
+                wait_grp(c);
                 if (l < 2) {
-                    epilogue(c, T_ACC1, 0, width, [&](int bc, float (&v)[8]) {
+                    epilogue(c, acc1, 0, width, [&](int bc, float (&v)[8]) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
                         store_block(c, sH, c0 + bc, v);
@@ -418,7 +455,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                     // readout partials straight from the fp32 registers (mpnn.py:143-159)
                     const int fa = 16 * c.q + (c.lane >> 2);
                     const float wa = s_wread[64 + fa], wb = s_wread[64 + fa + 8];
-                    epilogue(c, T_ACC1, 0, width, [&](int bc, float (&v)[8]) {
+                    epilogue(c, acc1, 0, width, [&](int bc, float (&v)[8]) {
                         float qv[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {     // j: columns {0,1,8,9} + 2(lane&3)
@@ -442,11 +479,6 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                     });
                 }
             }
-            if (l < 2) {
-                load_weights_tmem<64>(c, pk + PK_WM + (l + 1) * 128 * 64, T_WM);
-                load_weights_tmem<64>(c, pk + PK_WU + (l + 1) * 128 * 64, T_WU);
-                tmem_st_wait();
-            }
         }
 
         // ================= stage 3: readout + argmax ========================================================
@@ -454,8 +486,8 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         pool_b += __shfl_xor_sync(0xffffffffu, pool_b, 1); pool_b += __shfl_xor_sync(0xffffffffu, pool_b, 2);
         if ((c.lane & 3) == 0) {
             const int fa = 16 * c.q + (c.lane >> 2);
-            ppart[c.hw * 64 + fa] = pool_a;
-            ppart[c.hw * 64 + fa + 8] = pool_b;
+            ppart[c.grp * 64 + fa] = pool_a;
+            ppart[c.grp * 64 + fa + 8] = pool_b;
         }
         __syncthreads();
         if (c.tid < 64) pooled[c.tid] = (ppart[c.tid] + ppart[64 + c.tid]) / (float)N;
@@ -466,7 +498,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             for (int half = 0; half < 2; ++half) {
                 const int f = c.lane + 32 * half;
                 float p = 0.f;
-                for (int k = 0; k < 64; ++k) p = fmaf(w.w_pool[f * 64 + k], pooled[k], p);
+                for (int k = 0; k < 64; ++k) p = fmaf(__ldg(w.w_pool + f * 64 + k), pooled[k], p);
                 acc = fmaf(s_wread[f], fmaxf(p, 0.f), acc);
             }
 #pragma unroll
