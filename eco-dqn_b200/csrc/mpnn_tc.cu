@@ -200,11 +200,12 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     __shared__ uint32_t tmem_base_s;
     Ctx c;
     c.smem = smem; c.phase_all = 0; c.phase_grp = 0;
-    c.tid = threadIdx.x; c.warp = c.tid >> 5; c.lane = c.tid & 31; c.q = c.warp & 3; c.grp = c.warp >> 2;
+    c.tid = threadIdx.x; c.lane = c.tid & 31;
+    c.warp = __shfl_sync(0xffffffffu, c.tid >> 5, 0);     // warp-uniform: MMA issue code stays on the uniform datapath
+    c.q = c.warp & 3; c.grp = c.warp >> 2;
     c.bar_all = &bars[0]; c.bar_grp = &bars[1 + c.grp];
     c.N = g.N; c.NP = g.NP; c.NB = g.NP >> 3;
     const int N = c.N, NP = c.NP, NB = c.NB;
-    const bool leader = (c.tid & 127) == 0;
 
     float* xf = reinterpret_cast<float*>(smem + SM_XF);
     float* rdeg = reinterpret_cast<float*>(smem + SM_DEG);      // 1 / deg
@@ -343,8 +344,9 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             tmem_st_wait();
         }
         cta_stage_sync();
-        if (c.tid == 0) {
-            tc_fence_after();
+        if (c.warp == 0) {
+          tc_fence_after();
+          if (elect_one()) {
             const uint32_t idesc = instr_desc_bf16(128, NP, false, false);
             const uint64_t bd_abs = smem_desc(smem_u32(sAbs), NB * 128, 128);
             const uint64_t bd_a = smem_desc(smem_u32(sA), NB * 128, 128);
@@ -354,6 +356,8 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                 mma_ts(c.tmem + T_ACC0, c.tmem + T_D + 8 * ks, bd_a + ks * kstep, idesc, true);
             }
             mma_commit(c.bar_all);
+          }
+          __syncwarp();
         }
         wait_all(c);
 
@@ -393,9 +397,10 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                 store_block(c, sT, bc, v);
             });
             grp_stage_sync(c);
-            if (leader) {
+            if (c.q == 0) {
                 tc_fence_after();
-                issue_linear(c, acc1, T_WEF, sT, 0, nullptr, 0, width);
+                if (elect_one()) issue_linear(c, acc1, T_WEF, sT, 0, nullptr, 0, width);
+                __syncwarp();
             }
             wait_grp(c);
             epilogue(c, acc1, 0, width, [&](int bc, float (&v)[8]) {
@@ -409,8 +414,9 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         float pool_a = 0.f, pool_b = 0.f;       // readout partials (last layer)
         for (int l = 0; l < 3; ++l) {
             cta_stage_sync();                   // every h / e column of the previous stage is written
-            if (c.tid == 0) {                   // agg^T = H^T A  (both hi and lo rows in one M=128 chain)
-                tc_fence_after();
+            if (c.warp == 0) {                  // agg^T = H^T A  (both hi and lo rows in one M=128 chain)
+              tc_fence_after();
+              if (elect_one()) {
                 const uint32_t idesc = instr_desc_bf16(128, NP, false, false);
                 const uint64_t ad = smem_desc(smem_u32(sH), 2048, 128);
                 const uint64_t bd = smem_desc(smem_u32(sA), NB * 128, 128);
@@ -418,6 +424,8 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                 for (int ks = 0; ks < nsteps_A; ++ks)
                     mma_ss(c.tmem + T_ACC0, ad + (uint64_t)ks * (4096 >> 4), bd + ks * bstep, idesc, ks > 0);
                 mma_commit(c.bar_all);
+              }
+              __syncwarp();
             }
             if (l > 0) {                        // this layer's weights (the previous layer's MMAs all retired)
                 load_weights_tmem<64>(c, pk + PK_WM + l * 128 * 64, T_WM);
@@ -435,7 +443,11 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                     store_block(c, sT, bc, v);
                 });
                 grp_stage_sync(c);
-                if (leader) { tc_fence_after(); issue_linear(c, acc1, T_WM, sT, 0, sE, c0 >> 3, width); }   // m = W_m [agg ; e]
+                if (c.q == 0) {                                                                // m = W_m [agg ; e]
+                    tc_fence_after();
+                    if (elect_one()) issue_linear(c, acc1, T_WM, sT, 0, sE, c0 >> 3, width);
+                    __syncwarp();
+                }
                 wait_grp(c);
                 epilogue(c, acc1, 0, width, [&](int bc, float (&v)[8]) {
 #pragma unroll
@@ -443,7 +455,11 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                     store_block(c, sT, bc, v);
                 });
                 grp_stage_sync(c);
-                if (leader) { tc_fence_after(); issue_linear(c, acc1, T_WU, sH, c0 >> 3, sT, 0, width); }   // h' = W_u [h ; m]
+                if (c.q == 0) {                                                                // h' = W_u [h ; m]
+                    tc_fence_after();
+                    if (elect_one()) issue_linear(c, acc1, T_WU, sH, c0 >> 3, sT, 0, width);
+                    __syncwarp();
+                }
                 wait_grp(c);
                 if (l < 2) {
                     epilogue(c, acc1, 0, width, [&](int bc, float (&v)[8]) {
@@ -492,18 +508,28 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         __syncthreads();
         if (c.tid < 64) pooled[c.tid] = (ppart[c.tid] + ppart[64 + c.tid]) / (float)N;
         __syncthreads();
-        if (c.warp == 0) {
-            float acc = 0.f;
+        {   // p = W_p pooled: 4 lanes per output feature, then c0 = w_r[0:64] . ReLU(p) + b
+            const int f = c.tid >> 2, part = c.tid & 3;
+            const float4* wp = reinterpret_cast<const float4*>(w.w_pool + f * 64 + part * 16);
+            float p = 0.f;
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int f = c.lane + 32 * half;
-                float p = 0.f;
-                for (int k = 0; k < 64; ++k) p = fmaf(__ldg(w.w_pool + f * 64 + k), pooled[k], p);
-                acc = fmaf(s_wread[f], fmaxf(p, 0.f), acc);
+            for (int k4 = 0; k4 < 4; ++k4) {
+                const float4 wv = __ldg(wp + k4);
+                const float* pv = pooled + part * 16 + 4 * k4;
+                p = fmaf(wv.x, pv[0], p); p = fmaf(wv.y, pv[1], p); p = fmaf(wv.z, pv[2], p); p = fmaf(wv.w, pv[3], p);
             }
+            p += __shfl_xor_sync(0xffffffffu, p, 1);
+            p += __shfl_xor_sync(0xffffffffu, p, 2);
+            float t = part == 0 ? s_wread[f] * fmaxf(p, 0.f) : 0.f;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (c.lane == 0) *s_c0 = acc + w.b_read[0];
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (c.lane == 0) red_val[c.warp] = t;
+        }
+        __syncthreads();
+        if (c.tid == 0) {
+            float t = w.b_read[0];
+            for (int ww = 0; ww < THREADS / 32; ++ww) t += red_val[ww];
+            *s_c0 = t;
         }
         __syncthreads();
         {

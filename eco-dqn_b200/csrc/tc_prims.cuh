@@ -71,6 +71,13 @@ __host__ __device__ constexpr uint32_t instr_desc_bf16(int M, int N, bool a_mn_m
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// One lane of a converged warp (warp-uniform control flow up to here keeps descriptors in uniform registers).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- MMA issue (single thread) ------------------------------------------------------------------------
 __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
     asm volatile(
