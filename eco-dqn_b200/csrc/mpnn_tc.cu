@@ -122,14 +122,16 @@ __device__ __forceinline__ void wait_grp(Ctx& c) {
     tc_fence_after();
 }
 
-// weights: global packed [128][KW] words -> TMEM columns [tcol, tcol + KW); the two warps of a quadrant split the columns
+// weights: global packed [128][KW] words -> registers -> TMEM columns [tcol, tcol + KW); the two warps that share a
+// lane quadrant split the columns.  Split in two so the L2 latency can be hidden behind a barrier / MMA wait.
 template <int KW>
-__device__ __forceinline__ void load_weights_tmem(const Ctx& c, const uint32_t* __restrict__ pk, uint32_t tcol) {
-    const int r = 32 * c.q + c.lane;
-    const uint4* src = reinterpret_cast<const uint4*>(pk + (size_t)r * KW + c.grp * (KW / 2));
-    uint4 buf[KW / 8];
+__device__ __forceinline__ void ldg_weights(const Ctx& c, const uint32_t* __restrict__ pk, uint4 (&buf)[KW / 8]) {
+    const uint4* src = reinterpret_cast<const uint4*>(pk + (size_t)(32 * c.q + c.lane) * KW + c.grp * (KW / 2));
 #pragma unroll
     for (int i = 0; i < KW / 8; ++i) buf[i] = __ldg(src + i);
+}
+template <int KW>
+__device__ __forceinline__ void sttm_weights(const Ctx& c, const uint4 (&buf)[KW / 8], uint32_t tcol) {
 #pragma unroll
     for (int i = 0; i < KW / 16; ++i) {
         const uint4 a = buf[2 * i], b = buf[2 * i + 1];
@@ -173,22 +175,15 @@ __device__ __forceinline__ void store_block(const Ctx& c, unsigned char* buf, in
     }
 }
 
-// One linear layer on a chunk (single issuing thread): acc = W[:, 0:64] * X0 (+ W[:, 64:128] * X1), X given as stacked
-// buffers used MN-major: k-step kq covers features 16kq..16kq+15, split s selects the hi / lo rows.
-__device__ __forceinline__ void issue_linear(const Ctx& c, uint32_t acc_col, uint32_t tw, const unsigned char* x0, int cb0_0,
-                                             const unsigned char* x1, int cb0_1, int width) {
+// Half of a linear layer on a chunk (single issuing thread): acc (+)= W[:, 64*part .. 64*part+63] * X, X a stacked buffer
+// used MN-major: k-step kq covers features 16kq..16kq+15, split s selects the hi / lo rows (256-byte steps).
+__device__ __forceinline__ void issue_part(const Ctx& c, uint32_t acc_col, uint32_t tw, const unsigned char* x, int cb0,
+                                           int width, bool accumulate) {
     const uint32_t idesc = instr_desc_bf16(128, width, false, true);
-    const uint64_t d0 = smem_desc(smem_u32(x0) + cb0_0 * 2048, /*LBO (k groups)*/ 128, /*SBO (vertex groups)*/ 2048);
+    const uint64_t d = smem_desc(smem_u32(x) + cb0 * 2048, /*LBO (k groups)*/ 128, /*SBO (vertex groups)*/ 2048);
 #pragma unroll
-    for (int i = 0; i < 8; ++i)     // i = 2*kq + s -> rows 32kq + 16s: 256-byte steps (16 B units in the descriptor)
-        mma_ts(c.tmem + acc_col, c.tmem + tw + 8 * (i >> 1), d0 + (uint64_t)(16 * i), idesc, i > 0);
-    if (x1 != nullptr) {
-        const uint64_t d1 = smem_desc(smem_u32(x1) + cb0_1 * 2048, 128, 2048);
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            mma_ts(c.tmem + acc_col, c.tmem + tw + 32 + 8 * (i >> 1), d1 + (uint64_t)(16 * i), idesc, true);
-    }
-    mma_commit(c.bar_grp);
+    for (int i = 0; i < 8; ++i)     // i = 2*kq + s
+        mma_ts(c.tmem + acc_col, c.tmem + tw + 8 * (i >> 1), d + (uint64_t)(16 * i), idesc, accumulate || i > 0);
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -198,6 +193,8 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint64_t bars[3];
     __shared__ uint32_t tmem_base_s;
+    __shared__ int chunk_ctr[4];      // dynamic chunk hand-out: edge-feature stage + 3 layers
+    __shared__ int next_s[2][2];      // per group, double buffered: next chunk index, published across the group barrier
     Ctx c;
     c.smem = smem; c.phase_all = 0; c.phase_grp = 0;
     c.tid = threadIdx.x; c.lane = c.tid & 31;
@@ -253,6 +250,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         }
 
         // ================= stage 0: operands of the edge contraction ======================================
+        if (c.tid < 4) chunk_ctr[c.tid] = 2;              // chunks 0 / 1 are pre-assigned to group 0 / 1
         for (int i = c.tid; i < NP; i += THREADS) {
             const bool ok = i < N;
             xf[0 * NPMAX + i] = ok ? xn[((size_t)b * 3 + 0) * NP + i] : 0.f;
@@ -267,47 +265,27 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             rdeg[i] = 1.f / d;
             fdeg[i] = d * rdmax;
         }
-        // adjacency int8 -> bf16 A and |A| (K-major B operands): a warp converts 8 rows x 64 bytes per pass;
-        // all of a warp's loads are issued before the first conversion
-        {
-            const int nch = NP >> 4;                       // 16-byte chunks per row
-            const int ppr = (nch + 3) >> 2;                // passes per 8-row group
-            const int total = NB * ppr;
-            constexpr int MAXIT = (NPMAX / 8 * 4 + 7) / 8;  // 13 passes per warp at N = 208
-            uint4 raw[MAXIT];
+        for (int i = c.tid; i < 4 * NPMAX; i += THREADS) qpart[i] = 0.f;
+        // adjacency int8 -> bf16 A and |A| (K-major B operands): a warp converts 8 rows x 64 bytes per pass.  All of a
+        // warp's loads are issued first; the S / D operands are computed while they are in flight.
+        const int nch = NP >> 4;                       // 16-byte chunks per row
+        const int ppr = (nch + 3) >> 2;                // passes per 8-row group
+        const int total_passes = NB * ppr;
+        constexpr int MAXIT = (NPMAX / 8 * 4 + 7) / 8;  // 13 passes per warp at N = 208
+        uint4 raw[MAXIT];
 #pragma unroll
-            for (int k = 0; k < MAXIT; ++k) {
-                const int it = c.warp + 8 * k;
-                const int ib = it / ppr, ch = (it % ppr) * 4 + (c.lane >> 3);
-                raw[k] = make_uint4(0, 0, 0, 0);
-                if (it < total && ch < nch)
-                    raw[k] = *reinterpret_cast<const uint4*>(A8 + (size_t)(ib * 8 + (c.lane & 7)) * NP + ch * 16);
-            }
-#pragma unroll
-            for (int k = 0; k < MAXIT; ++k) {
-                const int it = c.warp + 8 * k;
-                const int ib = it / ppr, ch = (it % ppr) * 4 + (c.lane >> 3);
-                if (it < total && ch < nch) {
-                    union { uint4 v; int8_t s[16]; } u;
-                    u.v = raw[k];
-                    uint32_t wa[8], wb[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int a0 = u.s[2 * e], a1 = u.s[2 * e + 1];
-                        const uint32_t m0 = a0 ? 0x3F80u : 0u, m1 = a1 ? 0x3F80u : 0u;
-                        wb[e] = m0 | (m1 << 16);
-                        wa[e] = (m0 | (a0 < 0 ? 0x8000u : 0u)) | ((m1 | (a1 < 0 ? 0x8000u : 0u)) << 16);
-                    }
-                    const int off0 = ((2 * ch) * NB + ib) * 128 + (c.lane & 7) * 16;
-                    const int off1 = off0 + NB * 128;
-                    *reinterpret_cast<uint4*>(sA + off0) = make_uint4(wa[0], wa[1], wa[2], wa[3]);
-                    *reinterpret_cast<uint4*>(sA + off1) = make_uint4(wa[4], wa[5], wa[6], wa[7]);
-                    *reinterpret_cast<uint4*>(sAbs + off0) = make_uint4(wb[0], wb[1], wb[2], wb[3]);
-                    *reinterpret_cast<uint4*>(sAbs + off1) = make_uint4(wb[4], wb[5], wb[6], wb[7]);
-                }
-            }
+        for (int k = 0; k < MAXIT; ++k) {
+            const int it = c.warp + 8 * k;
+            const int ib = it / ppr, ch = (it % ppr) * 4 + (c.lane >> 3);
+            raw[k] = make_uint4(0, 0, 0, 0);
+            if (it < total_passes && ch < nch)
+                raw[k] = *reinterpret_cast<const uint4*>(A8 + (size_t)(ib * 8 + (c.lane & 7)) * NP + ch * 16);
         }
-        load_weights_tmem<32>(c, pk + PK_WEF, T_WEF);
+        {
+            uint4 wbuf[4];
+            ldg_weights<32>(c, pk + PK_WEF, wbuf);
+            sttm_weights<32>(c, wbuf, T_WEF);
+        }
         __syncthreads();                                   // xf visible
         // S = R+ + R-, D = R+ - R- with R+- = ReLU(P +- w0), P = W_x x  -> TMEM A operands (mpnn.py:89-100 factorised)
         {
@@ -341,8 +319,31 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                 tmem_st_16x128b_x2(tmem_addr(c.tmem, 32 * c.q, T_D + 8 * blk), dh);
                 tmem_st_16x128b_x2(tmem_addr(c.tmem, 32 * c.q + 16, T_D + 8 * blk), dl);
             }
-            tmem_st_wait();
         }
+#pragma unroll
+        for (int k = 0; k < MAXIT; ++k) {
+            const int it = c.warp + 8 * k;
+            const int ib = it / ppr, ch = (it % ppr) * 4 + (c.lane >> 3);
+            if (it < total_passes && ch < nch) {
+                union { uint4 v; int8_t s[16]; } u;
+                u.v = raw[k];
+                uint32_t wa[8], wb[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int a0 = u.s[2 * e], a1 = u.s[2 * e + 1];
+                    const uint32_t m0 = a0 ? 0x3F80u : 0u, m1 = a1 ? 0x3F80u : 0u;
+                    wb[e] = m0 | (m1 << 16);
+                    wa[e] = (m0 | (a0 < 0 ? 0x8000u : 0u)) | ((m1 | (a1 < 0 ? 0x8000u : 0u)) << 16);
+                }
+                const int off0 = ((2 * ch) * NB + ib) * 128 + (c.lane & 7) * 16;
+                const int off1 = off0 + NB * 128;
+                *reinterpret_cast<uint4*>(sA + off0) = make_uint4(wa[0], wa[1], wa[2], wa[3]);
+                *reinterpret_cast<uint4*>(sA + off1) = make_uint4(wa[4], wa[5], wa[6], wa[7]);
+                *reinterpret_cast<uint4*>(sAbs + off0) = make_uint4(wb[0], wb[1], wb[2], wb[3]);
+                *reinterpret_cast<uint4*>(sAbs + off1) = make_uint4(wb[4], wb[5], wb[6], wb[7]);
+            }
+        }
+        tmem_st_wait();
         cta_stage_sync();
         if (c.warp == 0) {
           tc_fence_after();
@@ -359,32 +360,43 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
           }
           __syncwarp();
         }
-        wait_all(c);
-
-        // ================= stage 1: h0 (CUDA cores), weights of layer 0, edge embeddings e =================
-        load_weights_tmem<64>(c, pk + PK_WM, T_WM);
-        load_weights_tmem<64>(c, pk + PK_WU, T_WU);
-        for (int blk = c.warp; blk < 8 * NB; blk += THREADS / 32) {      // (8-feature group, 8-vertex group) tiles
-            const int g8 = blk % 8, cb = blk / 8;
-            const int f = 8 * g8 + (c.lane >> 2), n0 = 8 * cb + 2 * (c.lane & 3);
-            float h0 = 0.f, h1 = 0.f;
-#pragma unroll
-            for (int k = 0; k < 7; ++k) {
-                const float2 x = *reinterpret_cast<const float2*>(xf + k * NPMAX + n0);
-                const float wk = s_winit[f * 7 + k];
-                h0 = fmaf(wk, x.x, h0); h1 = fmaf(wk, x.y, h1);
-            }
-            uint32_t hi, lo;
-            split2(fmaxf(h0, 0.f), fmaxf(h1, 0.f), hi, lo);
-            const int rb = 4 * (g8 >> 1) + (g8 & 1);
-            unsigned char* p = sH + (cb * 16 + rb) * 128 + 16 * (c.lane >> 2) + 4 * (c.lane & 3);
-            *reinterpret_cast<uint32_t*>(p) = hi;
-            *reinterpret_cast<uint32_t*>(p + 2 * 128) = lo;
+        {   // layer-0 weights: L2 -> registers while the edge contraction runs, registers -> TMEM once S / D are dead
+            uint4 wm[8], wu[8];
+            ldg_weights<64>(c, pk + PK_WM, wm);
+            ldg_weights<64>(c, pk + PK_WU, wu);
+            wait_all(c);
+            sttm_weights<64>(c, wm, T_WM);
+            sttm_weights<64>(c, wu, T_WU);
         }
-        for (int i = c.tid; i < 4 * NPMAX; i += THREADS) qpart[i] = 0.f;
+
+        // ================= stage 1: h0 (CUDA cores), edge embeddings e =====================================
+        {   // h0 = ReLU(W_init x): thread owns features fa, fb and 4 vertices of every 16-vertex block (epilogue mapping)
+            const int fa = 16 * c.q + (c.lane >> 2), fb = fa + 8;
+            float wia[7], wib[7];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) { wia[k] = s_winit[fa * 7 + k]; wib[k] = s_winit[fb * 7 + k]; }
+            for (int blk = c.grp; blk < nsteps_A; blk += 2) {
+                float v[8];
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int n0 = 16 * blk + 8 * half + 2 * (c.lane & 3);
+                    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) {
+                        const float2 x = *reinterpret_cast<const float2*>(xf + k * NPMAX + n0);
+                        a0 = fmaf(wia[k], x.x, a0); a1 = fmaf(wia[k], x.y, a1);
+                        b0 = fmaf(wib[k], x.x, b0); b1 = fmaf(wib[k], x.y, b1);
+                    }
+                    v[4 * half + 0] = fmaxf(a0, 0.f); v[4 * half + 1] = fmaxf(a1, 0.f);
+                    v[4 * half + 2] = fmaxf(b0, 0.f); v[4 * half + 3] = fmaxf(b1, 0.f);
+                }
+                store_block(c, sH, 16 * blk, v);
+            }
+        }
         tmem_st_wait();
         cta_stage_sync();            // xf (overlaying group 1's chunk buffer) is dead from here; weights visible to the MMAs
-        for (int ci = c.grp; ci < nchunks; ci += 2) {
+        int slot = 0;                 // parity of the hand-out slot (all threads of a group advance it together)
+        for (int ci = c.grp; ci < nchunks;) {
             const int c0 = ci * CHUNK, width = min(CHUNK, NP - c0);
             // g = (S|A| + D A) / (2 deg); feature 63 = deg / deg_max   (mpnn.py:100-102)
             epilogue(c, T_ACC0, c0, width, [&](int bc, float (&v)[8]) {
@@ -396,23 +408,35 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                 }
                 store_block(c, sT, bc, v);
             });
+            if (c.q == 0 && c.lane == 0) next_s[c.grp][slot] = atomicAdd(&chunk_ctr[0], 1);
             grp_stage_sync(c);
             if (c.q == 0) {
                 tc_fence_after();
-                if (elect_one()) issue_linear(c, acc1, T_WEF, sT, 0, nullptr, 0, width);
+                if (elect_one()) { issue_part(c, acc1, T_WEF, sT, 0, width, false); mma_commit(c.bar_grp); }
                 __syncwarp();
             }
+            const int nxt = next_s[c.grp][slot];
+            slot ^= 1;
             wait_grp(c);
             epilogue(c, acc1, 0, width, [&](int bc, float (&v)[8]) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
                 store_block(c, sE, c0 + bc, v);
             });
+            ci = nxt;
         }
 
         // ================= stage 2: three message-passing layers (mpnn.py:114-120) ==========================
+        // per chunk:  m = ReLU(W_m [agg ; e]) accumulates in the group's ACC1, h' = ReLU(W_u [h ; m]) accumulates in the
+        // chunk's own (already consumed) columns of ACC0.  The halves that do not depend on the running epilogue
+        // (W_m e, W_u h) are issued ahead, so they execute while the group's warps are busy in the epilogue.
         float pool_a = 0.f, pool_b = 0.f;       // readout partials (last layer)
         for (int l = 0; l < 3; ++l) {
+            uint4 wm[8], wu[8];
+            if (l > 0) {                        // next weights: L2 -> registers, latency hidden behind the barrier
+                ldg_weights<64>(c, pk + PK_WM + l * 128 * 64, wm);
+                ldg_weights<64>(c, pk + PK_WU + l * 128 * 64, wu);
+            }
             cta_stage_sync();                   // every h / e column of the previous stage is written
             if (c.warp == 0) {                  // agg^T = H^T A  (both hi and lo rows in one M=128 chain)
               tc_fence_after();
@@ -427,27 +451,40 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
               }
               __syncwarp();
             }
-            if (l > 0) {                        // this layer's weights (the previous layer's MMAs all retired)
-                load_weights_tmem<64>(c, pk + PK_WM + l * 128 * 64, T_WM);
-                load_weights_tmem<64>(c, pk + PK_WU + l * 128 * 64, T_WU);
+            if (l > 0) {                        // the previous layer's MMAs all retired (barrier above): overwrite weights
+                sttm_weights<64>(c, wm, T_WM);
+                sttm_weights<64>(c, wu, T_WU);
                 tmem_st_wait();
                 tc_fence_before();
                 __syncthreads();
             }
+            int ci = c.grp;
+            if (ci < nchunks && c.q == 0) {     // W_m e-half of the first chunk does not depend on the aggregation
+                tc_fence_after();
+                if (elect_one()) issue_part(c, acc1, T_WM + 32, sE, (ci * CHUNK) >> 3, min(CHUNK, NP - ci * CHUNK), false);
+                __syncwarp();
+            }
             wait_all(c);
-            for (int ci = c.grp; ci < nchunks; ci += 2) {
+            while (ci < nchunks) {
                 const int c0 = ci * CHUNK, width = min(CHUNK, NP - c0);
                 epilogue(c, T_ACC0, c0, width, [&](int bc, float (&v)[8]) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] = v[i] * rdeg[c0 + bc + 8 * (i >> 2) + 2 * (c.lane & 3) + (i & 1)];
                     store_block(c, sT, bc, v);
                 });
+                if (c.q == 0 && c.lane == 0) next_s[c.grp][slot] = atomicAdd(&chunk_ctr[1 + l], 1);
                 grp_stage_sync(c);
-                if (c.q == 0) {                                                                // m = W_m [agg ; e]
+                if (c.q == 0) {
                     tc_fence_after();
-                    if (elect_one()) issue_linear(c, acc1, T_WM, sT, 0, sE, c0 >> 3, width);
+                    if (elect_one()) {
+                        issue_part(c, acc1, T_WM, sT, 0, width, true);                    // += W_m[:, :64] agg
+                        mma_commit(c.bar_grp);
+                        issue_part(c, T_ACC0 + c0, T_WU, sH, c0 >> 3, width, false);       // h-half of W_u, ahead
+                    }
                     __syncwarp();
                 }
+                const int nxt = next_s[c.grp][slot];
+                slot ^= 1;
                 wait_grp(c);
                 epilogue(c, acc1, 0, width, [&](int bc, float (&v)[8]) {
 #pragma unroll
@@ -455,14 +492,19 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                     store_block(c, sT, bc, v);
                 });
                 grp_stage_sync(c);
-                if (c.q == 0) {                                                                // h' = W_u [h ; m]
+                if (c.q == 0) {
                     tc_fence_after();
-                    if (elect_one()) issue_linear(c, acc1, T_WU, sH, c0 >> 3, sT, 0, width);
+                    if (elect_one()) {
+                        issue_part(c, T_ACC0 + c0, T_WU + 32, sT, 0, width, true);         // += W_u[:, 64:] m
+                        mma_commit(c.bar_grp);
+                        if (nxt < nchunks)                                               // next chunk's e-half, ahead
+                            issue_part(c, acc1, T_WM + 32, sE, (nxt * CHUNK) >> 3, min(CHUNK, NP - nxt * CHUNK), false);
+                    }
                     __syncwarp();
                 }
                 wait_grp(c);
                 if (l < 2) {
-                    epilogue(c, acc1, 0, width, [&](int bc, float (&v)[8]) {
+                    epilogue(c, T_ACC0, c0, width, [&](int bc, float (&v)[8]) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
                         store_block(c, sH, c0 + bc, v);
@@ -471,7 +513,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                     // readout partials straight from the fp32 registers (mpnn.py:143-159)
                     const int fa = 16 * c.q + (c.lane >> 2);
                     const float wa = s_wread[64 + fa], wb = s_wread[64 + fa + 8];
-                    epilogue(c, acc1, 0, width, [&](int bc, float (&v)[8]) {
+                    epilogue(c, T_ACC0, c0, width, [&](int bc, float (&v)[8]) {
                         float qv[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {     // j: columns {0,1,8,9} + 2(lane&3)
@@ -494,6 +536,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                         }
                     });
                 }
+                ci = nxt;
             }
         }
 
