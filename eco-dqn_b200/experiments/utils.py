@@ -1,0 +1,185 @@
+"""Drop-in for reference experiments/utils.py on the rollout path: `test_network` (the batched greedy-Q driver plus
+the Greedy baselines) and the graph loaders.  Same signature, same DataFrame columns, same consumption of the
+global numpy RNG for the random initial spins -- but every episode of every same-sized graph is stepped on the
+device in one batch, with no host round trip per step.
+
+reference experiments/utils.py:22-31 (test_network), :33-303 (__test_network_batched), :391-432 (loaders).
+"""
+import os
+import pickle
+import time
+from collections import namedtuple
+
+import networkx as nx
+import numpy as np
+import pandas as pd
+import scipy as sp
+import torch
+
+from .. import engine
+from ..envs.spinsystem import check_supported
+from ..envs.utils import DEFAULT_OBSERVABLES, RewardSignal, ExtraAction, OptimisationTarget, SpinBasis, Stopping
+
+
+def _weights_of(network, device):
+    if isinstance(network, engine.MPNNWeights):
+        return network
+    if hasattr(network, "engine_weights"):
+        return network.engine_weights(device)
+    if hasattr(network, "state_dict"):
+        return engine.MPNNWeights(network.state_dict(), device=device)
+    return engine.MPNNWeights(network, device=device)       # a plain dict keyed like the reference's state_dict
+
+
+def _check_env_args(env_args, n_steps):
+    a = dict(observables=DEFAULT_OBSERVABLES, reward_signal=RewardSignal.DENSE, extra_action=ExtraAction.PASS,
+             optimisation_target=OptimisationTarget.ENERGY, spin_basis=SpinBasis.SIGNED, norm_rewards=False,
+             memory_length=None, horizon_length=None, stag_punishment=None, basin_reward=None, reversible_spins=True,
+             init_snap=None, stopping=Stopping.NORMAL)          # SpinSystemFactory.get defaults (spinsystem.py:30-45)
+    a.update(env_args)
+    check_supported(a["observables"], a["reward_signal"], a["extra_action"], a["optimisation_target"], a["spin_basis"],
+                    a["norm_rewards"], a["memory_length"], a["horizon_length"], a["stag_punishment"],
+                    a["reversible_spins"], a["init_snap"], a["stopping"], n_steps)
+    return a
+
+
+def test_network(network, env_args, graphs_test, device=None, step_factor=1, batched=True,
+                 n_attempts=50, return_raw=False, return_history=False, max_batch_size=None):
+    if not batched:
+        # the reference's sequential tester calls a method that does not exist (experiments/utils.py:343)
+        raise NotImplementedError("only the batched tester is supported (the reference's sequential one is broken)")
+    if device is None:
+        device = "cuda"
+    dev = engine._require_cuda(device)
+    weights = _weights_of(network, dev)
+
+    graphs_test = [np.asarray(g) for g in graphs_test]
+    n_graphs = len(graphs_test)
+    results, results_raw, history = [None] * n_graphs, [None] * n_graphs, [None] * n_graphs
+
+    # The reference walks the graphs in order and, per graph, draws (1 + n_attempts) x N random spins from numpy's
+    # global RNG: N for the constructor's reset (spinsystem.py:168,294), then N per episode (experiments/utils.py:154).
+    init = []
+    for g in graphs_test:
+        n = g.shape[0]
+        np.random.randint(2, size=n)
+        init.append(np.stack([2 * np.random.randint(2, size=n) - 1 for _ in range(n_attempts)]).astype(np.int8))
+
+    # group graphs of equal size: one graph set, one batch of len(group) x n_attempts episodes
+    groups = {}
+    for j, g in enumerate(graphs_test):
+        groups.setdefault(g.shape[0], []).append(j)
+    for n, idxs in groups.items():
+        n_steps = int(n * step_factor)
+        args = _check_env_args(env_args, n_steps)
+        gs = engine.GraphSet(np.stack([graphs_test[j] for j in idxs]), device=dev)
+        G = len(idxs)
+        B = G * n_attempts
+        gidx = np.repeat(np.arange(G, dtype=np.int32), n_attempts)
+        spins = np.concatenate([init[j] for j in idxs])
+
+        env = engine.BatchedSpinSystem(gs, B, n_steps, args["basin_reward"])
+        env.reset(spins=spins, graph_idx=gidx)
+        scores0 = env.episodes()["score"].copy() if return_history else None
+        torch.cuda.synchronize(dev)
+        t_start = time.time()
+        hist = env.rollout(weights, record_history=return_history)
+        best_cut, best_spins, _ = env.results()
+        torch.cuda.synchronize(dev)
+        t_total = time.time() - t_start
+        best_cut = best_cut.cpu().numpy().astype(np.float64)
+        best_spins = best_spins.cpu().numpy().astype(np.float64)
+
+        # Greedy baselines (experiments/utils.py:100-111, 218-227): from the same random starts, and from all -1
+        env.reset(spins=spins, graph_idx=gidx)
+        env.rollout(policy="greedy")
+        g_cut, g_spins, _ = env.results()
+        g_cut = g_cut.cpu().numpy().astype(np.float64)
+        g_spins = g_spins.cpu().numpy().astype(np.float64)
+        env1 = engine.BatchedSpinSystem(gs, G, n_steps, args["basin_reward"])
+        env1.reset(spins=-np.ones((G, n), dtype=np.int8), graph_idx=np.arange(G, dtype=np.int32))
+        env1.rollout(policy="greedy")
+        s_cut, s_spins, _ = env1.results()
+        s_cut = s_cut.cpu().numpy().astype(np.float64)
+        s_spins = s_spins.cpu().numpy().astype(np.float64)
+        if return_history:
+            ha, hr, hs = (h.cpu().numpy() for h in hist)
+
+        for k, j in enumerate(idxs):
+            sl = slice(k * n_attempts, (k + 1) * n_attempts)
+            cuts = best_cut[sl]
+            i_best = int(np.argmax(cuts))
+            ig = int(np.argmax(g_cut[sl]))
+            results[j] = [cuts[i_best], best_spins[sl][i_best], np.mean(cuts),
+                          s_cut[k], s_spins[k],
+                          g_cut[sl][ig], g_spins[sl][ig], np.mean(g_cut[sl]),
+                          t_total / B]
+            results_raw[j] = [[s.astype(np.float64) for s in init[j]], list(cuts), list(best_spins[sl]),
+                              list(g_cut[sl]), list(g_spins[sl])]
+            if return_history:
+                acts = [[None] + [int(a) for a in row] for row in ha[sl]]
+                rews = [[None] + [float(r) for r in row] for row in hr[sl]]
+                scs = [[float(s0)] + [float(s) for s in row] for s0, row in zip(scores0[sl], hs[sl])]
+                history[j] = [acts, scs, rews]
+            print('Graph {}, best(mean) cut: {}({}), greedy cut (rand init / +1 init) : {} / {}.  ({} attempts in {}s)'.format(
+                j, cuts[i_best], np.mean(cuts), g_cut[sl][ig], s_cut[k], n_attempts, np.round(t_total * n_attempts / B, 4)))
+
+    results = pd.DataFrame(data=results, columns=["cut", "sol", "mean cut",
+                                                  "greedy (+1 init) cut", "greedy (+1 init) sol",
+                                                  "greedy (rand init) cut", "greedy (rand init) sol",
+                                                  "greedy (rand init) mean cut", "time"])
+    results_raw = pd.DataFrame(data=results_raw, columns=["init spins", "cuts", "sols", "greedy cuts", "greedy sols"])
+    if return_history:
+        history = pd.DataFrame(data=history, columns=["actions", "scores", "rewards"])
+    if return_raw == False and return_history == False:
+        return results
+    ret = [results]
+    if return_raw:
+        ret.append(results_raw)
+    if return_history:
+        ret.append(history)
+    return ret
+
+
+Graph = namedtuple('Graph', 'name n_vertices n_edges matrix bk_val bk_sol')
+
+
+def load_graph(graph_dir, graph_name):
+    """GSet-style instance + best-known value/solution files (reference experiments/utils.py:391-418)."""
+    matrix = None
+    with open(os.path.join(graph_dir, 'instances', graph_name + '.mc')) as f:
+        for line in f:
+            arr = list(map(int, line.strip().split(' ')))
+            if len(arr) == 2:
+                n_vertices, n_edges = arr
+                matrix = np.zeros((n_vertices, n_vertices))
+            else:
+                assert type(matrix) == np.ndarray, 'First line in file should define graph dimensions.'
+                i, j, w = arr[0] - 1, arr[1] - 1, arr[2]
+                matrix[[i, j], [j, i]] = w
+    with open(os.path.join(graph_dir, 'bkvl', graph_name + '.bkvl')) as f:
+        bk_val = float(f.readline())
+    with open(os.path.join(graph_dir, 'bksol', graph_name + '.bksol')) as f:
+        bk_sol = np.array([int(x) for x in list(f.readline().strip())] + [np.random.choice([0, 1])])
+    return Graph(graph_name, n_vertices, n_edges, matrix, bk_val, bk_sol)
+
+
+def load_graph_set(graph_save_loc):
+    """Pickled list of ndarray / nx.Graph / scipy csr graphs -> list of dense arrays (experiments/utils.py:420-432)."""
+    with open(graph_save_loc, 'rb') as f:
+        graphs_test = pickle.load(f)
+
+    def graph_to_array(g):
+        if type(g) == nx.Graph:
+            g = nx.to_numpy_array(g)
+        elif type(g) == sp.sparse.csr_matrix:
+            g = g.toarray()
+        return g
+
+    graphs_test = [graph_to_array(g) for g in graphs_test]
+    print('{} target graphs loaded from {}'.format(len(graphs_test), graph_save_loc))
+    return graphs_test
+
+
+def mk_dir(export_dir, quite=False):
+    os.makedirs(export_dir, exist_ok=True)

@@ -243,6 +243,21 @@ def main():
                         er20=np.stack(er20[:16]).astype(np.int8), er20_opt=cuts20[:16])
     print("wrote graphsets.npz")
 
+    # Graph generators (reference src/envs/utils.py:165-236): same seeds -> same graphs in the host-side mirror.
+    import random
+    from src.envs.utils import RandomErdosRenyiGraphGenerator, RandomBarabasiAlbertGraphGenerator, EdgeType
+    out = {}
+    for tag, make_gen in (("er20", lambda: RandomErdosRenyiGraphGenerator(20, 0.15, EdgeType.DISCRETE)),
+                          ("er40u", lambda: RandomErdosRenyiGraphGenerator(40, [0.15, 0.02], EdgeType.UNIFORM)),
+                          ("ba20", lambda: RandomBarabasiAlbertGraphGenerator(20, 4, EdgeType.DISCRETE)),
+                          ("ba60u", lambda: RandomBarabasiAlbertGraphGenerator(60, 4, EdgeType.UNIFORM))):
+        np.random.seed(123)
+        random.seed(123)
+        gen = make_gen()
+        out[tag] = np.stack([gen.get() for _ in range(3)]).astype(np.int8)
+    np.savez_compressed(os.path.join(HERE, "generators.npz"), **out)
+    print("wrote generators.npz")
+
 
 if __name__ == "__main__":
     main()
