@@ -1,0 +1,372 @@
+"""Double-DQN trainer on the batched device engine (reference src/agents/dqn/dqn.py:20-610, BASELINE config 5).
+
+Same constructor keywords, same update rule (dqn.py:403-451: Double-DQN target, MSE / Huber, Adam, optional
+gradient clipping), same schedules (dqn.py:467-487), same evaluation metric and checkpoint format (dqn.py:604-610,
+`torch.save(state_dict)`).  What changes is where the work runs:
+
+  * acting: `n_envs` episodes step in lock-step on the device (n_envs = 1 is the reference's schedule); the greedy
+    branch is the fused MPNN + argmax kernel, evaluated per environment like the reference's B = 1 forward;
+  * replay: compact device-resident transitions (agents/dqn/utils.py) pointing into a device ring of graphs;
+  * update: target Q-values come from the CUDA forward kernels; the online forward/backward runs through PyTorch
+    autograd on the reference-compatible MPNN module; with several ranks the gradients are averaged with ONE
+    all-reduce over a flat buffer (NCCL over NVLink), then every rank applies the same Adam step.
+"""
+import os
+import pickle
+import random
+import time
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+import torch.optim as optim
+
+from ... import engine, sharding
+from ..._lib import lib, check
+from .utils import ReplayBuffer, TestMetric, set_global_seed
+
+import ctypes as C
+
+
+class DQN:
+    def __init__(self, envs, network, init_network_params=None, init_weight_std=None, double_dqn=True,
+                 update_target_frequency=10000, gamma=0.99, clip_Q_targets=False, replay_start_size=50000,
+                 replay_buffer_size=1000000, minibatch_size=32, update_frequency=1, update_learning_rate=True,
+                 initial_learning_rate=0, peak_learning_rate=1e-3, peak_learning_rate_step=10000,
+                 final_learning_rate=5e-5, final_learning_rate_step=200000, max_grad_norm=None, weight_decay=0,
+                 update_exploration=True, initial_exploration_rate=1, final_exploration_rate=0.1,
+                 final_exploration_step=1000000, adam_epsilon=1e-8, loss="mse", save_network_frequency=10000,
+                 network_save_path='network', evaluate=True, test_envs=None, test_episodes=20, test_frequency=10000,
+                 test_save_path='test_scores', test_metric=TestMetric.ENERGY_ERROR, logging=True, seed=None, n_envs=1):
+        self.device = engine._require_cuda()
+        self.rank, self.world = sharding.world_info()
+        self.double_dqn = double_dqn
+        self.replay_start_size = replay_start_size
+        self.replay_buffer_size = replay_buffer_size
+        self.gamma = gamma
+        self.clip_Q_targets = clip_Q_targets
+        self.update_target_frequency = update_target_frequency
+        self.minibatch_size = minibatch_size
+        self.update_learning_rate = update_learning_rate
+        self.initial_learning_rate = initial_learning_rate
+        self.peak_learning_rate = peak_learning_rate
+        self.peak_learning_rate_step = peak_learning_rate_step
+        self.final_learning_rate = final_learning_rate
+        self.final_learning_rate_step = final_learning_rate_step
+        self.max_grad_norm = max_grad_norm
+        self.weight_decay = weight_decay
+        self.update_frequency = update_frequency
+        self.update_exploration = True        # the reference stores a 1-tuple here, which is always truthy (dqn.py:161)
+        self.initial_exploration_rate = initial_exploration_rate
+        self.epsilon = self.initial_exploration_rate
+        self.final_exploration_rate = final_exploration_rate
+        self.final_exploration_step = final_exploration_step
+        self.adam_epsilon = adam_epsilon
+        self.logging = logging
+        if callable(loss):
+            self.loss = loss
+        else:
+            try:
+                self.loss = {'huber': F.smooth_l1_loss, 'mse': F.mse_loss}[loss]
+            except KeyError:
+                raise ValueError("loss must be 'huber', 'mse' or a callable")
+        if test_metric not in (TestMetric.BEST, TestMetric.FINAL):
+            raise NotImplementedError("test_metric must be TestMetric.BEST or TestMetric.FINAL on this path")
+
+        if type(envs) != list:
+            envs = [envs]
+        self.envs = envs
+        if len(set(e.n_spins for e in envs)) != 1 or len(set(e.max_steps for e in envs)) != 1:
+            raise NotImplementedError("all training environments must share n_spins and max_steps")
+        if any(not e.reversible_spins for e in envs):
+            raise NotImplementedError("irreversible (S2V-DQN) environments are outside the accelerated path")
+        self.acting_in_reversible_spin_env = True
+        self.n_spins, self.max_steps = envs[0].n_spins, envs[0].max_steps
+        self.basin_reward = envs[0].basin_reward
+        self.n_envs = int(n_envs)
+
+        self.seed = random.randint(0, int(1e6)) if seed is None else seed      # dqn.py:187 (int() for Python 3.12)
+        set_global_seed(self.seed + self.rank)
+        self._gen = torch.Generator(device=self.device)
+        self._gen.manual_seed(self.seed + 7919 * self.rank)
+
+        self.network = network().to(self.device)
+        self.init_network_params = init_network_params
+        self.init_weight_std = init_weight_std
+        if init_network_params is not None:
+            self.load(init_network_params)
+        elif init_weight_std is not None:
+            with torch.no_grad():
+                for m in self.network.modules():
+                    if type(m) == torch.nn.Linear:
+                        m.weight.normal_(0, init_weight_std)
+        if self.world > 1:                       # every rank starts from rank 0's parameters
+            for p in self.network.parameters():
+                torch.distributed.broadcast(p.data, src=0)
+        self.target_network = network().to(self.device)
+        self.target_network.load_state_dict(self.network.state_dict())
+        for p in self.target_network.parameters():
+            p.requires_grad = False
+        self.optimizer = optim.Adam(self.network.parameters(), lr=self.initial_learning_rate, eps=self.adam_epsilon,
+                                    weight_decay=self.weight_decay)
+
+        self.evaluate = evaluate
+        if test_envs in [None, [None]]:
+            self.test_envs = self.envs
+        else:
+            self.test_envs = test_envs if type(test_envs) == list else [test_envs]
+        self.test_episodes = int(test_episodes)
+        self.test_frequency = test_frequency
+        self.test_save_path = test_save_path
+        self.test_metric = test_metric
+        self.losses_save_path = os.path.join(os.path.split(self.test_save_path)[0], "losses.pkl")
+        self.solution_save_path = os.path.join(os.path.split(self.test_save_path)[0], "solution.pkl")
+        self.allowed_action_state = (-1, 1)
+        self.save_network_frequency = save_network_frequency
+        self.network_save_path = network_save_path
+
+        # ---- device state: graph ring, lock-step environments, replay --------------------------------------
+        n, T, E = self.n_spins, self.max_steps, self.n_envs
+        self._ring_size = int(np.ceil(replay_buffer_size / T)) + 2 * E + 2
+        first = [self._new_graph() for _ in range(E)]
+        ring = np.zeros((self._ring_size, n, n), dtype=np.int8)
+        ring[:] = engine.graphs_to_int8(first[0])[0]          # placeholder so that every slot holds a valid graph
+        self._graphs = engine.GraphSet(ring, device=self.device)
+        self._ring_pos = 0
+        self._env = engine.BatchedSpinSystem(self._graphs, E, T, self.basin_reward)
+        self.replay_buffer = ReplayBuffer(replay_buffer_size, self._env.NP, self.device)
+        self.replay_buffers = {n: self.replay_buffer}
+        self._start_episodes(first)
+
+    # ------------------------------------------------------------------ environment plumbing
+    def _new_graph(self):
+        env = random.sample(self.envs, k=1)[0]                # get_random_env, dqn.py:242-248
+        return np.asarray(env.gg.get())
+
+    def _write_ring(self, graphs):
+        """Put `graphs` into consecutive ring slots (wrapping) and return the slot indices."""
+        E = len(graphs)
+        slots = [(self._ring_pos + i) % self._ring_size for i in range(E)]
+        self._ring_pos = (self._ring_pos + E) % self._ring_size
+        J = torch.from_numpy(engine.graphs_to_int8(np.stack(graphs))).to(self.device)
+        start = 0
+        while start < E:                                      # contiguous runs (at most two: the ring wraps once)
+            run = 1
+            while start + run < E and slots[start + run] == slots[start + run - 1] + 1:
+                run += 1
+            check(lib().eco_graphs_update(C.byref(self._graphs.c), slots[start], run,
+                                          C.c_void_p(J[start:start + run].contiguous().data_ptr()), engine._stream()))
+            start += run
+        torch.cuda.current_stream().synchronize()
+        flags = self._graphs.gstat[torch.tensor(slots, device=self.device), 3].cpu().numpy()
+        if (flags & 7).any():
+            raise NotImplementedError("training graphs must be symmetric, non-empty, with couplings in {-1,0,1}")
+        return np.array(slots, dtype=np.int32)
+
+    def _start_episodes(self, graphs=None):
+        E = self.n_envs
+        if graphs is None:
+            graphs = [self._new_graph() for _ in range(E)]
+        slots = self._write_ring(graphs)
+        spins = np.stack([2 * np.random.randint(2, size=self.n_spins) - 1 for _ in range(E)])   # spinsystem.py:294
+        self._env.reset(spins=spins, graph_idx=slots)
+        self._scores = torch.zeros(E, dtype=torch.float64, device=self.device)
+
+    def _obs_from(self, xn, xg, graph):
+        """[B, 7 + N, N] fp32 observations in the reference's layout, rebuilt on the device for the autograd forward."""
+        n = self.n_spins
+        rows = torch.cat([xn[:, :, :n], xg.unsqueeze(-1).expand(-1, -1, n)], dim=1)
+        adj = self._graphs.J[graph.long(), :n, :n].to(torch.float32)
+        return torch.cat([rows, adj], dim=1)
+
+    def _q_kernel(self, network, xn, xg, graph, norm_max, want_q=True):
+        """Q-values / argmax through the CUDA forward kernels for arbitrary (replayed) features."""
+        B = xn.shape[0]
+        w = network.engine_weights(self.device)
+        q = torch.zeros(B, self._env.NP, dtype=torch.float32, device=self.device) if want_q else None
+        act = torch.zeros(B, dtype=torch.int32, device=self.device)
+        scratch = self._env._scratch_for(B)
+        xn, xg, graph = xn.contiguous(), xg.contiguous(), graph.to(torch.int32).contiguous()
+        check(lib().eco_mpnn_forward(C.byref(self._graphs.c), C.byref(w.c), B, engine._ptr(graph), engine._ptr(xn),
+                                     engine._ptr(xg), float(norm_max), engine._ptr(q), engine._ptr(act),
+                                     engine._ptr(scratch), self._env.mpnn_impl, engine._stream()))
+        return (q[:, :self.n_spins] if want_q else None), act
+
+    # ------------------------------------------------------------------ learning
+    def learn(self, timesteps, verbose=False):
+        E = self.n_envs
+        env = self._env
+        losses, test_scores, test_solutions, losses_eps = [], [], [], []
+        is_training_ready = False
+        t1 = time.time()
+        timestep = 0
+        while timestep < timesteps:
+            if not is_training_ready and len(self.replay_buffer) >= self.replay_start_size:
+                print('\nAll buffers have {} transitions stored - training is starting!\n'.format(self.replay_start_size))
+                is_training_ready = True
+
+            xn, xg, graph = env.xn.clone(), env.xg.clone(), env.graph_idx.clone()
+            actions = self.act((xn, xg, graph), is_training_ready)
+            if self.update_exploration:
+                self.update_epsilon(timestep)
+            if self.update_learning_rate:
+                self.update_lr(timestep)
+            reward, done = env.step(actions)
+            self._scores += reward
+            self.replay_buffer.add(xn, xg, actions, reward, env.xn, env.xg, done, graph)
+            t_before, timestep = timestep, timestep + E
+
+            if env.current_step == self.max_steps:            # lock-step: every episode ends together
+                if verbose:
+                    loss_str = "{:.2e}".format(np.mean(losses_eps)) if (is_training_ready and losses_eps) else "N/A"
+                    print("timestep : {}, episode time: {}, score : {}, mean loss: {}, time : {} s".format(
+                        timestep, env.current_step, np.round(float(self._scores.mean()), 3), loss_str,
+                        round(time.time() - t1, 3)))
+                self._start_episodes()
+                losses_eps = []
+                t1 = time.time()
+
+            if is_training_ready:
+                for _ in range(self._crossings(t_before, timestep, self.update_frequency)):
+                    loss = self.train_step(self.replay_buffer.sample(self.minibatch_size, self._gen))
+                    losses.append([timestep, loss])
+                    losses_eps.append(loss)
+                if self._crossings(t_before, timestep, self.update_target_frequency):
+                    self.target_network.load_state_dict(self.network.state_dict())
+
+            if self._crossings(t_before + 1, timestep + 1, self.test_frequency) and self.evaluate and is_training_ready:
+                test_score, test_solution = self.evaluate_agent()
+                print('\nTest score: {}\nTest solution: {}\n'.format(np.round(test_score, 3), np.round(test_solution, 3)))
+                if all(test_score > s for _, s in test_scores) and self.rank == 0:
+                    main, ext = os.path.splitext(self.network_save_path)
+                    self.save(main + "_best" + (ext if ext else '.pth'))
+                test_scores.append([timestep, test_score])
+                test_solutions.append([timestep, test_solution])
+            if self._crossings(t_before + 1, timestep + 1, self.save_network_frequency) and is_training_ready \
+                    and self.rank == 0:
+                main, ext = os.path.splitext(self.network_save_path)
+                self.save(main + str(timestep) + (ext if ext else '.pth'))
+
+        if self.rank == 0:
+            path = self.test_save_path if os.path.splitext(self.test_save_path)[-1] else self.test_save_path + '.pkl'
+            for p, obj in ((path, test_scores), (self.losses_save_path, losses), (self.solution_save_path, test_solutions)):
+                if os.path.dirname(p):
+                    os.makedirs(os.path.dirname(p), exist_ok=True)
+                with open(p, 'wb+') as output:
+                    pickle.dump(np.array(obj), output, pickle.HIGHEST_PROTOCOL)
+        return losses
+
+    @staticmethod
+    def _crossings(t0, t1, period):
+        """How many multiples of `period` lie in [t0, t1): the reference tests `timestep % period == 0` once per step."""
+        if period <= 0:
+            return 0
+        return (t1 + period - 1) // period - (t0 + period - 1) // period
+
+    def train_step(self, transitions):
+        """reference dqn.py:403-451 on a dict of compact transitions (see ReplayBuffer.FIELDS)."""
+        t = transitions
+        graph = t["graph"]
+        with torch.no_grad():
+            # the reference feeds the whole minibatch through the network: norm.max() is the batch's max degree
+            norm_max = float(self._graphs.gstat[graph.long(), 0].max().clamp(min=1).item())
+            if self.double_dqn:
+                _, greedy = self._q_kernel(self.network, t["xn_next"], t["xg_next"], graph, norm_max, want_q=False)
+                q_tgt, _ = self._q_kernel(self.target_network, t["xn_next"], t["xg_next"], graph, norm_max)
+                q_value_target = q_tgt.gather(1, greedy.long().unsqueeze(1))
+            else:
+                q_tgt, _ = self._q_kernel(self.target_network, t["xn_next"], t["xg_next"], graph, norm_max)
+                q_value_target = q_tgt.max(1, True)[0]
+            if self.clip_Q_targets:
+                q_value_target[q_value_target < 0] = 0
+            td_target = t["reward"].unsqueeze(1) + (1 - t["done"].unsqueeze(1)) * self.gamma * q_value_target
+
+        q_all = self.network(self._obs_from(t["xn"], t["xg"], graph))
+        if q_all.dim() == 1:
+            q_all = q_all.unsqueeze(0)
+        q_value = q_all.gather(1, t["action"].unsqueeze(1))
+        loss = self.loss(q_value, td_target, reduction='mean')
+        self.optimizer.zero_grad()
+        loss.backward()
+        if self.world > 1:
+            self._allreduce_grads()
+        if self.max_grad_norm is not None:
+            torch.nn.utils.clip_grad_norm_(self.network.parameters(), self.max_grad_norm)
+        self.optimizer.step()
+        return loss.item()
+
+    def _allreduce_grads(self):
+        """One collective per update: flatten the 12 gradient tensors (58 425 floats), average, scatter back."""
+        params = [p for p in self.network.parameters() if p.grad is not None]
+        flat = torch.cat([p.grad.reshape(-1) for p in params])
+        sharding.allreduce_mean_(flat)
+        off = 0
+        for p in params:
+            n = p.grad.numel()
+            p.grad.copy_(flat[off:off + n].view_as(p.grad))
+            off += n
+
+    def act(self, state, is_training_ready=True):
+        """epsilon-greedy for all lock-step environments (reference dqn.py:453-465, one environment there)."""
+        xn, xg, graph = state
+        E = xn.shape[0]
+        rand_actions = torch.randint(0, self.n_spins, (E,), device=self.device, generator=self._gen, dtype=torch.int32)
+        if not is_training_ready:
+            return rand_actions
+        greedy = self.predict(state)
+        explore = torch.rand(E, device=self.device, generator=self._gen) < self.epsilon
+        return torch.where(explore, rand_actions, greedy)
+
+    @torch.no_grad()
+    def predict(self, states, acting_in_reversible_spin_env=None):
+        """argmax_a Q(s, a) per environment; every environment is normalised by its own graph, like the reference's
+        one-environment forward (dqn.py:490-503)."""
+        xn, xg, graph = states
+        return self._q_kernel(self.network, xn, xg, graph, -1.0, want_q=False)[1]
+
+    def update_epsilon(self, timestep):
+        eps = self.initial_exploration_rate - (self.initial_exploration_rate - self.final_exploration_rate) * (
+            timestep / self.final_exploration_step)
+        self.epsilon = max(eps, self.final_exploration_rate)
+
+    def update_lr(self, timestep):
+        if timestep <= self.peak_learning_rate_step:
+            lr = self.initial_learning_rate - (self.initial_learning_rate - self.peak_learning_rate) * (
+                timestep / self.peak_learning_rate_step)
+        elif timestep <= self.final_learning_rate_step:
+            lr = self.peak_learning_rate - (self.peak_learning_rate - self.final_learning_rate) * (
+                (timestep - self.peak_learning_rate_step) / (self.final_learning_rate_step - self.peak_learning_rate_step))
+        else:
+            lr = None
+        if lr is not None:
+            for g in self.optimizer.param_groups:
+                g['lr'] = lr
+
+    @torch.no_grad()
+    def evaluate_agent(self, batch_size=None):
+        """Greedy-Q rollouts of `test_episodes` episodes on random test environments, all in one device batch
+        (reference dqn.py:514-602).  Returns (mean score, mean solution) for TestMetric.BEST / FINAL."""
+        k = self.test_episodes
+        envs = [random.sample(self.test_envs, k=1)[0] for _ in range(k)]
+        graphs = np.stack([np.asarray(e.gg.get()) for e in envs])
+        spins = np.stack([2 * np.random.randint(2, size=self.n_spins) - 1 for _ in range(k)])
+        gs = engine.GraphSet(graphs, device=self.device)
+        env = engine.BatchedSpinSystem(gs, k, envs[0].max_steps, envs[0].basin_reward)
+        env.reset(spins=spins, graph_idx=np.arange(k, dtype=np.int32))
+        env.rollout(self.network.engine_weights(self.device))
+        ep = env.episodes()
+        lb = gs.lb.cpu().numpy()
+        if self.test_metric == TestMetric.BEST:
+            scores, sols = ep["best_score"], ep["best_cut"].astype(np.float64)
+        else:
+            scores, sols = ep["score"], ep["cut"].astype(np.float64)
+        assert np.allclose(scores - np.abs(np.minimum(0, lb)), sols)
+        return (np.mean(scores), np.mean(sols))
+
+    def save(self, path='network.pth'):
+        if os.path.dirname(path):
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+        torch.save(self.network.state_dict(), path)
+
+    def load(self, path):
+        self.network.load_state_dict(torch.load(path, map_location=self.device))

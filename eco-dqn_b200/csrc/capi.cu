@@ -97,8 +97,8 @@ __global__ void dmax_kernel(const eco_graphs_t g) {
     if (threadIdx.x == 0) g.dmax[0] = (float)m;
 }
 
-static int prepare(const eco_graphs_t* g, cudaStream_t st) {
-    int rc = launch_graph_prepare(g, st);
+static int prepare(const eco_graphs_t* g, cudaStream_t st, int first = 0, int count = -1) {
+    int rc = launch_graph_prepare(g, first, count < 0 ? g->G : count, st);
     if (rc != ECO_OK) return rc;
     dmax_kernel<<<1, 32, 0, st>>>(*g);
     ECO_LAUNCH_CHECK();
@@ -189,9 +189,19 @@ int eco_graphs_upload(eco_graphs_t* g, const int8_t* J_host, void* stream) {
 int eco_graphs_load_dev(eco_graphs_t* g, const int8_t* J_dev, void* stream) {
     ECO_CHECK_ARG(g && J_dev && g->J, ECO_ERR_INVALID, "eco_graphs_load_dev: null argument");
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = launch_graph_pad(g, J_dev, st);
+    int rc = launch_graph_pad(g, J_dev, 0, g->G, st);
     if (rc != ECO_OK) return rc;
     return prepare(g, st);
+}
+
+int eco_graphs_update(eco_graphs_t* g, int32_t first, int32_t count, const int8_t* J_dev, void* stream) {
+    ECO_CHECK_ARG(g && J_dev && g->J, ECO_ERR_INVALID, "eco_graphs_update: null argument");
+    ECO_CHECK_ARG(first >= 0 && count >= 1 && first + count <= g->G, ECO_ERR_INVALID,
+                  "eco_graphs_update: slots [%d, %d) outside the set of %d graphs", first, first + count, g->G);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_graph_pad(g, J_dev, first, count, st);
+    if (rc != ECO_OK) return rc;
+    return prepare(g, st, first, count);
 }
 
 // ------------------------------------------------------------------------------------------------ env

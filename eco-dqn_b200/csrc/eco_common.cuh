@@ -70,8 +70,8 @@ __device__ __forceinline__ int group_max(int v) {
 }
 
 // ---- internal launchers (one translation unit each) -------------------------------------------------------
-int launch_graph_prepare(const eco_graphs_t* g, cudaStream_t st);
-int launch_graph_pad(const eco_graphs_t* g, const int8_t* dense_dev, cudaStream_t st);
+int launch_graph_prepare(const eco_graphs_t* g, int first, int count, cudaStream_t st);
+int launch_graph_pad(const eco_graphs_t* g, const int8_t* dense_dev, int first, int count, cudaStream_t st);
 int launch_env_reset(const eco_graphs_t* g, eco_env_t* env, const int32_t* gidx, const int8_t* spins, cudaStream_t st);
 int launch_env_step(const eco_graphs_t* g, eco_env_t* env, int policy, const int32_t* actions, double* reward,
                     uint8_t* done, int32_t* ha, double* hr, double* hs, cudaStream_t st);

@@ -11,6 +11,7 @@
 namespace eco {
 
 __global__ void graph_pad_kernel(const int8_t* __restrict__ dense, int8_t* __restrict__ J, int G, int N, int NP) {
+    // `dense` holds G graphs; J points at the first padded slot they go to
     // one thread per 16-byte chunk of the padded layout
     const size_t chunks_per_row = NP / 16;
     const size_t total = (size_t)G * NP * chunks_per_row;
@@ -33,8 +34,8 @@ __global__ void graph_pad_kernel(const int8_t* __restrict__ dense, int8_t* __res
 }
 
 // one CTA per graph, one warp per row (strided)
-__global__ void __launch_bounds__(256) graph_prepare_kernel(eco_graphs_t g) {
-    const int gi = blockIdx.x;
+__global__ void __launch_bounds__(256) graph_prepare_kernel(eco_graphs_t g, int first) {
+    const int gi = first + blockIdx.x;
     const int N = g.N, NP = g.NP;
     const int8_t* J = g.J + (size_t)gi * NP * NP;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
@@ -98,16 +99,16 @@ __global__ void __launch_bounds__(256) graph_prepare_kernel(eco_graphs_t g) {
     }
 }
 
-int launch_graph_pad(const eco_graphs_t* g, const int8_t* dense_dev, cudaStream_t st) {
-    const size_t total = (size_t)g->G * g->NP * (g->NP / 16);
+int launch_graph_pad(const eco_graphs_t* g, const int8_t* dense_dev, int first, int count, cudaStream_t st) {
+    const size_t total = (size_t)count * g->NP * (g->NP / 16);
     const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-    graph_pad_kernel<<<blocks, 256, 0, st>>>(dense_dev, g->J, g->G, g->N, g->NP);
+    graph_pad_kernel<<<blocks, 256, 0, st>>>(dense_dev, g->J + (size_t)first * g->NP * g->NP, count, g->N, g->NP);
     ECO_LAUNCH_CHECK();
     return ECO_OK;
 }
 
-int launch_graph_prepare(const eco_graphs_t* g, cudaStream_t st) {
-    graph_prepare_kernel<<<g->G, 256, 0, st>>>(*g);
+int launch_graph_prepare(const eco_graphs_t* g, int first, int count, cudaStream_t st) {
+    graph_prepare_kernel<<<count, 256, 0, st>>>(*g, first);
     ECO_LAUNCH_CHECK();
     return ECO_OK;
 }

@@ -116,7 +116,7 @@ mpnn_simt_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const in
     float* E = cta + (size_t)2 * NP * F;  // edge embeddings
     float* P = cta + (size_t)3 * NP * F;  // X W_x^T (63 used)
     float* xs = S.xs[warp];
-    const float dmax = norm_max > 0.f ? norm_max : *g.dmax;
+    const float dmax_set = norm_max > 0.f ? norm_max : *g.dmax;
     const int ntiles = (N + TILE - 1) / TILE;
 
     for (int i = tid; i < 64 * 7; i += blockDim.x) S.w_init[i] = w.w_init[i];
@@ -129,6 +129,7 @@ mpnn_simt_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const in
         const float* deg = g.deg + (size_t)gi * NP;
         const float* x0 = xn + (size_t)b * 3 * NP;
         const float4 xgl = *reinterpret_cast<const float4*>(xg + (size_t)b * 4);
+        const float dmax = norm_max < 0.f ? (float)max(g.gstat[(size_t)gi * 4], 1) : dmax_set;
 
         // edge-feature weights for phase 1
         for (int i = tid; i < 64 * F; i += blockDim.x) S.wa[i] = wt[OFF_WEF + i];

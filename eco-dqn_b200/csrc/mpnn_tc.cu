@@ -233,14 +233,14 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     __syncthreads();
     tc_fence_after();
     c.tmem = tmem_base_s;
-    const float dmax = norm_max > 0.f ? norm_max : *g.dmax;
-    const float rdmax = 1.f / dmax;
+    const float dmax_set = norm_max > 0.f ? norm_max : *g.dmax;
     const int nsteps_A = NP >> 4;                         // k-steps over vertices
     const int nchunks = (NP + CHUNK - 1) / CHUNK;
 
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
         const int gi = graph_idx[b];
         const int8_t* A8 = g.J + (size_t)gi * NP * NP;
+        const float rdmax = 1.f / (norm_max < 0.f ? (float)max(g.gstat[(size_t)gi * 4], 1) : dmax_set);
 
         // pull the next episode's adjacency towards L2 while this one computes
         if (b + (int)gridDim.x < B) {

@@ -75,6 +75,9 @@ int    eco_graphs_bind(eco_graphs_t* g, void* workspace_dev, int32_t G, int32_t 
 int    eco_graphs_upload(eco_graphs_t* g, const int8_t* J_host, void* stream);
 /* same, source already on the device, dense [G, N, N] */
 int    eco_graphs_load_dev(eco_graphs_t* g, const int8_t* J_dev, void* stream);
+/* replace the graphs in slots [first, first + count) (J_dev dense [count, N, N]) and refresh their constants: the
+ * graph ring of the DQN trainer (a new random graph per episode, reference spinsystem.py:196) */
+int    eco_graphs_update(eco_graphs_t* g, int32_t first, int32_t count, const int8_t* J_dev, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Batched environment state (struct of arrays), B independent episodes.
@@ -165,7 +168,8 @@ int    eco_mpnn_pack(const eco_mpnn_t* w, void* packed_dev, void* stream);
 
 /* Q[b, i] for b < B from features xn [B,3,NP] / xg [B,4] and graph_idx [B] (use env->xn etc. for live
  * episodes, or replayed features for training).  norm_max: the batch-wide max degree the reference divides
- * by (mpnn.py:102); <= 0 means "max degree over the graphs referenced by this batch's graph set".
+ * by (mpnn.py:102); 0 means "max degree over the whole graph set", < 0 means "each episode's own graph" (what the
+ * reference computes when it evaluates one environment at a time, e.g. DQN.act).
  * q_dev [B, NP] fp32 or NULL; actions_dev [B] int32 or NULL (argmax, lowest index on ties). */
 int eco_mpnn_forward(const eco_graphs_t* g, const eco_mpnn_t* w, int32_t B, const int32_t* graph_idx_dev,
                      const float* xn_dev, const float* xg_dev, float norm_max, float* q_dev,

@@ -258,6 +258,60 @@ def main():
     np.savez_compressed(os.path.join(HERE, "generators.npz"), **out)
     print("wrote generators.npz")
 
+    dqn_case(er40[:3], os.path.join(nets, "network_best_ER_40spin.pth"))
+
+
+def dqn_case(graphs, net_path):
+    """One reference DQN.train_step (dqn.py:403-451) on a hand-built minibatch: loss, gradients, updated weights."""
+    import tempfile
+    from src.agents.dqn.dqn import DQN
+    from src.agents.dqn.utils import TestMetric
+    from src.envs.utils import SetGraphGenerator
+    n, T, B = 40, 10, 16
+    env = ising_env.make("SpinSystem", SetGraphGenerator(list(graphs), ordered=True), T, **env_args_for(n))
+    tmp = tempfile.mkdtemp()
+    agent = DQN([env], lambda: MPNN(n_obs_in=7, n_layers=3, n_features=64, n_hid_readout=[], tied_weights=False),
+                init_network_params=net_path, double_dqn=True, gamma=0.95, update_learning_rate=False,
+                initial_learning_rate=1e-4, minibatch_size=B, logging=False, seed=3, adam_epsilon=1e-8,
+                test_save_path=os.path.join(tmp, "t"), network_save_path=os.path.join(tmp, "n"),
+                test_metric=TestMetric.BEST)
+    w0 = {k: v.clone().numpy() for k, v in agent.network.state_dict().items()}
+    # perturb the target network so that online != target (as after some training)
+    torch.manual_seed(0)
+    with torch.no_grad():
+        for p_ in agent.target_network.parameters():
+            p_.add_(0.01 * torch.randn_like(p_))
+    wt = {k: v.clone().numpy() for k, v in agent.target_network.state_dict().items()}
+    rng = np.random.RandomState(11)
+    trans, gidx = [], []
+    ep = 0
+    state = torch.as_tensor(env.reset())
+    g_of_episode = [i for i in range(len(graphs)) if np.array_equal(graphs[i], env.matrix)][0]
+    while len(trans) < B:
+        a = int(rng.randint(n)) if rng.rand() < 0.5 else int(np.argmax(env.scorer.get_score_mask(env.state[0], env.matrix)))
+        nxt, r, d, _ = env.step(a)
+        if env.current_step in (1, 4, 7, 10):       # a spread of steps, including the terminal one
+            trans.append((state, torch.as_tensor([a], dtype=torch.long), torch.as_tensor([r], dtype=torch.float),
+                          torch.as_tensor(nxt), torch.as_tensor([d], dtype=torch.float)))
+            gidx.append(g_of_episode)
+        if d:
+            state = torch.as_tensor(env.reset())
+            g_of_episode = [i for i in range(len(graphs)) if np.array_equal(graphs[i], env.matrix)][0]
+        else:
+            state = torch.as_tensor(nxt)
+    batch = [torch.stack(t) for t in zip(*trans)]
+    loss = agent.train_step(batch)
+    grads = {k: p_.grad.clone().numpy() for k, p_ in agent.network.named_parameters()}
+    w1 = {k: v.clone().numpy() for k, v in agent.network.state_dict().items()}
+    out = dict(graphs=np.stack(graphs).astype(np.int8), graph_idx=np.array(gidx, dtype=np.int32),
+               rows=batch[0][:, :7, :].float().numpy(), rows_next=batch[3][:, :7, :].float().numpy(),
+               actions=batch[1][:, 0].numpy().astype(np.int64), rewards=batch[2][:, 0].numpy(),
+               dones=batch[4][:, 0].numpy(), loss=np.float64(loss), gamma=np.float64(0.95), lr=np.float64(1e-4))
+    for k in w0:
+        out["w::" + k], out["wt::" + k], out["g::" + k], out["w1::" + k] = w0[k], wt[k], grads[k], w1[k]
+    np.savez_compressed(os.path.join(HERE, "dqn_er40.npz"), **out)
+    print("wrote dqn_er40.npz, loss %.6g, dones %s" % (loss, batch[4][:, 0].tolist()))
+
 
 if __name__ == "__main__":
     main()
