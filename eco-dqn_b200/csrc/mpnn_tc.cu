@@ -57,8 +57,9 @@ constexpr int SM_ABS = SM_H;                             // |A| overlays H and E
 constexpr int SM_XF = SM_T + 128 * CHUNK * 2;            // float xf[7][208] overlays group 1's chunk buffer (dead by then)
 constexpr int SM_DEG = SM_T + 2 * 128 * CHUNK * 2;       // float rdeg[208] = 1/deg, float fdeg[208] = deg/deg_max
 constexpr int SM_QP = SM_DEG + 2 * NPMAX * 4;            // float qpart[4][208]
-constexpr int SM_PP = SM_QP + 4 * NPMAX * 4;             // float ppart[2][64]
-constexpr int SM_WI = SM_PP + 2 * 64 * 4;                // float w_init[64*7]
+constexpr int MAXCHUNKS = (NPMAX + CHUNK - 1) / CHUNK;
+constexpr int SM_PP = SM_QP + 4 * NPMAX * 4;             // float ppart[MAXCHUNKS][64]: per-chunk pooled partial sums
+constexpr int SM_WI = SM_PP + MAXCHUNKS * 64 * 4;        // float w_init[64*7]
 constexpr int SM_WE = SM_WI + 64 * 7 * 4;                // float w_edge[64*8] (row 63 zero)
 constexpr int SM_WR = SM_WE + 64 * 8 * 4;                // float w_read[128]
 constexpr int SM_MISC = SM_WR + 128 * 4;                 // float pooled[64], c0, reductions
@@ -430,7 +431,6 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         // per chunk:  m = ReLU(W_m [agg ; e]) accumulates in the group's ACC1, h' = ReLU(W_u [h ; m]) accumulates in the
         // chunk's own (already consumed) columns of ACC0.  The halves that do not depend on the running epilogue
         // (W_m e, W_u h) are issued ahead, so they execute while the group's warps are busy in the epilogue.
-        float pool_a = 0.f, pool_b = 0.f;       // readout partials (last layer)
         for (int l = 0; l < 3; ++l) {
             uint4 wm[8], wu[8];
             if (l > 0) {                        // next weights: L2 -> registers, latency hidden behind the barrier
@@ -511,8 +511,11 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                     });
                 } else {
                     // readout partials straight from the fp32 registers (mpnn.py:143-159)
+                    // (pooled sums are kept per chunk and added in chunk order, so the result does not depend on
+                    //  which group happened to process which chunk)
                     const int fa = 16 * c.q + (c.lane >> 2);
                     const float wa = s_wread[64 + fa], wb = s_wread[64 + fa + 8];
+                    float pool_a = 0.f, pool_b = 0.f;
                     epilogue(c, T_ACC0, c0, width, [&](int bc, float (&v)[8]) {
                         float qv[4];
 #pragma unroll
@@ -535,21 +538,24 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                                 qpart[c.q * NPMAX + c0 + bc + 8 * (j >> 1) + 2 * (c.lane & 3) + (j & 1)] = qv[j];
                         }
                     });
+                    pool_a += __shfl_xor_sync(0xffffffffu, pool_a, 1); pool_a += __shfl_xor_sync(0xffffffffu, pool_a, 2);
+                    pool_b += __shfl_xor_sync(0xffffffffu, pool_b, 1); pool_b += __shfl_xor_sync(0xffffffffu, pool_b, 2);
+                    if ((c.lane & 3) == 0) {
+                        ppart[ci * 64 + fa] = pool_a;
+                        ppart[ci * 64 + fa + 8] = pool_b;
+                    }
                 }
                 ci = nxt;
             }
         }
 
         // ================= stage 3: readout + argmax ========================================================
-        pool_a += __shfl_xor_sync(0xffffffffu, pool_a, 1); pool_a += __shfl_xor_sync(0xffffffffu, pool_a, 2);
-        pool_b += __shfl_xor_sync(0xffffffffu, pool_b, 1); pool_b += __shfl_xor_sync(0xffffffffu, pool_b, 2);
-        if ((c.lane & 3) == 0) {
-            const int fa = 16 * c.q + (c.lane >> 2);
-            ppart[c.grp * 64 + fa] = pool_a;
-            ppart[c.grp * 64 + fa + 8] = pool_b;
-        }
         __syncthreads();
-        if (c.tid < 64) pooled[c.tid] = (ppart[c.tid] + ppart[64 + c.tid]) / (float)N;
+        if (c.tid < 64) {
+            float t = 0.f;
+            for (int k = 0; k < nchunks; ++k) t += ppart[k * 64 + c.tid];
+            pooled[c.tid] = t / (float)N;
+        }
         __syncthreads();
         {   // p = W_p pooled: 4 lanes per output feature, then c0 = w_r[0:64] . ReLU(p) + b
             const int f = c.tid >> 2, part = c.tid & 3;

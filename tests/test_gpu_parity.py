@@ -307,3 +307,27 @@ def test_error_behaviour(eng):
         eng.GraphSet(np.zeros((1, 8, 8)))
     with pytest.raises(ValueError):
         eng.GraphSet(np.triu(np.ones((1, 8, 8)), 1))   # not symmetric
+
+
+def test_mpnn_tc_is_run_to_run_deterministic(eng):
+    """Chunks are handed out dynamically to the two warp groups; results must not depend on the hand-out."""
+    from eco_dqn_b200 import _lib
+    gsets = np.load(os.path.join(GOLDEN, "graphsets.npz"))
+    z = load("ba200_g0")
+    B, n = 2048, 200
+    rng = np.random.default_rng(3)
+    gs = eng.GraphSet(gsets["ba200"])
+    env = eng.BatchedSpinSystem(gs, B, 400, 1.0 / n)
+    env.reset(spins=(2 * rng.integers(0, 2, size=(B, n)) - 1).astype(np.int8))
+    w = eng.MPNNWeights(weights_dict(z))
+    if w.c.packed is None:
+        pytest.skip("tcgen05 path not built")
+    for t in range(3):
+        q1, a1 = env.q_values(w, impl=_lib.MPNN_TCGEN05)
+        q1, a1 = q1.clone(), a1.clone()
+        for rep in range(3):
+            q2, a2 = env.q_values(w, impl=_lib.MPNN_TCGEN05)
+            assert torch.equal(q1, q2) and torch.equal(a1, a2)
+        qs, _ = env.q_values(w, impl=_lib.MPNN_SIMT)
+        assert torch.allclose(q1, qs, rtol=Q_RTOL, atol=Q_ATOL_FRAC * float(qs.abs().max()))
+        env.step(a1)
