@@ -145,7 +145,7 @@ def run_reference(args):
     n = N_SPINS
     weights = load_weights()
     J = ba_graphs(1, n, BA_M, seed=0)[0]
-    n_eps, n_steps = 16, 10
+    n_eps, n_steps = 32, 100
     vals = []
     for i in range(args.warmup):
         cpu_reference_sample(J, weights, 4, 2, seed=i)
@@ -313,9 +313,10 @@ def run_ours(args):
                             (bytes_env(n) * B / 1e6)}
         cpu = None
         if not args.skip_cpu:
-            v, cores, secs = cpu_reference_sample(J[0], wd, 16, 10)
+            v, cores, secs = cpu_reference_sample(J[0], wd, 32, 2 * n)
             cpu = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                   "sample": "16 episodes x 10 env steps of one BA-200 graph (%.1f s of CPU work)" % secs}
+                   "sample": "32 complete episodes (400 env steps each) of one BA-200 graph, batched like the "
+                             "reference's test_network (%.1f s of CPU work)" % secs}
         line = {"metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16x2-split/f32" if used_impl == "tcgen05" else "f32",
