@@ -26,6 +26,7 @@
 //                 chunks on group 0 and odd chunks on group 1, each group with its own accumulator columns, chunk
 //                 buffer, mbarrier and named barrier, so one group's MMAs overlap the other group's epilogue.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "eco_common.cuh"
 #include "tc_prims.cuh"
@@ -36,7 +37,7 @@ namespace {
 using namespace tc;
 
 constexpr int NPMAX = 208;
-constexpr int CHUNK = 48;        // vertices per linear-layer chunk (accumulator columns)
+constexpr int CHUNK = 64;        // max vertices per linear-layer chunk (accumulator columns)
 constexpr int THREADS = 256;
 
 // ---- TMEM column map -------------------------------------------------------------------------------------
@@ -55,13 +56,11 @@ constexpr int SM_E = SM_H + 128 * NPMAX * 2;             // E^T stacked
 constexpr int SM_T = SM_E + 128 * NPMAX * 2;             // chunk buffers [2 groups][128][48]
 constexpr int SM_ABS = SM_H;                             // |A| overlays H and E during the edge stage
 constexpr int SM_XF = SM_T + 128 * CHUNK * 2;            // float xf[7][208] overlays group 1's chunk buffer (dead by then)
-constexpr int SM_DEG = SM_T + 2 * 128 * CHUNK * 2;       // float rdeg[208] = 1/deg, float fdeg[208] = deg/deg_max
-constexpr int SM_QP = SM_DEG + 2 * NPMAX * 4;            // float qpart[4][208]
+constexpr int SM_DEG = SM_T + 2 * 128 * CHUNK * 2;       // float rdeg[208] = 1/deg
+constexpr int SM_QP = SM_DEG + NPMAX * 4;                // float qpart[4][208]
 constexpr int MAXCHUNKS = (NPMAX + CHUNK - 1) / CHUNK;
 constexpr int SM_PP = SM_QP + 4 * NPMAX * 4;             // float ppart[MAXCHUNKS][64]: per-chunk pooled partial sums
-constexpr int SM_WI = SM_PP + MAXCHUNKS * 64 * 4;        // float w_init[64*7]
-constexpr int SM_WE = SM_WI + 64 * 7 * 4;                // float w_edge[64*8] (row 63 zero)
-constexpr int SM_WR = SM_WE + 64 * 8 * 4;                // float w_read[128]
+constexpr int SM_WR = SM_PP + MAXCHUNKS * 64 * 4;        // float w_read[128]
 constexpr int SM_MISC = SM_WR + 128 * 4;                 // float pooled[64], c0, reductions
 constexpr int SM_TOTAL = SM_MISC + 64 * 4 + 64 + 8 * 8 + 8 * 8;
 static_assert(NPMAX * NPMAX * 2 <= 2 * 128 * NPMAX * 2, "|A| must fit in the H+E region");
@@ -76,20 +75,27 @@ constexpr int PK_WORDS = PK_WU + 3 * 128 * 64;
 
 __device__ __forceinline__ uint16_t bf16_bits(float x) { return __bfloat16_as_ushort(__float2bfloat16_rn(x)); }
 
+// Packed layout per matrix (KW words per stacked row): word (r, c) with r = 32q + lane, c = 8cg + 4h + j lives at
+// ((((q * KW/8 + cg) * 2 + h) * 32 + lane) * 4 + j): every LDG.128 of a warp in ldg_weights() is 512 contiguous bytes.
+__host__ __device__ inline int packed_index(int r, int c, int kw) {
+    const int q = r >> 5, lane = r & 31, cg = c >> 3, h = (c >> 2) & 1, j = c & 3;
+    return (((q * (kw / 8) + cg) * 2 + h) * 32 + lane) * 4 + j;
+}
+
 __global__ void mpnn_pack_kernel(const eco_mpnn_t w, uint32_t* __restrict__ out) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= PK_WORDS) return;
     const float* src;
-    int kw, rel;   // words per row, index within the matrix
-    if (idx < PK_WM) { src = w.w_edge_feat; kw = 32; rel = idx; }
-    else if (idx < PK_WU) { const int l = (idx - PK_WM) / (128 * 64); src = w.w_msg[l]; kw = 64; rel = (idx - PK_WM) % (128 * 64); }
-    else { const int l = (idx - PK_WU) / (128 * 64); src = w.w_upd[l]; kw = 64; rel = (idx - PK_WU) % (128 * 64); }
+    int kw, rel, base;   // words per row, index within the matrix, matrix offset
+    if (idx < PK_WM) { src = w.w_edge_feat; kw = 32; rel = idx; base = PK_WEF; }
+    else if (idx < PK_WU) { const int l = (idx - PK_WM) / (128 * 64); src = w.w_msg[l]; kw = 64; rel = (idx - PK_WM) % (128 * 64); base = PK_WM + l * 128 * 64; }
+    else { const int l = (idx - PK_WU) / (128 * 64); src = w.w_upd[l]; kw = 64; rel = (idx - PK_WU) % (128 * 64); base = PK_WU + l * 128 * 64; }
     const int r = rel / kw, c = rel % kw;
     const int f = 16 * (r >> 5) + (r & 15), s = (r >> 4) & 1;
     const float a = src[f * (2 * kw) + 2 * c], b = src[f * (2 * kw) + 2 * c + 1];
     uint32_t hi, lo;
     split2(a, b, hi, lo);
-    out[idx] = s ? lo : hi;
+    out[base + packed_index(r, c, kw)] = s ? lo : hi;
 }
 
 struct Ctx {
@@ -101,6 +107,19 @@ struct Ctx {
     int tid, warp, lane, q, grp;
     int N, NP, NB;
 };
+
+// Linear-layer chunks: the NP/16 column blocks are split into an EVEN number of chunks of <= CHUNK/16 blocks, sizes
+// as equal as possible (208 vertices -> 64,48,48,48), so the two warp groups finish a layer at about the same time.
+__device__ __forceinline__ int chunk_count(int nblocks) {
+    if (nblocks < 2) return 1;
+    const int need = (nblocks + CHUNK / 16 - 1) / (CHUNK / 16);
+    return (need + 1) & ~1;
+}
+__device__ __forceinline__ void chunk_span(int ci, int nblocks, int nch, int& c0, int& width) {
+    const int base = nblocks / nch, extra = nblocks % nch;
+    c0 = 16 * (ci * base + min(ci, extra));
+    width = 16 * (base + (ci < extra ? 1 : 0));
+}
 
 __device__ __forceinline__ void cta_stage_sync() {   // operands written by everyone (smem: generic proxy; TMEM: st/ld retired)
     fence_proxy_async();
@@ -127,9 +146,10 @@ __device__ __forceinline__ void wait_grp(Ctx& c) {
 // lane quadrant split the columns.  Split in two so the L2 latency can be hidden behind a barrier / MMA wait.
 template <int KW>
 __device__ __forceinline__ void ldg_weights(const Ctx& c, const uint32_t* __restrict__ pk, uint4 (&buf)[KW / 8]) {
-    const uint4* src = reinterpret_cast<const uint4*>(pk + (size_t)(32 * c.q + c.lane) * KW + c.grp * (KW / 2));
+    // this warp: quadrant q, column groups [grp * KW/16, (grp + 1) * KW/16); buf[2i], buf[2i+1] = the two 4-word halves
+    const uint4* src = reinterpret_cast<const uint4*>(pk) + ((c.q * (KW / 8) + c.grp * (KW / 16)) * 2) * 32 + c.lane;
 #pragma unroll
-    for (int i = 0; i < KW / 8; ++i) buf[i] = __ldg(src + i);
+    for (int i = 0; i < KW / 8; ++i) buf[i] = __ldg(src + i * 32);
 }
 template <int KW>
 __device__ __forceinline__ void sttm_weights(const Ctx& c, const uint4 (&buf)[KW / 8], uint32_t tcol) {
@@ -190,8 +210,15 @@ __device__ __forceinline__ void issue_part(const Ctx& c, uint32_t acc_col, uint3
 __global__ void __launch_bounds__(THREADS, 1)
 mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int32_t* __restrict__ graph_idx,
                const float* __restrict__ xn, const float* __restrict__ xg, const float norm_max,
-               float* __restrict__ q_out, int32_t* __restrict__ act_out) {
-    extern __shared__ __align__(1024) unsigned char smem[];
+               float* __restrict__ q_out, int32_t* __restrict__ act_out, unsigned long long* __restrict__ dbg) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    // optional timeline (tools/tc_timeline.py): CTA 0, lane 0 of every warp records (event id << 48 | clock)
+    int dbg_n = 0;
+#define TL(id)                                                                                           \
+    do {                                                                                                 \
+        if (dbg != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && dbg_n < 1024)                \
+            dbg[(threadIdx.x >> 5) * 1024 + dbg_n++] = ((unsigned long long)(id) << 48) | (clock64() & 0xFFFFFFFFFFFFull); \
+    } while (0)
     __shared__ uint64_t bars[3];
     __shared__ uint32_t tmem_base_s;
     __shared__ int chunk_ctr[4];      // dynamic chunk hand-out: edge-feature stage + 3 layers
@@ -207,11 +234,8 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
 
     float* xf = reinterpret_cast<float*>(smem + SM_XF);
     float* rdeg = reinterpret_cast<float*>(smem + SM_DEG);      // 1 / deg
-    float* fdeg = rdeg + NPMAX;                                   // deg / deg_max
     float* qpart = reinterpret_cast<float*>(smem + SM_QP);
     float* ppart = reinterpret_cast<float*>(smem + SM_PP);
-    float* s_winit = reinterpret_cast<float*>(smem + SM_WI);
-    float* s_wedge = reinterpret_cast<float*>(smem + SM_WE);
     float* s_wread = reinterpret_cast<float*>(smem + SM_WR);
     float* pooled = reinterpret_cast<float*>(smem + SM_MISC);
     float* s_c0 = pooled + 64;
@@ -227,8 +251,6 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
 
     if (c.warp == 0) tmem_alloc(&tmem_base_s, 512);
     if (c.tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); fence_mbar_init(); }
-    for (int i = c.tid; i < 64 * 7; i += THREADS) s_winit[i] = w.w_init[i];
-    for (int i = c.tid; i < 64 * 8; i += THREADS) s_wedge[i] = i < 63 * 8 ? w.w_edge[i] : 0.f;
     for (int i = c.tid; i < 128; i += THREADS) s_wread[i] = w.w_read[i];
     tc_fence_before();
     __syncthreads();
@@ -236,7 +258,8 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     c.tmem = tmem_base_s;
     const float dmax_set = norm_max > 0.f ? norm_max : *g.dmax;
     const int nsteps_A = NP >> 4;                         // k-steps over vertices
-    const int nchunks = (NP + CHUNK - 1) / CHUNK;
+    const int nblocks = NP >> 4;
+    const int nchunks = chunk_count(nblocks);
 
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
         const int gi = graph_idx[b];
@@ -250,8 +273,19 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + off));
         }
 
+        TL(1);
         // ================= stage 0: operands of the edge contraction ======================================
         if (c.tid < 4) chunk_ctr[c.tid] = 2;              // chunks 0 / 1 are pre-assigned to group 0 / 1
+        // this thread's rows of the two small input weights (features fa, fb), issued early so the latency is hidden
+        const int fa = 16 * c.q + (c.lane >> 2), fb = fa + 8;
+        float wxa[8], wxb[8], wia[7], wib[7];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {       // row 63 of the 63 x 8 edge weight does not exist: zero
+            wxa[k] = __ldg(w.w_edge + fa * 8 + k);
+            wxb[k] = fb < 63 ? __ldg(w.w_edge + fb * 8 + k) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 7; ++k) { wia[k] = __ldg(w.w_init + fa * 7 + k); wib[k] = __ldg(w.w_init + fb * 7 + k); }
         for (int i = c.tid; i < NP; i += THREADS) {
             const bool ok = i < N;
             xf[0 * NPMAX + i] = ok ? xn[((size_t)b * 3 + 0) * NP + i] : 0.f;
@@ -264,7 +298,6 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             xf[6 * NPMAX + i] = ok ? gl.w : 0.f;
             const float d = g.deg[(size_t)gi * NP + i];
             rdeg[i] = 1.f / d;
-            fdeg[i] = d * rdmax;
         }
         for (int i = c.tid; i < 4 * NPMAX; i += THREADS) qpart[i] = 0.f;
         // adjacency int8 -> bf16 A and |A| (K-major B operands): a warp converts 8 rows x 64 bytes per pass.  All of a
@@ -282,18 +315,13 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             if (it < total_passes && ch < nch)
                 raw[k] = *reinterpret_cast<const uint4*>(A8 + (size_t)(ib * 8 + (c.lane & 7)) * NP + ch * 16);
         }
-        {
-            uint4 wbuf[4];
-            ldg_weights<32>(c, pk + PK_WEF, wbuf);
-            sttm_weights<32>(c, wbuf, T_WEF);
-        }
+        uint4 wef[4];
+        ldg_weights<32>(c, pk + PK_WEF, wef);
+        TL(2);
         __syncthreads();                                   // xf visible
+        TL(3);
         // S = R+ + R-, D = R+ - R- with R+- = ReLU(P +- w0), P = W_x x  -> TMEM A operands (mpnn.py:89-100 factorised)
         {
-            const int fa = 16 * c.q + (c.lane >> 2), fb = fa + 8;
-            float wxa[8], wxb[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) { wxa[k] = s_wedge[fa * 8 + k]; wxb[k] = s_wedge[fb * 8 + k]; }
             for (int blk = c.grp; blk < nsteps_A; blk += 2) {
                 uint32_t sh[4], sl[4], dh[4], dl[4];
 #pragma unroll
@@ -321,20 +349,22 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                 tmem_st_16x128b_x2(tmem_addr(c.tmem, 32 * c.q + 16, T_D + 8 * blk), dl);
             }
         }
+        sttm_weights<32>(c, wef, T_WEF);
+        TL(4);
 #pragma unroll
         for (int k = 0; k < MAXIT; ++k) {
             const int it = c.warp + 8 * k;
             const int ib = it / ppr, ch = (it % ppr) * 4 + (c.lane >> 3);
             if (it < total_passes && ch < nch) {
-                union { uint4 v; int8_t s[16]; } u;
-                u.v = raw[k];
+                // 16 int8 in {-1,0,1} -> bf16 pairs: spread two bytes into halfwords (PRMT), |a| = (h & 1) * 0x3F80,
+                // sign = bit 7 moved to bit 15
+                const uint32_t x[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
                 uint32_t wa[8], wb[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const int a0 = u.s[2 * e], a1 = u.s[2 * e + 1];
-                    const uint32_t m0 = a0 ? 0x3F80u : 0u, m1 = a1 ? 0x3F80u : 0u;
-                    wb[e] = m0 | (m1 << 16);
-                    wa[e] = (m0 | (a0 < 0 ? 0x8000u : 0u)) | ((m1 | (a1 < 0 ? 0x8000u : 0u)) << 16);
+                    const uint32_t h = __byte_perm(x[e >> 1], 0, (e & 1) ? 0x4342 : 0x4140);   // [b_lo, 0, b_hi, 0]
+                    wb[e] = (h & 0x00010001u) * 0x3F80u;
+                    wa[e] = wb[e] | ((h << 8) & 0x80008000u);
                 }
                 const int off0 = ((2 * ch) * NB + ib) * 128 + (c.lane & 7) * 16;
                 const int off1 = off0 + NB * 128;
@@ -345,7 +375,9 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             }
         }
         tmem_st_wait();
+        TL(5);
         cta_stage_sync();
+        TL(6);
         if (c.warp == 0) {
           tc_fence_after();
           if (elect_one()) {
@@ -366,16 +398,13 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             ldg_weights<64>(c, pk + PK_WM, wm);
             ldg_weights<64>(c, pk + PK_WU, wu);
             wait_all(c);
+            TL(7);
             sttm_weights<64>(c, wm, T_WM);
             sttm_weights<64>(c, wu, T_WU);
         }
 
         // ================= stage 1: h0 (CUDA cores), edge embeddings e =====================================
         {   // h0 = ReLU(W_init x): thread owns features fa, fb and 4 vertices of every 16-vertex block (epilogue mapping)
-            const int fa = 16 * c.q + (c.lane >> 2), fb = fa + 8;
-            float wia[7], wib[7];
-#pragma unroll
-            for (int k = 0; k < 7; ++k) { wia[k] = s_winit[fa * 7 + k]; wib[k] = s_winit[fb * 7 + k]; }
             for (int blk = c.grp; blk < nsteps_A; blk += 2) {
                 float v[8];
 #pragma unroll
@@ -395,22 +424,26 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             }
         }
         tmem_st_wait();
+        TL(8);
         cta_stage_sync();            // xf (overlaying group 1's chunk buffer) is dead from here; weights visible to the MMAs
         int slot = 0;                 // parity of the hand-out slot (all threads of a group advance it together)
         for (int ci = c.grp; ci < nchunks;) {
-            const int c0 = ci * CHUNK, width = min(CHUNK, NP - c0);
+            int c0, width;
+            chunk_span(ci, nblocks, nchunks, c0, width);
             // g = (S|A| + D A) / (2 deg); feature 63 = deg / deg_max   (mpnn.py:100-102)
             epilogue(c, T_ACC0, c0, width, [&](int bc, float (&v)[8]) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int n = c0 + bc + 8 * (i >> 2) + 2 * (c.lane & 3) + (i & 1);
                     const int f = 16 * c.q + (c.lane >> 2) + 8 * ((i >> 1) & 1);
-                    v[i] = f == 63 ? fdeg[n] : (0.5f * v[i]) * rdeg[n];
+                    v[i] = f == 63 ? __fdividef(rdmax, rdeg[n]) : (0.5f * v[i]) * rdeg[n];
                 }
                 store_block(c, sT, bc, v);
             });
             if (c.q == 0 && c.lane == 0) next_s[c.grp][slot] = atomicAdd(&chunk_ctr[0], 1);
+            TL(10);
             grp_stage_sync(c);
+            TL(11);
             if (c.q == 0) {
                 tc_fence_after();
                 if (elect_one()) { issue_part(c, acc1, T_WEF, sT, 0, width, false); mma_commit(c.bar_grp); }
@@ -419,11 +452,13 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             const int nxt = next_s[c.grp][slot];
             slot ^= 1;
             wait_grp(c);
+            TL(12);
             epilogue(c, acc1, 0, width, [&](int bc, float (&v)[8]) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
                 store_block(c, sE, c0 + bc, v);
             });
+            TL(13);
             ci = nxt;
         }
 
@@ -432,12 +467,9 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         // chunk's own (already consumed) columns of ACC0.  The halves that do not depend on the running epilogue
         // (W_m e, W_u h) are issued ahead, so they execute while the group's warps are busy in the epilogue.
         for (int l = 0; l < 3; ++l) {
-            uint4 wm[8], wu[8];
-            if (l > 0) {                        // next weights: L2 -> registers, latency hidden behind the barrier
-                ldg_weights<64>(c, pk + PK_WM + l * 128 * 64, wm);
-                ldg_weights<64>(c, pk + PK_WU + l * 128 * 64, wu);
-            }
+            TL(20);
             cta_stage_sync();                   // every h / e column of the previous stage is written
+            TL(21);
             if (c.warp == 0) {                  // agg^T = H^T A  (both hi and lo rows in one M=128 chain)
               tc_fence_after();
               if (elect_one()) {
@@ -452,6 +484,9 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
               __syncwarp();
             }
             if (l > 0) {                        // the previous layer's MMAs all retired (barrier above): overwrite weights
+                uint4 wm[8], wu[8];             // (loaded after the barrier: before it, the global loads would contend
+                ldg_weights<64>(c, pk + PK_WM + l * 128 * 64, wm);   //  with the slower group's shared-memory stores)
+                ldg_weights<64>(c, pk + PK_WU + l * 128 * 64, wu);
                 sttm_weights<64>(c, wm, T_WM);
                 sttm_weights<64>(c, wu, T_WU);
                 tmem_st_wait();
@@ -460,20 +495,27 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             }
             int ci = c.grp;
             if (ci < nchunks && c.q == 0) {     // W_m e-half of the first chunk does not depend on the aggregation
+                int c0, width;
+                chunk_span(ci, nblocks, nchunks, c0, width);
                 tc_fence_after();
-                if (elect_one()) issue_part(c, acc1, T_WM + 32, sE, (ci * CHUNK) >> 3, min(CHUNK, NP - ci * CHUNK), false);
+                if (elect_one()) issue_part(c, acc1, T_WM + 32, sE, c0 >> 3, width, false);
                 __syncwarp();
             }
+            TL(22);
             wait_all(c);
+            TL(23);
             while (ci < nchunks) {
-                const int c0 = ci * CHUNK, width = min(CHUNK, NP - c0);
+                int c0, width;
+                chunk_span(ci, nblocks, nchunks, c0, width);
                 epilogue(c, T_ACC0, c0, width, [&](int bc, float (&v)[8]) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] = v[i] * rdeg[c0 + bc + 8 * (i >> 2) + 2 * (c.lane & 3) + (i & 1)];
                     store_block(c, sT, bc, v);
                 });
                 if (c.q == 0 && c.lane == 0) next_s[c.grp][slot] = atomicAdd(&chunk_ctr[1 + l], 1);
+                TL(30);
                 grp_stage_sync(c);
+                TL(31);
                 if (c.q == 0) {
                     tc_fence_after();
                     if (elect_one()) {
@@ -485,24 +527,33 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                 }
                 const int nxt = next_s[c.grp][slot];
                 slot ^= 1;
+                TL(32);
                 wait_grp(c);
+                TL(33);
                 epilogue(c, acc1, 0, width, [&](int bc, float (&v)[8]) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
                     store_block(c, sT, bc, v);
                 });
+                TL(34);
                 grp_stage_sync(c);
+                TL(35);
                 if (c.q == 0) {
                     tc_fence_after();
                     if (elect_one()) {
                         issue_part(c, T_ACC0 + c0, T_WU + 32, sT, 0, width, true);         // += W_u[:, 64:] m
                         mma_commit(c.bar_grp);
-                        if (nxt < nchunks)                                               // next chunk's e-half, ahead
-                            issue_part(c, acc1, T_WM + 32, sE, (nxt * CHUNK) >> 3, min(CHUNK, NP - nxt * CHUNK), false);
+                        if (nxt < nchunks) {                                             // next chunk's e-half, ahead
+                            int n0, nw;
+                            chunk_span(nxt, nblocks, nchunks, n0, nw);
+                            issue_part(c, acc1, T_WM + 32, sE, n0 >> 3, nw, false);
+                        }
                     }
                     __syncwarp();
                 }
+                TL(36);
                 wait_grp(c);
+                TL(37);
                 if (l < 2) {
                     epilogue(c, T_ACC0, c0, width, [&](int bc, float (&v)[8]) {
 #pragma unroll
@@ -513,7 +564,6 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                     // readout partials straight from the fp32 registers (mpnn.py:143-159)
                     // (pooled sums are kept per chunk and added in chunk order, so the result does not depend on
                     //  which group happened to process which chunk)
-                    const int fa = 16 * c.q + (c.lane >> 2);
                     const float wa = s_wread[64 + fa], wb = s_wread[64 + fa + 8];
                     float pool_a = 0.f, pool_b = 0.f;
                     epilogue(c, T_ACC0, c0, width, [&](int bc, float (&v)[8]) {
@@ -545,9 +595,11 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                         ppart[ci * 64 + fa + 8] = pool_b;
                     }
                 }
+                TL(38);
                 ci = nxt;
             }
         }
+        TL(40);
 
         // ================= stage 3: readout + argmax ========================================================
         __syncthreads();
@@ -607,7 +659,9 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             act_out[b] = bi;
         }
         __syncthreads();
+        TL(41);
     }
+#undef TL
 
     tc_fence_before();
     __syncthreads();
@@ -617,7 +671,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
 }  // namespace
 
 bool mpnn_tc_supported(const eco_graphs_t* g) { return g->N <= NPMAX && (g->reserved & 1); }
-size_t mpnn_tc_scratch_bytes(int, int) { return 256; }
+size_t mpnn_tc_scratch_bytes(int, int) { return 8 * 1024 * 8 + 256; }   // room for the optional debug timeline
 size_t mpnn_tc_packed_bytes() { return (size_t)PK_WORDS * 4; }
 
 int launch_mpnn_pack(const eco_mpnn_t* w, void* packed, cudaStream_t st) {
@@ -627,7 +681,7 @@ int launch_mpnn_pack(const eco_mpnn_t* w, void* packed, cudaStream_t st) {
 }
 
 int launch_mpnn_tc(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int32_t* gidx, const float* xn,
-                   const float* xg, float norm_max, float* q, int32_t* actions, void*, cudaStream_t st) {
+                   const float* xg, float norm_max, float* q, int32_t* actions, void* scratch, cudaStream_t st) {
     static bool attr_set = false;
     static int n_sm = 148;
     if (!attr_set) {
@@ -639,7 +693,10 @@ int launch_mpnn_tc(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int3
     }
     const int grid = B < n_sm ? B : n_sm;
     prof_begin(ECO_PROF_MPNN, st);
-    mpnn_tc_kernel<<<grid, THREADS, SM_TOTAL, st>>>(*g, *w, B, gidx, xn, xg, norm_max, q, actions);
+    static const bool timeline = getenv("ECO_TC_TIMELINE") != nullptr;
+    if (timeline) ECO_CUDA(cudaMemsetAsync(scratch, 0, 8 * 1024 * 8, st));
+    mpnn_tc_kernel<<<grid, THREADS, SM_TOTAL, st>>>(*g, *w, B, gidx, xn, xg, norm_max, q, actions,
+                                                    timeline ? (unsigned long long*)scratch : nullptr);
     prof_end(ECO_PROF_MPNN, st);
     ECO_LAUNCH_CHECK();
     return ECO_OK;
