@@ -297,7 +297,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             xf[5 * NPMAX + i] = ok ? gl.z : 0.f;
             xf[6 * NPMAX + i] = ok ? gl.w : 0.f;
             const float d = g.deg[(size_t)gi * NP + i];
-            rdeg[i] = 1.f / d;
+            rdeg[i] = __fdividef(1.f, d);
         }
         for (int i = c.tid; i < 4 * NPMAX; i += THREADS) qpart[i] = 0.f;
         // adjacency int8 -> bf16 A and |A| (K-major B operands): a warp converts 8 rows x 64 bytes per pass.  All of a
