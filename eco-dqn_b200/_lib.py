@@ -17,7 +17,7 @@ i32 = C.c_int32
 
 class Graphs(C.Structure):
     _fields_ = [("G", i32), ("N", i32), ("NP", i32), ("reserved", i32),
-                ("J", vp), ("gscal", vp), ("deg", vp), ("gstat", vp), ("dmax", vp)]
+                ("J", vp), ("gscal", vp), ("deg", vp), ("gstat", vp), ("dmax", vp), ("gain_tab", vp), ("dn_tab", vp)]
 
 
 class Episode(C.Structure):
@@ -37,7 +37,7 @@ class Env(C.Structure):
                 ("basin_reward", C.c_double),
                 ("spins", vp), ("hfield", vp), ("last_flip", vp), ("diff_bits", vp), ("graph_idx", vp),
                 ("ep", vp), ("visited", vp), ("zobrist", vp), ("tsf_tab", vp), ("imm_tab", vp),
-                ("xn", vp), ("xg", vp)]
+                ("xn", vp), ("xg", vp), ("frac_tab", vp)]
 
 
 class Mpnn(C.Structure):

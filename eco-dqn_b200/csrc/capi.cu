@@ -60,6 +60,8 @@ static void carve_graphs(eco_graphs_t* g, Carver& c, int G, int N) {
     g->deg = c.take<float>((size_t)G * NP);
     g->gstat = c.take<int32_t>((size_t)G * 4);
     g->dmax = c.take<float>(64);
+    g->gain_tab = c.take<float>((size_t)G * (2 * NP + 1));
+    g->dn_tab = c.take<double>((size_t)G * (2 * NP + 1));
 }
 
 static int hcap_for(int T) {
@@ -85,9 +87,15 @@ static void carve_env(eco_env_t* e, Carver& c, int B, int N, int T, double basin
     e->imm_tab = c.take<float>((size_t)T + 1);
     e->xn = c.take<float>((size_t)B * 3 * NP);
     e->xg = c.take<float>((size_t)B * 4);
+    e->frac_tab = c.take<float>((size_t)N + 1);
 }
 
 static bool shape_ok(int N) { return N >= 1 && N <= ECO_MAX_SPINS; }
+
+__global__ void frac_tab_kernel(float* tab, int N) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k <= N) tab[k] = (float)__ddiv_rn((double)k, (double)N);     // np.sum(gains > 0) / n_spins, then the fp32 cast
+}
 
 __global__ void dmax_kernel(const eco_graphs_t g) {
     // single warp: max degree over all graphs of the set -> g.dmax[0]
@@ -229,6 +237,8 @@ int eco_env_set_tables(eco_env_t* env, const uint64_t* zob, const float* tsf, co
     ECO_CUDA(cudaMemcpyAsync(env->zobrist, zob, (size_t)env->NP * 16, cudaMemcpyHostToDevice, st));
     ECO_CUDA(cudaMemcpyAsync(env->tsf_tab, tsf, ((size_t)env->T + 1) * 4, cudaMemcpyHostToDevice, st));
     ECO_CUDA(cudaMemcpyAsync(env->imm_tab, imm, ((size_t)env->T + 1) * 4, cudaMemcpyHostToDevice, st));
+    frac_tab_kernel<<<(env->N + 256) / 256, 256, 0, st>>>(env->frac_tab, env->N);
+    ECO_LAUNCH_CHECK();
     return ECO_OK;
 }
 

@@ -59,13 +59,16 @@ int         eco_abi_version(void);
  * of MaximumCutUnbiasedScorer (src/envs/score_solver.py:347-375): mlr, qn, lb.
  * --------------------------------------------------------------------------------------------------------- */
 typedef struct {
-    int32_t  G, N, NP, reserved;
+    int32_t  G, N, NP, reserved;   /* reserved bit0: caller asserts every coupling is in {-1,0,1} (see gstat flags) */
     int8_t*  J;          /* [G, NP, NP]  couplings, zero padded                                              */
     double*  gscal;      /* [G, 4]       mlr (max non-zero weighted degree), qn, lb, sum_ij J_ij             */
     float*   deg;        /* [G, NP]      max(1, #non-zeros in row i)  (mpnn.py:34-38)                        */
     int32_t* gstat;      /* [G, 4]       max degree, nnz, max |row abs sum|, flags (bit0: weights outside {-1,0,1},
                                          bit1: all weighted degrees zero, bit2: not symmetric / non-zero diagonal)  */
     float*   dmax;       /* [1]          max degree over the whole set (default norm.max(), mpnn.py:102)     */
+    float*   gain_tab;   /* [G, 2*NP+1]  (float)((double)k / mlr) for k = -NP..NP: observable row 1 of a vertex whose
+                                         flip changes the cut by k (valid for couplings in {-1,0,1}; spinsystem.py:490) */
+    double*  dn_tab;     /* [G, 2*NP+1]  (double)k / qn: the normalised score change of such a flip (spinsystem.py:394) */
 } eco_graphs_t;
 
 size_t eco_graphs_workspace_bytes(int32_t G, int32_t N);
@@ -115,6 +118,7 @@ typedef struct {
     float*         imm_tab;         /* [T+1]  termination immanency per step (spinsystem.py:509-511)         */
     float*         xn;              /* [B, 3, NP] per-vertex observables: spin, s*h/mlr, time since flip     */
     float*         xg;              /* [B, 4]  global observables rows 3..6                                  */
+    float*         frac_tab;        /* [N+1]  (float)((double)k / N): observable row 5 (spinsystem.py:513-514)  */
 } eco_env_t;
 
 size_t eco_env_workspace_bytes(int32_t B, int32_t N, int32_t T);
