@@ -38,7 +38,10 @@ using namespace tc;
 
 constexpr int NPMAX = 208;
 constexpr int CHUNK = 64;        // max vertices per linear-layer chunk (accumulator columns)
-constexpr int THREADS = 256;
+constexpr int SUBS = 2;            // warps per (group, TMEM lane quadrant): they split the 16-column blocks of every epilogue
+constexpr int THREADS = 256 * SUBS;
+constexpr int GROUP_THREADS = 128 * SUBS;
+constexpr int NWARPS = THREADS / 32;
 
 // ---- TMEM column map -------------------------------------------------------------------------------------
 constexpr uint32_t T_ACC0 = 0;       // 208 cols: aggregation / edge accumulator
@@ -59,13 +62,12 @@ constexpr int SM_XF = SM_T + 128 * CHUNK * 2;            // float xf[7][208] ove
 constexpr int SM_DEG = SM_T + 2 * 128 * CHUNK * 2;       // float rdeg[208] = 1/deg
 constexpr int SM_QP = SM_DEG + NPMAX * 4;                // float qpart[4][208]
 constexpr int MAXCHUNKS = (NPMAX + CHUNK - 1) / CHUNK;
-constexpr int SM_PP = SM_QP + 4 * NPMAX * 4;             // float ppart[MAXCHUNKS][64]: per-chunk pooled partial sums
-constexpr int SM_WR = SM_PP + MAXCHUNKS * 64 * 4;        // float w_read[128]
-constexpr int SM_MISC = SM_WR + 128 * 4;                 // float pooled[64], c0, reductions
-constexpr int SM_TOTAL = SM_MISC + 64 * 4 + 64 + 8 * 8 + 8 * 8;
+constexpr int SM_PP = SM_QP + 4 * NPMAX * 4;             // float ppart[MAXCHUNKS][SUBS][64]: per-chunk pooled partial sums
+constexpr int SM_MISC = SM_PP + MAXCHUNKS * SUBS * 64 * 4;   // c0, cross-warp reductions (pooled[64] overlays rdeg)
+constexpr int SM_TOTAL = SM_MISC + 64 + 16 * 4 + 16 * 4;
 static_assert(NPMAX * NPMAX * 2 <= 2 * 128 * NPMAX * 2, "|A| must fit in the H+E region");
 static_assert(7 * NPMAX * 4 <= 128 * CHUNK * 2, "xf must fit in a chunk buffer");
-static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
+static_assert(SM_TOTAL + 128 <= 227 * 1024, "shared memory budget (dynamic + static)");
 
 // packed weights (uint32 words): [128 stacked rows][k/2] per matrix
 constexpr int PK_WEF = 0;                    // 128 x 32
@@ -104,7 +106,7 @@ struct Ctx {
     uint64_t* bar_all;     // completion of CTA-wide MMA batches (edge contraction, aggregation)
     uint64_t* bar_grp;     // completion of this group's linear MMAs
     uint32_t phase_all, phase_grp;
-    int tid, warp, lane, q, grp;
+    int tid, warp, lane, q, grp, sub;
     int N, NP, NB;
 };
 
@@ -129,7 +131,7 @@ __device__ __forceinline__ void cta_stage_sync() {   // operands written by ever
 __device__ __forceinline__ void grp_stage_sync(const Ctx& c) {   // same, among the 128 threads of one group
     fence_proxy_async();
     tc_fence_before();
-    asm volatile("bar.sync %0, 128;" ::"r"(c.grp + 1) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"r"(c.grp + 1), "n"(GROUP_THREADS) : "memory");
 }
 __device__ __forceinline__ void wait_all(Ctx& c) {
     mbar_wait(c.bar_all, c.phase_all);
@@ -145,19 +147,23 @@ __device__ __forceinline__ void wait_grp(Ctx& c) {
 // weights: global packed [128][KW] words -> registers -> TMEM columns [tcol, tcol + KW); the two warps that share a
 // lane quadrant split the columns.  Split in two so the L2 latency can be hidden behind a barrier / MMA wait.
 template <int KW>
-__device__ __forceinline__ void ldg_weights(const Ctx& c, const uint32_t* __restrict__ pk, uint4 (&buf)[KW / 8]) {
-    // this warp: quadrant q, column groups [grp * KW/16, (grp + 1) * KW/16); buf[2i], buf[2i+1] = the two 4-word halves
-    const uint4* src = reinterpret_cast<const uint4*>(pk) + ((c.q * (KW / 8) + c.grp * (KW / 16)) * 2) * 32 + c.lane;
+__device__ __forceinline__ void ldg_weights(const Ctx& c, const uint32_t* __restrict__ pk, uint4 (&buf)[KW / (8 * SUBS)]) {
+    // this warp: quadrant q, 8-column groups [part * CGP, (part + 1) * CGP); buf[2i], buf[2i+1] = the two 4-word halves
+    constexpr int CGP = KW / (16 * SUBS);
+    const int part = c.grp * SUBS + c.sub;
+    const uint4* src = reinterpret_cast<const uint4*>(pk) + ((c.q * (KW / 8) + part * CGP) * 2) * 32 + c.lane;
 #pragma unroll
-    for (int i = 0; i < KW / 8; ++i) buf[i] = __ldg(src + i * 32);
+    for (int i = 0; i < 2 * CGP; ++i) buf[i] = __ldg(src + i * 32);
 }
 template <int KW>
-__device__ __forceinline__ void sttm_weights(const Ctx& c, const uint4 (&buf)[KW / 8], uint32_t tcol) {
+__device__ __forceinline__ void sttm_weights(const Ctx& c, const uint4 (&buf)[KW / (8 * SUBS)], uint32_t tcol) {
+    constexpr int CGP = KW / (16 * SUBS);
+    const int part = c.grp * SUBS + c.sub;
 #pragma unroll
-    for (int i = 0; i < KW / 16; ++i) {
+    for (int i = 0; i < CGP; ++i) {
         const uint4 a = buf[2 * i], b = buf[2 * i + 1];
         const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        tmem_st_32x32b_x8(tmem_addr(c.tmem, 32 * c.q, tcol + c.grp * (KW / 2) + 8 * i), v);
+        tmem_st_32x32b_x8(tmem_addr(c.tmem, 32 * c.q, tcol + (part * CGP + i) * 8), v);
     }
 }
 
@@ -166,7 +172,7 @@ __device__ __forceinline__ void sttm_weights(const Ctx& c, const uint4 (&buf)[KW
 // 16q + lane/4 + 8*((i>>1)&1) and column blk_col + 8*(i>>2) + 2*(lane&3) + (i&1)  (blk_col relative to col0).
 template <class Fn>
 __device__ __forceinline__ void epilogue(const Ctx& c, uint32_t acc, int col0, int width, Fn fn) {
-    for (int blk = 0; blk < width / 16; ++blk) {
+    for (int blk = c.sub; blk < width / 16; blk += SUBS) {
         uint32_t vh[8], vl[8];
         tmem_ld_16x256b_x2(tmem_addr(c.tmem, 32 * c.q, acc + col0 + 16 * blk), vh);
         tmem_ld_16x256b_x2(tmem_addr(c.tmem, 32 * c.q + 16, acc + col0 + 16 * blk), vl);
@@ -227,7 +233,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     c.smem = smem; c.phase_all = 0; c.phase_grp = 0;
     c.tid = threadIdx.x; c.lane = c.tid & 31;
     c.warp = __shfl_sync(0xffffffffu, c.tid >> 5, 0);     // warp-uniform: MMA issue code stays on the uniform datapath
-    c.q = c.warp & 3; c.grp = c.warp >> 2;
+    c.q = c.warp & 3; c.sub = (c.warp >> 2) % SUBS; c.grp = c.warp / (4 * SUBS);
     c.bar_all = &bars[0]; c.bar_grp = &bars[1 + c.grp];
     c.N = g.N; c.NP = g.NP; c.NB = g.NP >> 3;
     const int N = c.N, NP = c.NP, NB = c.NB;
@@ -236,11 +242,10 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     float* rdeg = reinterpret_cast<float*>(smem + SM_DEG);      // 1 / deg
     float* qpart = reinterpret_cast<float*>(smem + SM_QP);
     float* ppart = reinterpret_cast<float*>(smem + SM_PP);
-    float* s_wread = reinterpret_cast<float*>(smem + SM_WR);
-    float* pooled = reinterpret_cast<float*>(smem + SM_MISC);
-    float* s_c0 = pooled + 64;
-    float* red_val = pooled + 64 + 16;
-    int* red_idx = reinterpret_cast<int*>(pooled + 64 + 32);
+    float* pooled = rdeg;                                         // readout only: the inverse degrees are dead by then
+    float* s_c0 = reinterpret_cast<float*>(smem + SM_MISC);
+    float* red_val = s_c0 + 16;
+    int* red_idx = reinterpret_cast<int*>(s_c0 + 32);
     unsigned char* sA = smem + SM_A;
     unsigned char* sAbs = smem + SM_ABS;
     unsigned char* sH = smem + SM_H;
@@ -251,7 +256,6 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
 
     if (c.warp == 0) tmem_alloc(&tmem_base_s, 512);
     if (c.tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); fence_mbar_init(); }
-    for (int i = c.tid; i < 128; i += THREADS) s_wread[i] = w.w_read[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -305,24 +309,24 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         const int nch = NP >> 4;                       // 16-byte chunks per row
         const int ppr = (nch + 3) >> 2;                // passes per 8-row group
         const int total_passes = NB * ppr;
-        constexpr int MAXIT = (NPMAX / 8 * 4 + 7) / 8;  // 13 passes per warp at N = 208
+        constexpr int MAXIT = (NPMAX / 8 * 4 + NWARPS - 1) / NWARPS;  // passes per warp at N = 208
         uint4 raw[MAXIT];
 #pragma unroll
         for (int k = 0; k < MAXIT; ++k) {
-            const int it = c.warp + 8 * k;
+            const int it = c.warp + NWARPS * k;
             const int ib = it / ppr, ch = (it % ppr) * 4 + (c.lane >> 3);
             raw[k] = make_uint4(0, 0, 0, 0);
             if (it < total_passes && ch < nch)
                 raw[k] = *reinterpret_cast<const uint4*>(A8 + (size_t)(ib * 8 + (c.lane & 7)) * NP + ch * 16);
         }
-        uint4 wef[4];
+        uint4 wef[32 / (8 * SUBS)];
         ldg_weights<32>(c, pk + PK_WEF, wef);
         TL(2);
         __syncthreads();                                   // xf visible
         TL(3);
         // S = R+ + R-, D = R+ - R- with R+- = ReLU(P +- w0), P = W_x x  -> TMEM A operands (mpnn.py:89-100 factorised)
         {
-            for (int blk = c.grp; blk < nsteps_A; blk += 2) {
+            for (int blk = c.grp * SUBS + c.sub; blk < nsteps_A; blk += 2 * SUBS) {
                 uint32_t sh[4], sl[4], dh[4], dl[4];
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
@@ -353,7 +357,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         TL(4);
 #pragma unroll
         for (int k = 0; k < MAXIT; ++k) {
-            const int it = c.warp + 8 * k;
+            const int it = c.warp + NWARPS * k;
             const int ib = it / ppr, ch = (it % ppr) * 4 + (c.lane >> 3);
             if (it < total_passes && ch < nch) {
                 // 16 int8 in {-1,0,1} -> bf16 pairs: spread two bytes into halfwords (PRMT), |a| = (h & 1) * 0x3F80,
@@ -394,7 +398,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
           __syncwarp();
         }
         {   // layer-0 weights: L2 -> registers while the edge contraction runs, registers -> TMEM once S / D are dead
-            uint4 wm[8], wu[8];
+            uint4 wm[64 / (8 * SUBS)], wu[64 / (8 * SUBS)];
             ldg_weights<64>(c, pk + PK_WM, wm);
             ldg_weights<64>(c, pk + PK_WU, wu);
             wait_all(c);
@@ -405,7 +409,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
 
         // ================= stage 1: h0 (CUDA cores), edge embeddings e =====================================
         {   // h0 = ReLU(W_init x): thread owns features fa, fb and 4 vertices of every 16-vertex block (epilogue mapping)
-            for (int blk = c.grp; blk < nsteps_A; blk += 2) {
+            for (int blk = c.grp * SUBS + c.sub; blk < nsteps_A; blk += 2 * SUBS) {
                 float v[8];
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
@@ -440,11 +444,11 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                 }
                 store_block(c, sT, bc, v);
             });
-            if (c.q == 0 && c.lane == 0) next_s[c.grp][slot] = atomicAdd(&chunk_ctr[0], 1);
+            if (c.q == 0 && c.sub == 0 && c.lane == 0) next_s[c.grp][slot] = atomicAdd(&chunk_ctr[0], 1);
             TL(10);
             grp_stage_sync(c);
             TL(11);
-            if (c.q == 0) {
+            if (c.q == 0 && c.sub == 0) {
                 tc_fence_after();
                 if (elect_one()) { issue_part(c, acc1, T_WEF, sT, 0, width, false); mma_commit(c.bar_grp); }
                 __syncwarp();
@@ -484,7 +488,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
               __syncwarp();
             }
             if (l > 0) {                        // the previous layer's MMAs all retired (barrier above): overwrite weights
-                uint4 wm[8], wu[8];             // (loaded after the barrier: before it, the global loads would contend
+                uint4 wm[64 / (8 * SUBS)], wu[64 / (8 * SUBS)];   // (loaded after the barrier: before it, the global loads would contend
                 ldg_weights<64>(c, pk + PK_WM + l * 128 * 64, wm);   //  with the slower group's shared-memory stores)
                 ldg_weights<64>(c, pk + PK_WU + l * 128 * 64, wu);
                 sttm_weights<64>(c, wm, T_WM);
@@ -494,7 +498,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                 __syncthreads();
             }
             int ci = c.grp;
-            if (ci < nchunks && c.q == 0) {     // W_m e-half of the first chunk does not depend on the aggregation
+            if (ci < nchunks && c.q == 0 && c.sub == 0) {     // W_m e-half of the first chunk does not depend on the aggregation
                 int c0, width;
                 chunk_span(ci, nblocks, nchunks, c0, width);
                 tc_fence_after();
@@ -512,11 +516,11 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                     for (int i = 0; i < 8; ++i) v[i] = v[i] * rdeg[c0 + bc + 8 * (i >> 2) + 2 * (c.lane & 3) + (i & 1)];
                     store_block(c, sT, bc, v);
                 });
-                if (c.q == 0 && c.lane == 0) next_s[c.grp][slot] = atomicAdd(&chunk_ctr[1 + l], 1);
+                if (c.q == 0 && c.sub == 0 && c.lane == 0) next_s[c.grp][slot] = atomicAdd(&chunk_ctr[1 + l], 1);
                 TL(30);
                 grp_stage_sync(c);
                 TL(31);
-                if (c.q == 0) {
+                if (c.q == 0 && c.sub == 0) {
                     tc_fence_after();
                     if (elect_one()) {
                         issue_part(c, acc1, T_WM, sT, 0, width, true);                    // += W_m[:, :64] agg
@@ -538,7 +542,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                 TL(34);
                 grp_stage_sync(c);
                 TL(35);
-                if (c.q == 0) {
+                if (c.q == 0 && c.sub == 0) {
                     tc_fence_after();
                     if (elect_one()) {
                         issue_part(c, T_ACC0 + c0, T_WU + 32, sT, 0, width, true);         // += W_u[:, 64:] m
@@ -564,7 +568,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                     // readout partials straight from the fp32 registers (mpnn.py:143-159)
                     // (pooled sums are kept per chunk and added in chunk order, so the result does not depend on
                     //  which group happened to process which chunk)
-                    const float wa = s_wread[64 + fa], wb = s_wread[64 + fa + 8];
+                    const float wa = __ldg(w.w_read + 64 + fa), wb = __ldg(w.w_read + 64 + fa + 8);
                     float pool_a = 0.f, pool_b = 0.f;
                     epilogue(c, T_ACC0, c0, width, [&](int bc, float (&v)[8]) {
                         float qv[4];
@@ -591,8 +595,8 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                     pool_a += __shfl_xor_sync(0xffffffffu, pool_a, 1); pool_a += __shfl_xor_sync(0xffffffffu, pool_a, 2);
                     pool_b += __shfl_xor_sync(0xffffffffu, pool_b, 1); pool_b += __shfl_xor_sync(0xffffffffu, pool_b, 2);
                     if ((c.lane & 3) == 0) {
-                        ppart[ci * 64 + fa] = pool_a;
-                        ppart[ci * 64 + fa + 8] = pool_b;
+                        ppart[(ci * SUBS + c.sub) * 64 + fa] = pool_a;
+                        ppart[(ci * SUBS + c.sub) * 64 + fa + 8] = pool_b;
                     }
                 }
                 TL(38);
@@ -605,11 +609,11 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         __syncthreads();
         if (c.tid < 64) {
             float t = 0.f;
-            for (int k = 0; k < nchunks; ++k) t += ppart[k * 64 + c.tid];
+            for (int k = 0; k < nchunks * SUBS; ++k) t += ppart[k * 64 + c.tid];
             pooled[c.tid] = t / (float)N;
         }
         __syncthreads();
-        {   // p = W_p pooled: 4 lanes per output feature, then c0 = w_r[0:64] . ReLU(p) + b
+        if (c.tid < 256) {   // p = W_p pooled: 4 lanes per output feature, then c0 = w_r[0:64] . ReLU(p) + b
             const int f = c.tid >> 2, part = c.tid & 3;
             const float4* wp = reinterpret_cast<const float4*>(w.w_pool + f * 64 + part * 16);
             float p = 0.f;
@@ -621,7 +625,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             }
             p += __shfl_xor_sync(0xffffffffu, p, 1);
             p += __shfl_xor_sync(0xffffffffu, p, 2);
-            float t = part == 0 ? s_wread[f] * fmaxf(p, 0.f) : 0.f;
+            float t = part == 0 ? __ldg(w.w_read + f) * fmaxf(p, 0.f) : 0.f;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
             if (c.lane == 0) red_val[c.warp] = t;
@@ -629,7 +633,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         __syncthreads();
         if (c.tid == 0) {
             float t = w.b_read[0];
-            for (int ww = 0; ww < THREADS / 32; ++ww) t += red_val[ww];
+            for (int ww = 0; ww < 8; ++ww) t += red_val[ww];
             *s_c0 = t;
         }
         __syncthreads();
@@ -671,7 +675,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
 }  // namespace
 
 bool mpnn_tc_supported(const eco_graphs_t* g) { return g->N <= NPMAX && (g->reserved & 1); }
-size_t mpnn_tc_scratch_bytes(int, int) { return 8 * 1024 * 8 + 256; }   // room for the optional debug timeline
+size_t mpnn_tc_scratch_bytes(int, int) { return NWARPS * 1024 * 8 + 256; }   // room for the optional debug timeline
 size_t mpnn_tc_packed_bytes() { return (size_t)PK_WORDS * 4; }
 
 int launch_mpnn_pack(const eco_mpnn_t* w, void* packed, cudaStream_t st) {
@@ -694,7 +698,7 @@ int launch_mpnn_tc(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int3
     const int grid = B < n_sm ? B : n_sm;
     prof_begin(ECO_PROF_MPNN, st);
     static const bool timeline = getenv("ECO_TC_TIMELINE") != nullptr;
-    if (timeline) ECO_CUDA(cudaMemsetAsync(scratch, 0, 8 * 1024 * 8, st));
+    if (timeline) ECO_CUDA(cudaMemsetAsync(scratch, 0, NWARPS * 1024 * 8, st));
     mpnn_tc_kernel<<<grid, THREADS, SM_TOTAL, st>>>(*g, *w, B, gidx, xn, xg, norm_max, q, actions,
                                                     timeline ? (unsigned long long*)scratch : nullptr);
     prof_end(ECO_PROF_MPNN, st);
