@@ -300,8 +300,12 @@ def run_ours(args):
         pk = peaks()
         avg_mpnn_s = mpnn_ms / max(mpnn_n, 1) / 1000.0
         ach = flops_mpnn(n) * B / avg_mpnn_s / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if used_impl == "tcgen05" and os.path.exists(tpath):      # dram bytes per launch from the committed ncu capture
+            traffic = json.load(open(tpath))["mpnn_tc_kernel"]["dram_bytes_per_launch"]
         roof = {"bound": "tensor", "kernel": "mpnn_forward_argmax (%s)" % used_impl, "achieved": ach,
-                "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": None,
+                "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": traffic,
                 "peak_source": pk["source"] + " (bf16 sustained)", "avg_launch_ms": avg_mpnn_s * 1e3,
                 "launches_timed": mpnn_n, "share_of_step": mpnn_ms / ms_total,
                 "flops_per_launch": flops_mpnn(n) * B}
