@@ -296,15 +296,8 @@ class DQN:
         return loss.item()
 
     def _allreduce_grads(self):
-        """One collective per update: flatten the 12 gradient tensors (58 425 floats), average, scatter back."""
-        params = [p for p in self.network.parameters() if p.grad is not None]
-        flat = torch.cat([p.grad.reshape(-1) for p in params])
-        sharding.allreduce_mean_(flat)
-        off = 0
-        for p in params:
-            n = p.grad.numel()
-            p.grad.copy_(flat[off:off + n].view_as(p.grad))
-            off += n
+        """One collective per update over a flat buffer of the 12 gradient tensors (sharding.allreduce_mean_grads)."""
+        sharding.allreduce_mean_grads(self.network.parameters())
 
     def act(self, state, is_training_ready=True):
         """epsilon-greedy for all lock-step environments (reference dqn.py:453-465, one environment there)."""

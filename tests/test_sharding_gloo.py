@@ -30,6 +30,16 @@ def _worker(rank, world, port, n_total, q):
     alls = sharding.gather_best(spins, n_total)
     grad = torch.full((7,), float(rank + 1))
     sharding.allreduce_mean_(grad)
+    # gradient averaging over a module: one flat collective, scattered back in place
+    torch.manual_seed(0)
+    lin = torch.nn.Sequential(torch.nn.Linear(3, 4), torch.nn.Linear(4, 2, bias=False))
+    lin(torch.full((5, 3), float(rank + 1))).sum().backward()
+    local = [p.grad.clone() for p in lin.parameters()]
+    flat = sharding.allreduce_mean_grads(lin.parameters())
+    others = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(others, torch.cat([g.reshape(-1) for g in local]))
+    assert torch.allclose(flat, sum(others) / world)
+    assert torch.allclose(torch.cat([p.grad.reshape(-1) for p in lin.parameters()]), flat)
     per_graph = sharding.best_per_graph(allc, torch.arange(n_total) % 3, 3)
     q.put((rank, lo, hi, allc.tolist(), alls[:, 0].tolist(), grad.tolist(), per_graph.tolist()))
     dist.destroy_process_group()
