@@ -451,6 +451,238 @@ env_step_sw_kernel(const eco_graphs_t g, const eco_env_t env, const int policy, 
     if (new_best && active && lane < env.NW) env.diff_bits[(size_t)b * env.NW + lane] = 0u;   // NW <= 8 <= TPE... see launch
 }
 
+// ------------------------------------------------------------------------------------------------ step, 128 < N <= 256
+// Bulk-copy (TMA) staged variant: persistent warps, one episode per warp at a time, a 3-deep shared-memory ring per
+// warp.  While episode e is processed from shared memory, the 1-D bulk copies (cp.async.bulk, completion on an
+// mbarrier) of episode e+2 -- spins, local fields, last-flip steps, the scalar block and row `a` of its adjacency -- and
+// the visited-set slot of episode e+1 are already in flight, so no global-load latency sits on the per-episode path.
+// Same arithmetic as env_step_kernel (bit-exact); caller-supplied actions only (the greedy policy needs the fields to
+// pick the row).
+namespace tma {
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    const long long t0 = clock64();
+    while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+        if (!ok && clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+}  // namespace tma
+
+constexpr int TMA_STAGES = 3;
+constexpr int TMA_WARPS = 4;
+struct __align__(16) TmaStage {
+    int8_t spins[256];
+    int16_t h[256];
+    uint16_t lf[256];
+    int8_t jrow[256];
+    eco_episode_t ep;
+};
+
+__global__ void __launch_bounds__(TMA_WARPS * 32, 6)
+env_step_tma_kernel(const eco_graphs_t g, const eco_env_t env, const int32_t* __restrict__ actions,
+                    double* __restrict__ reward_out, uint8_t* __restrict__ done_out, int32_t* __restrict__ hist_a,
+                    double* __restrict__ hist_r, double* __restrict__ hist_s) {
+    __shared__ TmaStage ring[TMA_WARPS][TMA_STAGES];
+    __shared__ uint64_t bars[TMA_WARPS][TMA_STAGES];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long wglobal = (long long)blockIdx.x * TMA_WARPS + warp;
+    const long long wtotal = (long long)gridDim.x * TMA_WARPS;
+    const int N = env.N, NP = env.NP, NCH = NP >> 3;
+    const bool has = lane < NCH;
+    const bool use_tab = (g.reserved & 1) != 0;
+    if (lane == 0)
+        for (int s = 0; s < TMA_STAGES; ++s) tma::mbar_init(&bars[warp][s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+
+    auto issue = [&](long long b, int a, int gi, int st) {          // lane 0: bulk copies of episode b into stage st
+        TmaStage& S = ring[warp][st];
+        uint64_t* bar = &bars[warp][st];
+        tma::mbar_expect_tx(bar, (uint32_t)(NP + 2 * NP + 2 * NP + NP + sizeof(eco_episode_t)));
+        tma::bulk_g2s(S.spins, env.spins + (size_t)b * NP, NP, bar);
+        tma::bulk_g2s(S.h, env.hfield + (size_t)b * NP, 2 * NP, bar);
+        tma::bulk_g2s(S.lf, env.last_flip + (size_t)b * NP, 2 * NP, bar);
+        tma::bulk_g2s(S.jrow, g.J + ((size_t)gi * NP + a) * NP, NP, bar);
+        tma::bulk_g2s(&S.ep, env.ep + b, sizeof(eco_episode_t), bar);
+    };
+    auto clamp_action = [&](int a) { return (a < 0 || a >= N) ? 0 : a; };
+
+    // prologue: episodes e0, e0 + wtotal in flight; action / graph of the third one in registers
+    long long b0 = wglobal;
+    int a_cur = 0, gi_cur = 0, a_n1 = 0, gi_n1 = 0, a_n2 = 0, gi_n2 = 0;
+    if (b0 < env.B) { a_cur = actions[b0]; gi_cur = env.graph_idx[b0]; }
+    if (b0 + wtotal < env.B) { a_n1 = actions[b0 + wtotal]; gi_n1 = env.graph_idx[b0 + wtotal]; }
+    if (b0 + 2 * wtotal < env.B) { a_n2 = actions[b0 + 2 * wtotal]; gi_n2 = env.graph_idx[b0 + 2 * wtotal]; }
+    if (lane == 0) {
+        if (b0 < env.B) issue(b0, clamp_action(a_cur), gi_cur, 0);
+        if (b0 + wtotal < env.B) issue(b0 + wtotal, clamp_action(a_n1), gi_n1, 1);
+    }
+    uint32_t phase_bits = 0;      // parity per stage
+    int st = 0;
+
+    for (long long b = b0; b < env.B; b += wtotal) {
+        TmaStage& S = ring[warp][st];
+        // ---- keep the pipeline full: bulk copies of episode b + 2*wtotal, action / graph of b + 3*wtotal -------
+        const long long b2 = b + 2 * wtotal, b3 = b + 3 * wtotal;
+        int a_n3 = 0, gi_n3 = 0;
+        if (b3 < env.B) { a_n3 = actions[b3]; gi_n3 = env.graph_idx[b3]; }
+        if (lane == 0 && b2 < env.B) issue(b2, clamp_action(a_n2), gi_n2, (st + 2) % TMA_STAGES);
+
+        tma::mbar_wait(&bars[warp][st], (phase_bits >> st) & 1u);
+        phase_bits ^= 1u << st;
+
+        // ---- episode b from shared memory ---------------------------------------------------------------------
+        const int gi = gi_cur;
+        int a = a_cur;
+        const int4 e0 = *reinterpret_cast<const int4*>(&S.ep);
+        const int4 e1 = *(reinterpret_cast<const int4*>(&S.ep) + 1);
+        const int flags = e1.y;
+        const int step_new = e0.x + 1;
+        bool active = !(flags & (FLAG_DONE | FLAG_STOPPED)) && step_new <= env.T;
+        if (a < 0 || a >= N) { a = 0; active = false; }
+        V8s s, j; V8h h; V8u l;
+        s.v = make_uint2(0, 0); j.v = make_uint2(0, 0); h.v = make_uint4(0, 0, 0, 0); l.v = make_uint4(0, 0, 0, 0);
+        if (has) {
+            s.v = *reinterpret_cast<const uint2*>(S.spins + lane * 8);
+            j.v = *reinterpret_cast<const uint2*>(S.jrow + lane * 8);
+            h.v = *reinterpret_cast<const uint4*>(S.h + lane * 8);
+            l.v = *reinterpret_cast<const uint4*>(S.lf + lane * 8);
+        }
+        const int s_a_old = S.spins[a];
+        const int h_a_old = S.h[a];
+        const int s_a_new = -s_a_old;
+        const int delta = s_a_old * h_a_old;                            // spinsystem.py:393
+        const double mlr = g.gscal[(size_t)gi * 4 + 0];
+        const float* gtab = g.gain_tab + (size_t)gi * (2 * NP + 1) + NP;
+
+        // lane 0: scalar state, dependent lookups requested now, used after the vertex loop
+        double sc0 = 0, sc1 = 0, sc2 = 0, sc3 = 0, total_reward = 0, delta_n = 0, qn = 1.0;
+        ulonglong2 key = make_ulonglong2(0, 0), zob = make_ulonglong2(0, 0);
+        uint32_t old_word = 0;
+        if (lane == 0) {
+            sc0 = S.ep.score; sc1 = S.ep.nscore; sc2 = S.ep.best_score; sc3 = S.ep.best_nscore;
+            key = make_ulonglong2(S.ep.key[0], S.ep.key[1]);
+            total_reward = S.ep.total_reward;
+            zob = *reinterpret_cast<const ulonglong2*>(env.zobrist + 2 * a);
+            old_word = env.diff_bits[(size_t)b * env.NW + (a >> 5)];
+            if (use_tab) delta_n = __ldg(g.dn_tab + (size_t)gi * (2 * NP + 1) + NP + delta);
+            else qn = g.gscal[(size_t)gi * 4 + 1];
+        }
+        const uint64_t k0 = key.x ^ zob.x, k1 = key.y ^ zob.y;
+        uint64_t* tab = env.visited + (size_t)b * env.HCAP * 2;
+        uint32_t slot = (uint32_t)(k0 ^ (k0 >> 29)) & (env.HCAP - 1);
+        ulonglong2 tv = make_ulonglong2(0, 0);
+        if (lane == 0 && active && env.use_basin) tv = *reinterpret_cast<const ulonglong2*>(tab + 2 * slot);
+
+        int nimp = 0;
+        if (has && active) {
+            float* x0 = env.xn + (size_t)b * 3 * NP + lane * 8;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float f0[4], f1[4], f2[4];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const int k = half * 4 + kk;
+                    const int i = lane * 8 + k;
+                    int si = s.b[k];
+                    if (i == a) { si = s_a_new; s.b[k] = (int8_t)si; l.h[k] = (uint16_t)step_new; }
+                    const int hi = h.h[k] + 2 * j.b[k] * s_a_new;
+                    h.h[k] = (int16_t)hi;
+                    const int gain = si * hi;
+                    nimp += gain > 0;
+                    f0[kk] = (float)si;
+                    f1[kk] = use_tab ? __ldg(gtab + gain) : feat_gain(gain, mlr);
+                    f2[kk] = __ldg(env.tsf_tab + (step_new - l.h[k]));
+                }
+                *reinterpret_cast<float4*>(x0 + 4 * half) = make_float4(f0[0], f0[1], f0[2], f0[3]);
+                *reinterpret_cast<float4*>(x0 + NP + 4 * half) = make_float4(f1[0], f1[1], f1[2], f1[3]);
+                *reinterpret_cast<float4*>(x0 + 2 * NP + 4 * half) = make_float4(f2[0], f2[1], f2[2], f2[3]);
+            }
+            *reinterpret_cast<uint4*>(env.hfield + (size_t)b * NP + lane * 8) = h.v;
+            if ((a >> 3) == lane) {
+                *reinterpret_cast<uint2*>(env.spins + (size_t)b * NP + lane * 8) = s.v;
+                *reinterpret_cast<uint4*>(env.last_flip + (size_t)b * NP + lane * 8) = l.v;
+            }
+        }
+        nimp = group_sum<32>(nimp);
+
+        int new_best = 0;
+        eco_episode_t* ep = env.ep + b;
+        if (lane == 0 && active) {
+            if (!use_tab) delta_n = __ddiv_rn((double)delta, qn);           // :394
+            const double score = __dadd_rn(sc0, (double)delta);             // :399
+            const double nscore = __dadd_rn(sc1, delta_n);                  // :400
+            const double best_score = sc2, best_nscore = sc3;
+            const int cut = e0.y + delta;
+            double rew = 0.0;
+            if (score > best_score) rew = __dsub_rn(nscore, best_nscore);   // :418-424
+            int n_visited = e1.z;
+            if (env.use_basin) {                                            // :443-457
+                const uint64_t w0 = k0 ^ VISITED_SALT0, w1 = k1 ^ VISITED_SALT1;
+                bool is_new = false;
+                for (int probe = 0; probe < env.HCAP; ++probe) {
+                    if (tv.x == 0 && tv.y == 0) {
+                        *reinterpret_cast<ulonglong2*>(tab + 2 * slot) = make_ulonglong2(w0, w1);
+                        is_new = true; ++n_visited;
+                        break;
+                    }
+                    if (tv.x == w0 && tv.y == w1) break;
+                    slot = (slot + 1) & (env.HCAP - 1);
+                    tv = *reinterpret_cast<const ulonglong2*>(tab + 2 * slot);
+                }
+                if (nimp == 0 && is_new) rew = __dadd_rn(rew, env.basin_reward);
+            }
+            int dist = e0.w + (((old_word >> (a & 31)) & 1u) ? -1 : 1);
+            int best_cut = e0.z;
+            double nbs = best_score, nbn = best_nscore;
+            if (score > best_score) { nbs = score; nbn = nscore; best_cut = cut; dist = 0; new_best = 1; }   // :459-463
+            const int done = step_new == env.T;                             // :541-544
+            int4* epw = reinterpret_cast<int4*>(ep);
+            epw[0] = make_int4(step_new, cut, best_cut, dist);
+            epw[1] = make_int4(nimp, flags | (done ? FLAG_DONE : 0), n_visited, 0);
+            *reinterpret_cast<double2*>(&ep->score) = make_double2(score, nscore);
+            *reinterpret_cast<double2*>(&ep->best_score) = make_double2(nbs, nbn);
+            *reinterpret_cast<ulonglong2*>(&ep->key[0]) = make_ulonglong2(k0, k1);
+            *reinterpret_cast<double2*>(&ep->total_reward) = make_double2(__dadd_rn(total_reward, rew), rew);
+            float4 xg;                                                      // rows 3..6 (spinsystem.py:509-527)
+            xg.x = (float)__ddiv_rn(fabs(__dsub_rn(score, nbs)), mlr);
+            xg.y = (float)dist;
+            xg.z = __ldg(env.frac_tab + nimp);
+            xg.w = __ldg(env.imm_tab + step_new);
+            *reinterpret_cast<float4*>(env.xg + (size_t)b * 4) = xg;
+            if (reward_out) reward_out[b] = rew;
+            if (done_out) done_out[b] = (uint8_t)done;
+            const size_t hidx = (size_t)b * env.T + (step_new - 1);
+            if (hist_a) hist_a[hidx] = a;
+            if (hist_r) hist_r[hidx] = rew;
+            if (hist_s) hist_s[hidx] = score;
+            if (!new_best) env.diff_bits[(size_t)b * env.NW + (a >> 5)] = old_word ^ (1u << (a & 31));
+        } else if (lane == 0) {
+            if (reward_out) reward_out[b] = 0.0;
+            if (done_out) done_out[b] = 1;
+        }
+        new_best = __shfl_sync(0xffffffffu, new_best, 0);
+        if (new_best && active && lane < env.NW) env.diff_bits[(size_t)b * env.NW + lane] = 0u;
+
+        __syncwarp();                 // every lane is done with this stage before it is refilled two iterations on
+        st = (st + 1) % TMA_STAGES;
+        a_cur = a_n1; gi_cur = gi_n1; a_n1 = a_n2; gi_n1 = gi_n2; a_n2 = a_n3; gi_n2 = gi_n3;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ reset
 template <int TPE, bool BLOCK>
 __global__ void __launch_bounds__(BLOCK ? TPE : 128)
@@ -579,7 +811,15 @@ int launch_env_step(const eco_graphs_t* g, eco_env_t* env, int policy, const int
         if (NP_ <= 32) ECO_SW(4);
         else if (NP_ <= 64) ECO_SW(8);
         else if (NP_ <= 128) ECO_SW(16);
-        else if (NP_ <= 256) ECO_SW(32);
+        else if (NP_ <= 256) {
+            if (policy == ECO_POLICY_ACTIONS && B_ >= 4096) {      // bulk-copy staged, persistent warps
+                static int n_sm = 0;
+                if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+                long long blocks = (B_ + TMA_WARPS - 1) / TMA_WARPS;
+                if (blocks > (long long)n_sm * 6) blocks = (long long)n_sm * 6;
+                env_step_tma_kernel<<<(unsigned)blocks, TMA_WARPS * 32, 0, st>>>(*g, *env, actions, reward, done, ha, hr, hs);
+            } else ECO_SW(32);
+        }
         else if (NP_ <= 1024) env_step_kernel<128, true><<<(unsigned)B_, 128, 0, st>>>(*g, *env, policy, actions, reward, done, ha, hr, hs);
         else env_step_kernel<256, true><<<(unsigned)B_, 256, 0, st>>>(*g, *env, policy, actions, reward, done, ha, hr, hs);
 #undef ECO_SW
