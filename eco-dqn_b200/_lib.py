@@ -17,7 +17,8 @@ i32 = C.c_int32
 
 class Graphs(C.Structure):
     _fields_ = [("G", i32), ("N", i32), ("NP", i32), ("reserved", i32),
-                ("J", vp), ("gscal", vp), ("deg", vp), ("gstat", vp), ("dmax", vp), ("gain_tab", vp), ("dn_tab", vp)]
+                ("J", vp), ("gscal", vp), ("deg", vp), ("gstat", vp), ("dmax", vp), ("gain_tab", vp), ("dn_tab", vp),
+                ("tc_ops", vp)]
 
 
 class Episode(C.Structure):

@@ -6,6 +6,8 @@
 //   src/envs/score_solver.py:367-375  set_max_local_reward    mlr = max over NON-ZERO weighted degrees
 //   src/networks/mpnn.py:34-38        get_normalisation       deg_i = max(1, #{j : J_ij != 0})
 // All sums are integer (int8 couplings), hence exact and identical to the reference's fp64 sums.
+#include <cuda_bf16.h>
+
 #include "eco_common.cuh"
 
 namespace eco {
@@ -109,6 +111,31 @@ __global__ void __launch_bounds__(256) graph_prepare_kernel(eco_graphs_t g, int 
     for (int k = threadIdx.x; k <= 2 * NP; k += blockDim.x) {
         tab[k] = (float)__ddiv_rn((double)(k - NP), mlr_d);
         dtab[k] = __ddiv_rn((double)(k - NP), qn_d);                  // delta_score / quality normaliser (spinsystem.py:394)
+    }
+    // bf16 operand images of J and |J| for the tensor-core MPNN (mpnn_tc.cu): element (r, c) of the K-major operand
+    // lives in core matrix (rb = r / 8, cb = c / 8) at byte ((cb * NP/8 + rb) * 8 + r % 8) * 16 + (c % 8) * 2, i.e.
+    // exactly the shared-memory layout, so an episode fetches each image with one bulk copy.  int8 is exact in bf16.
+    if (g.tc_ops != nullptr) {
+        const int NB = NP >> 3;
+        uint4* img_a = reinterpret_cast<uint4*>(g.tc_ops + (size_t)gi * 2 * NP * NP);
+        uint4* img_abs = img_a + (size_t)NP * NP / 8;
+        for (int idx = threadIdx.x; idx < NB * NB * 8; idx += blockDim.x) {
+            const int r7 = idx & 7, rb = (idx >> 3) % NB, cb = (idx >> 3) / NB;
+            const int8_t* src = J + (size_t)(rb * 8 + r7) * NP + cb * 8;
+            const uint2 raw = *reinterpret_cast<const uint2*>(src);
+            uint32_t wa[4], wb[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const uint32_t word = e < 2 ? raw.x : raw.y;
+                const int v0 = (int)(int8_t)(word >> (16 * (e & 1))), v1 = (int)(int8_t)(word >> (16 * (e & 1) + 8));
+                wa[e] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn((float)v0)) |
+                        ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn((float)v1)) << 16);
+                wb[e] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn((float)abs(v0))) |
+                        ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn((float)abs(v1))) << 16);
+            }
+            img_a[idx] = make_uint4(wa[0], wa[1], wa[2], wa[3]);
+            img_abs[idx] = make_uint4(wb[0], wb[1], wb[2], wb[3]);
+        }
     }
 }
 

@@ -226,6 +226,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             dbg[(threadIdx.x >> 5) * 1024 + dbg_n++] = ((unsigned long long)(id) << 48) | (clock64() & 0xFFFFFFFFFFFFull); \
     } while (0)
     __shared__ uint64_t bars[3];
+    __shared__ uint64_t bar_ops[2];   // arrival of the bulk copies of the adjacency operand images: 0 = A, 1 = |A|
     __shared__ uint32_t tmem_base_s;
     __shared__ int chunk_ctr[4];      // dynamic chunk hand-out: edge-feature stage + 3 layers
     __shared__ int next_s[2][2];      // per group, double buffered: next chunk index, published across the group barrier
@@ -255,7 +256,11 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     const uint32_t* pk = reinterpret_cast<const uint32_t*>(w.packed);
 
     if (c.warp == 0) tmem_alloc(&tmem_base_s, 512);
-    if (c.tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); fence_mbar_init(); }
+    if (c.tid == 0) {
+        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+        mbar_init(&bar_ops[0], 1); mbar_init(&bar_ops[1], 1);
+        fence_mbar_init();
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -265,23 +270,38 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     const int nblocks = NP >> 4;
     const int nchunks = chunk_count(nblocks);
 
+    // The adjacency operands come ready-made (graph_prepare.cu: bf16 images of J and |J| in this kernel's core-matrix
+    // layout): one bulk copy each, issued as soon as the previous episode's last reader of the destination retired, so
+    // the transfer of episode e+1 runs under the layers / readout of episode e.
+    const uint32_t ops_bytes = (uint32_t)NP * NP * 2;
+    auto fetch_ops = [&](int which, int episode) {          // one thread
+        const uint16_t* src = g.tc_ops + ((size_t)graph_idx[episode] * 2 + which) * NP * NP;
+        mbar_expect_tx(&bar_ops[which], ops_bytes);
+        bulk_g2s(which ? smem + SM_ABS : smem + SM_A, src, ops_bytes, &bar_ops[which]);
+    };
+    if (c.tid == 0 && (int)blockIdx.x < B) { fetch_ops(0, blockIdx.x); fetch_ops(1, blockIdx.x); }
+    uint32_t ops_phase = 0;
+
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
         const int gi = graph_idx[b];
-        const int8_t* A8 = g.J + (size_t)gi * NP * NP;
         const float rdmax = 1.f / (norm_max < 0.f ? (float)max(g.gstat[(size_t)gi * 4], 1) : dmax_set);
-
-        // pull the next episode's adjacency towards L2 while this one computes
-        if (b + (int)gridDim.x < B) {
-            const int8_t* nxt = g.J + (size_t)graph_idx[b + gridDim.x] * NP * NP;
-            for (int off = c.tid * 128; off < NP * NP; off += THREADS * 128)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + off));
-        }
 
         TL(1);
         // ================= stage 0: operands of the edge contraction ======================================
         if (c.tid < 4) chunk_ctr[c.tid] = 2;              // chunks 0 / 1 are pre-assigned to group 0 / 1
         // this thread's rows of the two small input weights (features fa, fb), issued early so the latency is hidden
         const int fa = 16 * c.q + (c.lane >> 2), fb = fa + 8;
+        // this vertex's observations and degree first (they gate the first barrier), then the weight rows
+        const bool has_v = c.tid < NP;                 // NP <= 208 < THREADS: one vertex per thread
+        float xin0 = 0.f, xin1 = 0.f, xin2 = 0.f, degv = 1.f;
+        float4 gl = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_v) {
+            xin0 = xn[((size_t)b * 3 + 0) * NP + c.tid];
+            xin1 = xn[((size_t)b * 3 + 1) * NP + c.tid];
+            xin2 = xn[((size_t)b * 3 + 2) * NP + c.tid];
+            degv = g.deg[(size_t)gi * NP + c.tid];
+            gl = *reinterpret_cast<const float4*>(xg + (size_t)b * 4);
+        }
         float wxa[8], wxb[8], wia[7], wib[7];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {       // row 63 of the 63 x 8 edge weight does not exist: zero
@@ -290,35 +310,19 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         }
 #pragma unroll
         for (int k = 0; k < 7; ++k) { wia[k] = __ldg(w.w_init + fa * 7 + k); wib[k] = __ldg(w.w_init + fb * 7 + k); }
-        for (int i = c.tid; i < NP; i += THREADS) {
+        if (has_v) {
+            const int i = c.tid;
             const bool ok = i < N;
-            xf[0 * NPMAX + i] = ok ? xn[((size_t)b * 3 + 0) * NP + i] : 0.f;
-            xf[1 * NPMAX + i] = ok ? xn[((size_t)b * 3 + 1) * NP + i] : 0.f;
-            xf[2 * NPMAX + i] = ok ? xn[((size_t)b * 3 + 2) * NP + i] : 0.f;
-            const float4 gl = *reinterpret_cast<const float4*>(xg + (size_t)b * 4);
+            xf[0 * NPMAX + i] = ok ? xin0 : 0.f;
+            xf[1 * NPMAX + i] = ok ? xin1 : 0.f;
+            xf[2 * NPMAX + i] = ok ? xin2 : 0.f;
             xf[3 * NPMAX + i] = ok ? gl.x : 0.f;
             xf[4 * NPMAX + i] = ok ? gl.y : 0.f;
             xf[5 * NPMAX + i] = ok ? gl.z : 0.f;
             xf[6 * NPMAX + i] = ok ? gl.w : 0.f;
-            const float d = g.deg[(size_t)gi * NP + i];
-            rdeg[i] = __fdividef(1.f, d);
+            rdeg[i] = __fdividef(1.f, degv);
         }
         for (int i = c.tid; i < 4 * NPMAX; i += THREADS) qpart[i] = 0.f;
-        // adjacency int8 -> bf16 A and |A| (K-major B operands): a warp converts 8 rows x 64 bytes per pass.  All of a
-        // warp's loads are issued first; the S / D operands are computed while they are in flight.
-        const int nch = NP >> 4;                       // 16-byte chunks per row
-        const int ppr = (nch + 3) >> 2;                // passes per 8-row group
-        const int total_passes = NB * ppr;
-        constexpr int MAXIT = (NPMAX / 8 * 4 + NWARPS - 1) / NWARPS;  // passes per warp at N = 208
-        uint4 raw[MAXIT];
-#pragma unroll
-        for (int k = 0; k < MAXIT; ++k) {
-            const int it = c.warp + NWARPS * k;
-            const int ib = it / ppr, ch = (it % ppr) * 4 + (c.lane >> 3);
-            raw[k] = make_uint4(0, 0, 0, 0);
-            if (it < total_passes && ch < nch)
-                raw[k] = *reinterpret_cast<const uint4*>(A8 + (size_t)(ib * 8 + (c.lane & 7)) * NP + ch * 16);
-        }
         uint4 wef[32 / (8 * SUBS)];
         ldg_weights<32>(c, pk + PK_WEF, wef);
         TL(2);
@@ -355,34 +359,13 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         }
         sttm_weights<32>(c, wef, T_WEF);
         TL(4);
-#pragma unroll
-        for (int k = 0; k < MAXIT; ++k) {
-            const int it = c.warp + NWARPS * k;
-            const int ib = it / ppr, ch = (it % ppr) * 4 + (c.lane >> 3);
-            if (it < total_passes && ch < nch) {
-                // 16 int8 in {-1,0,1} -> bf16 pairs: spread two bytes into halfwords (PRMT), |a| = (h & 1) * 0x3F80,
-                // sign = bit 7 moved to bit 15
-                const uint32_t x[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
-                uint32_t wa[8], wb[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const uint32_t h = __byte_perm(x[e >> 1], 0, (e & 1) ? 0x4342 : 0x4140);   // [b_lo, 0, b_hi, 0]
-                    wb[e] = (h & 0x00010001u) * 0x3F80u;
-                    wa[e] = wb[e] | ((h << 8) & 0x80008000u);
-                }
-                const int off0 = ((2 * ch) * NB + ib) * 128 + (c.lane & 7) * 16;
-                const int off1 = off0 + NB * 128;
-                *reinterpret_cast<uint4*>(sA + off0) = make_uint4(wa[0], wa[1], wa[2], wa[3]);
-                *reinterpret_cast<uint4*>(sA + off1) = make_uint4(wa[4], wa[5], wa[6], wa[7]);
-                *reinterpret_cast<uint4*>(sAbs + off0) = make_uint4(wb[0], wb[1], wb[2], wb[3]);
-                *reinterpret_cast<uint4*>(sAbs + off1) = make_uint4(wb[4], wb[5], wb[6], wb[7]);
-            }
-        }
         tmem_st_wait();
         TL(5);
         cta_stage_sync();
         TL(6);
         if (c.warp == 0) {
+          mbar_wait(&bar_ops[0], ops_phase);        // A and |A| of this episode have landed (async proxy -> async proxy)
+          mbar_wait(&bar_ops[1], ops_phase);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t idesc = instr_desc_bf16(128, NP, false, false);
@@ -508,6 +491,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             TL(22);
             wait_all(c);
             TL(23);
+            if (l == 2 && c.tid == 0 && b + (int)gridDim.x < B) fetch_ops(0, b + gridDim.x);   // A has no reader left
             while (ci < nchunks) {
                 int c0, width;
                 chunk_span(ci, nblocks, nchunks, c0, width);
@@ -606,7 +590,19 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         TL(40);
 
         // ================= stage 3: readout + argmax ========================================================
+        // the readout weights do not depend on the episode: request them ahead of the barriers
+        float4 wpv[4] = {};
+        float wrf = 0.f;
+        if (c.tid < 256) {
+            const float4* wp = reinterpret_cast<const float4*>(w.w_pool + (c.tid >> 2) * 64 + (c.tid & 3) * 16);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) wpv[k4] = __ldg(wp + k4);
+            wrf = __ldg(w.w_read + (c.tid >> 2));
+        }
+        const float bread = __ldg(w.b_read);
         __syncthreads();
+        if (c.tid == 0 && b + (int)gridDim.x < B) fetch_ops(1, b + gridDim.x);   // H / E (which |A| overlays) have no reader left
+        ops_phase ^= 1u;
         if (c.tid < 64) {
             float t = 0.f;
             for (int k = 0; k < nchunks * SUBS; ++k) t += ppart[k * 64 + c.tid];
@@ -614,35 +610,31 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         }
         __syncthreads();
         if (c.tid < 256) {   // p = W_p pooled: 4 lanes per output feature, then c0 = w_r[0:64] . ReLU(p) + b
-            const int f = c.tid >> 2, part = c.tid & 3;
-            const float4* wp = reinterpret_cast<const float4*>(w.w_pool + f * 64 + part * 16);
+            const int part = c.tid & 3;
             float p = 0.f;
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
-                const float4 wv = __ldg(wp + k4);
+                const float4 wv = wpv[k4];
                 const float* pv = pooled + part * 16 + 4 * k4;
                 p = fmaf(wv.x, pv[0], p); p = fmaf(wv.y, pv[1], p); p = fmaf(wv.z, pv[2], p); p = fmaf(wv.w, pv[3], p);
             }
             p += __shfl_xor_sync(0xffffffffu, p, 1);
             p += __shfl_xor_sync(0xffffffffu, p, 2);
-            float t = part == 0 ? __ldg(w.w_read + f) * fmaxf(p, 0.f) : 0.f;
+            float t = part == 0 ? wrf * fmaxf(p, 0.f) : 0.f;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-            if (c.lane == 0) red_val[c.warp] = t;
+            if (c.lane == 0) s_c0[1 + c.warp] = t;
         }
         __syncthreads();
-        if (c.tid == 0) {
-            float t = w.b_read[0];
-            for (int ww = 0; ww < 8; ++ww) t += red_val[ww];
-            *s_c0 = t;
-        }
-        __syncthreads();
+        float c0v = bread;                                  // every thread adds the 8 partials in the same order
+#pragma unroll
+        for (int ww = 0; ww < 8; ++ww) c0v += s_c0[1 + ww];
         {
             float bv = -INFINITY;
             int bi = 0x7fffffff;
             if (c.tid < N) {
                 const int i = c.tid;
-                bv = *s_c0 + ((qpart[i] + qpart[NPMAX + i]) + (qpart[2 * NPMAX + i] + qpart[3 * NPMAX + i]));
+                bv = c0v + ((qpart[i] + qpart[NPMAX + i]) + (qpart[2 * NPMAX + i] + qpart[3 * NPMAX + i]));
                 bi = i;
                 if (q_out) q_out[(size_t)b * NP + i] = bv;
             }
@@ -674,7 +666,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
 
 }  // namespace
 
-bool mpnn_tc_supported(const eco_graphs_t* g) { return g->N <= NPMAX && (g->reserved & 1); }
+bool mpnn_tc_supported(const eco_graphs_t* g) { return g->N <= NPMAX && (g->reserved & 1) && g->tc_ops != nullptr; }
 size_t mpnn_tc_scratch_bytes(int, int) { return NWARPS * 1024 * 8 + 256; }   // room for the optional debug timeline
 size_t mpnn_tc_packed_bytes() { return (size_t)PK_WORDS * 4; }
 

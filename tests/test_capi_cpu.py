@@ -43,7 +43,7 @@ def test_library_exports_every_declared_symbol(L):
 def test_struct_layouts_match_header():
     import eco_dqn_b200._lib as _lib
     assert C.sizeof(_lib.Episode) == 96
-    assert C.sizeof(_lib.Graphs) == 16 + 7 * 8
+    assert C.sizeof(_lib.Graphs) == 16 + 8 * 8
     assert C.sizeof(_lib.Env) == 32 + 8 + 13 * 8
     assert C.sizeof(_lib.Mpnn) == 13 * 8
 

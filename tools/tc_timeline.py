@@ -13,7 +13,7 @@ import bench  # noqa: E402
 import eco_dqn_b200.engine as engine  # noqa: E402
 from eco_dqn_b200 import _lib  # noqa: E402
 
-G = B = 148 * 6
+G = B = int(os.environ.get("ECO_TL_B", str(148 * 6)))
 n, T = 200, 400
 J = bench.ba_graphs(G, n, 4, seed=0)
 gs = engine.GraphSet(J)
