@@ -282,26 +282,33 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     if (c.tid == 0 && (int)blockIdx.x < B) { fetch_ops(0, blockIdx.x); fetch_ops(1, blockIdx.x); }
     uint32_t ops_phase = 0;
 
+    // per-episode inputs, requested one episode ahead (during the previous readout): this thread's vertex observations
+    // and degree, the four graph-level observations, the graph's maximum degree
+    const bool has_v = c.tid < NP;                 // NP <= 208 < THREADS: one vertex per thread
+    float xin0 = 0.f, xin1 = 0.f, xin2 = 0.f, degv = 1.f;
+    float4 gl = make_float4(0.f, 0.f, 0.f, 0.f);
+    int gmaxdeg = 1;
+    auto load_inputs = [&](int e) {
+        const int ge = graph_idx[e];
+        if (has_v) {
+            xin0 = xn[((size_t)e * 3 + 0) * NP + c.tid];
+            xin1 = xn[((size_t)e * 3 + 1) * NP + c.tid];
+            xin2 = xn[((size_t)e * 3 + 2) * NP + c.tid];
+            degv = g.deg[(size_t)ge * NP + c.tid];
+        }
+        gl = *reinterpret_cast<const float4*>(xg + (size_t)e * 4);
+        gmaxdeg = g.gstat[(size_t)ge * 4];
+    };
+    if ((int)blockIdx.x < B) load_inputs(blockIdx.x);
+
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
-        const int gi = graph_idx[b];
-        const float rdmax = 1.f / (norm_max < 0.f ? (float)max(g.gstat[(size_t)gi * 4], 1) : dmax_set);
+        const float rdmax = 1.f / (norm_max < 0.f ? (float)max(gmaxdeg, 1) : dmax_set);
 
         TL(1);
         // ================= stage 0: operands of the edge contraction ======================================
         if (c.tid < 4) chunk_ctr[c.tid] = 2;              // chunks 0 / 1 are pre-assigned to group 0 / 1
         // this thread's rows of the two small input weights (features fa, fb), issued early so the latency is hidden
         const int fa = 16 * c.q + (c.lane >> 2), fb = fa + 8;
-        // this vertex's observations and degree first (they gate the first barrier), then the weight rows
-        const bool has_v = c.tid < NP;                 // NP <= 208 < THREADS: one vertex per thread
-        float xin0 = 0.f, xin1 = 0.f, xin2 = 0.f, degv = 1.f;
-        float4 gl = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (has_v) {
-            xin0 = xn[((size_t)b * 3 + 0) * NP + c.tid];
-            xin1 = xn[((size_t)b * 3 + 1) * NP + c.tid];
-            xin2 = xn[((size_t)b * 3 + 2) * NP + c.tid];
-            degv = g.deg[(size_t)gi * NP + c.tid];
-            gl = *reinterpret_cast<const float4*>(xg + (size_t)b * 4);
-        }
         float wxa[8], wxb[8], wia[7], wib[7];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {       // row 63 of the 63 x 8 edge weight does not exist: zero
@@ -316,12 +323,14 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             xf[0 * NPMAX + i] = ok ? xin0 : 0.f;
             xf[1 * NPMAX + i] = ok ? xin1 : 0.f;
             xf[2 * NPMAX + i] = ok ? xin2 : 0.f;
-            xf[3 * NPMAX + i] = ok ? gl.x : 0.f;
-            xf[4 * NPMAX + i] = ok ? gl.y : 0.f;
-            xf[5 * NPMAX + i] = ok ? gl.z : 0.f;
-            xf[6 * NPMAX + i] = ok ? gl.w : 0.f;
             rdeg[i] = __fdividef(1.f, degv);
         }
+        // observations 3..6 are the same for every vertex: their share of W_x x and W_init x is one constant per feature
+        // (padded vertices get it too; nothing reads their columns: no edges, masked out of the pooling and the argmax)
+        float cxa = wxa[4] * gl.x, cxb = wxb[4] * gl.x, cia = wia[3] * gl.x, cib = wib[3] * gl.x;
+        cxa = fmaf(wxa[5], gl.y, cxa); cxb = fmaf(wxb[5], gl.y, cxb); cia = fmaf(wia[4], gl.y, cia); cib = fmaf(wib[4], gl.y, cib);
+        cxa = fmaf(wxa[6], gl.z, cxa); cxb = fmaf(wxb[6], gl.z, cxb); cia = fmaf(wia[5], gl.z, cia); cib = fmaf(wib[5], gl.z, cib);
+        cxa = fmaf(wxa[7], gl.w, cxa); cxb = fmaf(wxb[7], gl.w, cxb); cia = fmaf(wia[6], gl.w, cia); cib = fmaf(wib[6], gl.w, cib);
         for (int i = c.tid; i < 4 * NPMAX; i += THREADS) qpart[i] = 0.f;
         uint4 wef[32 / (8 * SUBS)];
         ldg_weights<32>(c, pk + PK_WEF, wef);
@@ -335,9 +344,9 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     const int n0 = 16 * blk + 8 * half + 2 * (c.lane & 3);
-                    float pa0 = 0.f, pa1 = 0.f, pb0 = 0.f, pb1 = 0.f;
+                    float pa0 = cxa, pa1 = cxa, pb0 = cxb, pb1 = cxb;
 #pragma unroll
-                    for (int k = 0; k < 7; ++k) {
+                    for (int k = 0; k < 3; ++k) {
                         const float2 x = *reinterpret_cast<const float2*>(xf + k * NPMAX + n0);
                         pa0 = fmaf(wxa[1 + k], x.x, pa0); pa1 = fmaf(wxa[1 + k], x.y, pa1);
                         pb0 = fmaf(wxb[1 + k], x.x, pb0); pb1 = fmaf(wxb[1 + k], x.y, pb1);
@@ -397,9 +406,9 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     const int n0 = 16 * blk + 8 * half + 2 * (c.lane & 3);
-                    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+                    float a0 = cia, a1 = cia, b0 = cib, b1 = cib;
 #pragma unroll
-                    for (int k = 0; k < 7; ++k) {
+                    for (int k = 0; k < 3; ++k) {
                         const float2 x = *reinterpret_cast<const float2*>(xf + k * NPMAX + n0);
                         a0 = fmaf(wia[k], x.x, a0); a1 = fmaf(wia[k], x.y, a1);
                         b0 = fmaf(wib[k], x.x, b0); b1 = fmaf(wib[k], x.y, b1);
@@ -600,6 +609,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             wrf = __ldg(w.w_read + (c.tid >> 2));
         }
         const float bread = __ldg(w.b_read);
+        if (b + (int)gridDim.x < B) load_inputs(b + gridDim.x);     // next episode's inputs: in flight during the readout
         __syncthreads();
         if (c.tid == 0 && b + (int)gridDim.x < B) fetch_ops(1, b + gridDim.x);   // H / E (which |A| overlays) have no reader left
         ops_phase ^= 1u;
