@@ -42,6 +42,8 @@ constexpr int SUBS = 2;            // warps per (group, TMEM lane quadrant): the
 constexpr int THREADS = 256 * SUBS;
 constexpr int GROUP_THREADS = 128 * SUBS;
 constexpr int NWARPS = THREADS / 32;
+constexpr int LAUNCH_THREADS = THREADS + 32;   // + warp 16: issues the N x N contractions (tcgen05.mma issue blocks while the
+                                               //   tensor queue is full -- 26 MMAs -- which must not hold up an epilogue warp)
 
 // ---- TMEM column map -------------------------------------------------------------------------------------
 constexpr uint32_t T_ACC0 = 0;       // 208 cols: aggregation / edge accumulator
@@ -74,8 +76,6 @@ constexpr int PK_WEF = 0;                    // 128 x 32
 constexpr int PK_WM = PK_WEF + 128 * 32;     // 3 x 128 x 64
 constexpr int PK_WU = PK_WM + 3 * 128 * 64;  // 3 x 128 x 64
 constexpr int PK_WORDS = PK_WU + 3 * 128 * 64;
-
-__device__ __forceinline__ uint16_t bf16_bits(float x) { return __bfloat16_as_ushort(__float2bfloat16_rn(x)); }
 
 // Packed layout per matrix (KW words per stacked row): word (r, c) with r = 32q + lane, c = 8cg + 4h + j lives at
 // ((((q * KW/8 + cg) * 2 + h) * 32 + lane) * 4 + j): every LDG.128 of a warp in ldg_weights() is 512 contiguous bytes.
@@ -123,10 +123,11 @@ __device__ __forceinline__ void chunk_span(int ci, int nblocks, int nch, int& c0
     width = 16 * (base + (ci < extra ? 1 : 0));
 }
 
-__device__ __forceinline__ void cta_stage_sync() {   // operands written by everyone (smem: generic proxy; TMEM: st/ld retired)
+__device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 3, %0;" ::"n"(THREADS) : "memory"); }
+__device__ __forceinline__ void cta_stage_sync() {   // operands written by every worker (smem: generic proxy; TMEM: st/ld retired)
     fence_proxy_async();
     tc_fence_before();
-    __syncthreads();
+    workers_sync();
 }
 __device__ __forceinline__ void grp_stage_sync(const Ctx& c) {   // same, among the 128 threads of one group
     fence_proxy_async();
@@ -213,7 +214,7 @@ __device__ __forceinline__ void issue_part(const Ctx& c, uint32_t acc_col, uint3
         mma_ts(c.tmem + acc_col, c.tmem + tw + 8 * (i >> 1), d + (uint64_t)(16 * i), idesc, accumulate || i > 0);
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(LAUNCH_THREADS, 1)
 mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int32_t* __restrict__ graph_idx,
                const float* __restrict__ xn, const float* __restrict__ xg, const float norm_max,
                float* __restrict__ q_out, int32_t* __restrict__ act_out, unsigned long long* __restrict__ dbg) {
@@ -225,11 +226,10 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         if (dbg != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && dbg_n < 1024)                \
             dbg[(threadIdx.x >> 5) * 1024 + dbg_n++] = ((unsigned long long)(id) << 48) | (clock64() & 0xFFFFFFFFFFFFull); \
     } while (0)
-    __shared__ uint64_t bars[3];
+    __shared__ uint64_t bars[5];      // 0: edge contraction; 1, 2: linear MMAs of group 0 / 1; 3, 4: aggregation columns of group 0 / 1
+    __shared__ uint64_t sig[2];       // workers -> contraction issuer: 0 edge operands ready, 1 layer inputs ready
     __shared__ uint64_t bar_ops[2];   // arrival of the bulk copies of the adjacency operand images: 0 = A, 1 = |A|
     __shared__ uint32_t tmem_base_s;
-    __shared__ int chunk_ctr[4];      // dynamic chunk hand-out: edge-feature stage + 3 layers
-    __shared__ int next_s[2][2];      // per group, double buffered: next chunk index, published across the group barrier
     Ctx c;
     c.smem = smem; c.phase_all = 0; c.phase_grp = 0;
     c.tid = threadIdx.x; c.lane = c.tid & 31;
@@ -257,8 +257,9 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
 
     if (c.warp == 0) tmem_alloc(&tmem_base_s, 512);
     if (c.tid == 0) {
-        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+        for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
         mbar_init(&bar_ops[0], 1); mbar_init(&bar_ops[1], 1);
+        mbar_init(&sig[0], 1); mbar_init(&sig[1], 1);
         fence_mbar_init();
     }
     tc_fence_before();
@@ -269,6 +270,14 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     const int nsteps_A = NP >> 4;                         // k-steps over vertices
     const int nblocks = NP >> 4;
     const int nchunks = chunk_count(nblocks);
+    // group 0 owns the first half of the chunks, group 1 the rest: the aggregation is issued (and committed) per half, so
+    // group 0 starts its epilogues while group 1's columns are still being computed -- the two groups stay out of phase
+    // and one's MMAs run under the other's epilogue
+    const int chunk_split = (nchunks + 1) / 2;
+    const int cs = c.grp == 0 ? 0 : chunk_split, ce = c.grp == 0 ? chunk_split : nchunks;
+    int ncols0 = NP;                                      // columns of group 0's chunks
+    if (chunk_split < nchunks) { int w_; chunk_span(chunk_split, nblocks, nchunks, ncols0, w_); }
+    uint32_t phase_half = 0;
 
     // The adjacency operands come ready-made (graph_prepare.cu: bf16 images of J and |J| in this kernel's core-matrix
     // layout): one bulk copy each, issued as soon as the previous episode's last reader of the destination retired, so
@@ -280,7 +289,6 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         bulk_g2s(which ? smem + SM_ABS : smem + SM_A, src, ops_bytes, &bar_ops[which]);
     };
     if (c.tid == 0 && (int)blockIdx.x < B) { fetch_ops(0, blockIdx.x); fetch_ops(1, blockIdx.x); }
-    uint32_t ops_phase = 0;
 
     // per-episode inputs, requested one episode ahead (during the previous readout): this thread's vertex observations
     // and degree, the four graph-level observations, the graph's maximum degree
@@ -299,14 +307,53 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         gl = *reinterpret_cast<const float4*>(xg + (size_t)e * 4);
         gmaxdeg = g.gstat[(size_t)ge * 4];
     };
-    if ((int)blockIdx.x < B) load_inputs(blockIdx.x);
+    if (c.warp == NWARPS) {
+        // ================= contraction issuer ===============================================================
+        uint32_t sp0 = 0, sp1 = 0, op = 0;
+        for (int b = blockIdx.x; b < B; b += gridDim.x) {
+            mbar_wait(&sig[0], sp0); sp0 ^= 1u;
+            mbar_wait(&bar_ops[0], op);               // A and |A| of this episode have landed (async proxy -> async proxy)
+            mbar_wait(&bar_ops[1], op); op ^= 1u;
+            tc_fence_after();
+            if (elect_one()) {                        // edge contraction  S |A| + D A
+                const uint32_t idesc = instr_desc_bf16(128, NP, false, false);
+                const uint64_t bd_abs = smem_desc(smem_u32(sAbs), NB * 128, 128);
+                const uint64_t bd_a = smem_desc(smem_u32(sA), NB * 128, 128);
+                const uint64_t kstep = (uint64_t)((2 * NB * 128) >> 4);
+                for (int ks = 0; ks < nsteps_A; ++ks) {
+                    mma_ts(c.tmem + T_ACC0, c.tmem + T_S + 8 * ks, bd_abs + ks * kstep, idesc, ks > 0);
+                    mma_ts(c.tmem + T_ACC0, c.tmem + T_D + 8 * ks, bd_a + ks * kstep, idesc, true);
+                }
+                mma_commit(c.bar_all);
+            }
+            __syncwarp();
+            for (int l = 0; l < 3; ++l) {
+                mbar_wait(&sig[1], sp1); sp1 ^= 1u;
+                tc_fence_after();
+                if (elect_one()) {                    // agg^T = H^T A  (both hi and lo rows in one M=128 chain), per half
+                    const uint64_t ad = smem_desc(smem_u32(sH), 2048, 128);
+                    const uint64_t bstep = (uint64_t)((2 * NB * 128) >> 4);
+                    for (int half = 0; half < 2; ++half) {
+                        const int n0 = half ? ncols0 : 0, ncols = half ? NP - ncols0 : ncols0;
+                        if (ncols == 0) break;
+                        const uint32_t idesc = instr_desc_bf16(128, ncols, false, false);
+                        const uint64_t bd = smem_desc(smem_u32(sA) + (n0 >> 3) * 128, NB * 128, 128);
+                        for (int ks = 0; ks < nsteps_A; ++ks)
+                            mma_ss(c.tmem + T_ACC0 + n0, ad + (uint64_t)ks * (4096 >> 4), bd + ks * bstep, idesc, ks > 0);
+                        mma_commit(&bars[3 + half]);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    if (c.warp < NWARPS && (int)blockIdx.x < B) load_inputs(blockIdx.x);
 
-    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    for (int b = blockIdx.x; b < B && c.warp < NWARPS; b += gridDim.x) {
         const float rdmax = 1.f / (norm_max < 0.f ? (float)max(gmaxdeg, 1) : dmax_set);
 
         TL(1);
         // ================= stage 0: operands of the edge contraction ======================================
-        if (c.tid < 4) chunk_ctr[c.tid] = 2;              // chunks 0 / 1 are pre-assigned to group 0 / 1
         // this thread's rows of the two small input weights (features fa, fb), issued early so the latency is hidden
         const int fa = 16 * c.q + (c.lane >> 2), fb = fa + 8;
         float wxa[8], wxb[8], wia[7], wib[7];
@@ -335,7 +382,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         uint4 wef[32 / (8 * SUBS)];
         ldg_weights<32>(c, pk + PK_WEF, wef);
         TL(2);
-        __syncthreads();                                   // xf visible
+        workers_sync();                                   // xf visible
         TL(3);
         // S = R+ + R-, D = R+ - R- with R+- = ReLU(P +- w0), P = W_x x  -> TMEM A operands (mpnn.py:89-100 factorised)
         {
@@ -372,23 +419,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         TL(5);
         cta_stage_sync();
         TL(6);
-        if (c.warp == 0) {
-          mbar_wait(&bar_ops[0], ops_phase);        // A and |A| of this episode have landed (async proxy -> async proxy)
-          mbar_wait(&bar_ops[1], ops_phase);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t idesc = instr_desc_bf16(128, NP, false, false);
-            const uint64_t bd_abs = smem_desc(smem_u32(sAbs), NB * 128, 128);
-            const uint64_t bd_a = smem_desc(smem_u32(sA), NB * 128, 128);
-            const uint64_t kstep = (uint64_t)((2 * NB * 128) >> 4);
-            for (int ks = 0; ks < nsteps_A; ++ks) {
-                mma_ts(c.tmem + T_ACC0, c.tmem + T_S + 8 * ks, bd_abs + ks * kstep, idesc, ks > 0);
-                mma_ts(c.tmem + T_ACC0, c.tmem + T_D + 8 * ks, bd_a + ks * kstep, idesc, true);
-            }
-            mma_commit(c.bar_all);
-          }
-          __syncwarp();
-        }
+        if (c.tid == 0) mbar_arrive(&sig[0]);      // -> issuer: S / D are in TMEM (the images of A / |A| arrive by bulk copy)
         {   // layer-0 weights: L2 -> registers while the edge contraction runs, registers -> TMEM once S / D are dead
             uint4 wm[64 / (8 * SUBS)], wu[64 / (8 * SUBS)];
             ldg_weights<64>(c, pk + PK_WM, wm);
@@ -422,8 +453,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         tmem_st_wait();
         TL(8);
         cta_stage_sync();            // xf (overlaying group 1's chunk buffer) is dead from here; weights visible to the MMAs
-        int slot = 0;                 // parity of the hand-out slot (all threads of a group advance it together)
-        for (int ci = c.grp; ci < nchunks;) {
+        for (int ci = cs; ci < ce; ++ci) {
             int c0, width;
             chunk_span(ci, nblocks, nchunks, c0, width);
             // g = (S|A| + D A) / (2 deg); feature 63 = deg / deg_max   (mpnn.py:100-102)
@@ -436,7 +466,6 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                 }
                 store_block(c, sT, bc, v);
             });
-            if (c.q == 0 && c.sub == 0 && c.lane == 0) next_s[c.grp][slot] = atomicAdd(&chunk_ctr[0], 1);
             TL(10);
             grp_stage_sync(c);
             TL(11);
@@ -445,8 +474,6 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                 if (elect_one()) { issue_part(c, acc1, T_WEF, sT, 0, width, false); mma_commit(c.bar_grp); }
                 __syncwarp();
             }
-            const int nxt = next_s[c.grp][slot];
-            slot ^= 1;
             wait_grp(c);
             TL(12);
             epilogue(c, acc1, 0, width, [&](int bc, float (&v)[8]) {
@@ -455,7 +482,6 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                 store_block(c, sE, c0 + bc, v);
             });
             TL(13);
-            ci = nxt;
         }
 
         // ================= stage 2: three message-passing layers (mpnn.py:114-120) ==========================
@@ -466,19 +492,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             TL(20);
             cta_stage_sync();                   // every h / e column of the previous stage is written
             TL(21);
-            if (c.warp == 0) {                  // agg^T = H^T A  (both hi and lo rows in one M=128 chain)
-              tc_fence_after();
-              if (elect_one()) {
-                const uint32_t idesc = instr_desc_bf16(128, NP, false, false);
-                const uint64_t ad = smem_desc(smem_u32(sH), 2048, 128);
-                const uint64_t bd = smem_desc(smem_u32(sA), NB * 128, 128);
-                const uint64_t bstep = (uint64_t)((2 * NB * 128) >> 4);
-                for (int ks = 0; ks < nsteps_A; ++ks)
-                    mma_ss(c.tmem + T_ACC0, ad + (uint64_t)ks * (4096 >> 4), bd + ks * bstep, idesc, ks > 0);
-                mma_commit(c.bar_all);
-              }
-              __syncwarp();
-            }
+            if (c.tid == 0) mbar_arrive(&sig[1]);   // -> issuer: agg^T = H^T A, per half
             if (l > 0) {                        // the previous layer's MMAs all retired (barrier above): overwrite weights
                 uint4 wm[64 / (8 * SUBS)], wu[64 / (8 * SUBS)];   // (loaded after the barrier: before it, the global loads would contend
                 ldg_weights<64>(c, pk + PK_WM + l * 128 * 64, wm);   //  with the slower group's shared-memory stores)
@@ -487,10 +501,10 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                 sttm_weights<64>(c, wu, T_WU);
                 tmem_st_wait();
                 tc_fence_before();
-                __syncthreads();
+                workers_sync();
             }
-            int ci = c.grp;
-            if (ci < nchunks && c.q == 0 && c.sub == 0) {     // W_m e-half of the first chunk does not depend on the aggregation
+            int ci = cs;
+            if (ci < ce && c.q == 0 && c.sub == 0) {          // W_m e-half of the first chunk does not depend on the aggregation
                 int c0, width;
                 chunk_span(ci, nblocks, nchunks, c0, width);
                 tc_fence_after();
@@ -498,10 +512,15 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                 __syncwarp();
             }
             TL(22);
-            wait_all(c);
+            if (cs < ce) {                                    // this group's aggregation columns
+                mbar_wait(&bars[3 + c.grp], phase_half);
+                phase_half ^= 1u;
+                tc_fence_after();
+            }
             TL(23);
-            if (l == 2 && c.tid == 0 && b + (int)gridDim.x < B) fetch_ops(0, b + gridDim.x);   // A has no reader left
-            while (ci < nchunks) {
+            // A has no reader left once the LAST half retired (the halves retire in order)
+            if (l == 2 && c.tid == (chunk_split < nchunks ? THREADS / 2 : 0) && b + (int)gridDim.x < B) fetch_ops(0, b + gridDim.x);
+            while (ci < ce) {
                 int c0, width;
                 chunk_span(ci, nblocks, nchunks, c0, width);
                 epilogue(c, T_ACC0, c0, width, [&](int bc, float (&v)[8]) {
@@ -509,7 +528,6 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                     for (int i = 0; i < 8; ++i) v[i] = v[i] * rdeg[c0 + bc + 8 * (i >> 2) + 2 * (c.lane & 3) + (i & 1)];
                     store_block(c, sT, bc, v);
                 });
-                if (c.q == 0 && c.sub == 0 && c.lane == 0) next_s[c.grp][slot] = atomicAdd(&chunk_ctr[1 + l], 1);
                 TL(30);
                 grp_stage_sync(c);
                 TL(31);
@@ -522,8 +540,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                     }
                     __syncwarp();
                 }
-                const int nxt = next_s[c.grp][slot];
-                slot ^= 1;
+                const int nxt = ci + 1;
                 TL(32);
                 wait_grp(c);
                 TL(33);
@@ -540,7 +557,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                     if (elect_one()) {
                         issue_part(c, T_ACC0 + c0, T_WU + 32, sT, 0, width, true);         // += W_u[:, 64:] m
                         mma_commit(c.bar_grp);
-                        if (nxt < nchunks) {                                             // next chunk's e-half, ahead
+                        if (nxt < ce) {                                                  // next chunk's e-half, ahead
                             int n0, nw;
                             chunk_span(nxt, nblocks, nchunks, n0, nw);
                             issue_part(c, acc1, T_WM + 32, sE, n0 >> 3, nw, false);
@@ -610,15 +627,14 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         }
         const float bread = __ldg(w.b_read);
         if (b + (int)gridDim.x < B) load_inputs(b + gridDim.x);     // next episode's inputs: in flight during the readout
-        __syncthreads();
+        workers_sync();
         if (c.tid == 0 && b + (int)gridDim.x < B) fetch_ops(1, b + gridDim.x);   // H / E (which |A| overlays) have no reader left
-        ops_phase ^= 1u;
         if (c.tid < 64) {
             float t = 0.f;
             for (int k = 0; k < nchunks * SUBS; ++k) t += ppart[k * 64 + c.tid];
             pooled[c.tid] = t / (float)N;
         }
-        __syncthreads();
+        workers_sync();
         if (c.tid < 256) {   // p = W_p pooled: 4 lanes per output feature, then c0 = w_r[0:64] . ReLU(p) + b
             const int part = c.tid & 3;
             float p = 0.f;
@@ -635,7 +651,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
             if (c.lane == 0) s_c0[1 + c.warp] = t;
         }
-        __syncthreads();
+        workers_sync();
         float c0v = bread;                                  // every thread adds the 8 partials in the same order
 #pragma unroll
         for (int ww = 0; ww < 8; ++ww) c0v += s_c0[1 + ww];
@@ -656,7 +672,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             }
             if (c.lane == 0) { red_val[c.warp] = bv; red_idx[c.warp] = bi; }
         }
-        __syncthreads();
+        workers_sync();
         if (c.tid == 0 && act_out) {
             float bv = red_val[0];
             int bi = red_idx[0];
@@ -664,7 +680,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                 if (red_val[ww] > bv || (red_val[ww] == bv && red_idx[ww] < bi)) { bv = red_val[ww]; bi = red_idx[ww]; }
             act_out[b] = bi;
         }
-        __syncthreads();
+        workers_sync();
         TL(41);
     }
 #undef TL
@@ -677,7 +693,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
 }  // namespace
 
 bool mpnn_tc_supported(const eco_graphs_t* g) { return g->N <= NPMAX && (g->reserved & 1) && g->tc_ops != nullptr; }
-size_t mpnn_tc_scratch_bytes(int, int) { return NWARPS * 1024 * 8 + 256; }   // room for the optional debug timeline
+size_t mpnn_tc_scratch_bytes(int, int) { return (NWARPS + 1) * 1024 * 8 + 256; }   // room for the optional debug timeline
 size_t mpnn_tc_packed_bytes() { return (size_t)PK_WORDS * 4; }
 
 int launch_mpnn_pack(const eco_mpnn_t* w, void* packed, cudaStream_t st) {
@@ -700,8 +716,8 @@ int launch_mpnn_tc(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int3
     const int grid = B < n_sm ? B : n_sm;
     prof_begin(ECO_PROF_MPNN, st);
     static const bool timeline = getenv("ECO_TC_TIMELINE") != nullptr;
-    if (timeline) ECO_CUDA(cudaMemsetAsync(scratch, 0, NWARPS * 1024 * 8, st));
-    mpnn_tc_kernel<<<grid, THREADS, SM_TOTAL, st>>>(*g, *w, B, gidx, xn, xg, norm_max, q, actions,
+    if (timeline) ECO_CUDA(cudaMemsetAsync(scratch, 0, (NWARPS + 1) * 1024 * 8, st));
+    mpnn_tc_kernel<<<grid, LAUNCH_THREADS, SM_TOTAL, st>>>(*g, *w, B, gidx, xn, xg, norm_max, q, actions,
                                                     timeline ? (unsigned long long*)scratch : nullptr);
     prof_end(ECO_PROF_MPNN, st);
     ECO_LAUNCH_CHECK();
