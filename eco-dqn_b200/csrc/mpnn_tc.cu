@@ -243,7 +243,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     float* rdeg = reinterpret_cast<float*>(smem + SM_DEG);      // 1 / deg
     float* qpart = reinterpret_cast<float*>(smem + SM_QP);
     float* ppart = reinterpret_cast<float*>(smem + SM_PP);
-    float* pooled = rdeg;                                         // readout only: the inverse degrees are dead by then
+    float* pooled = ppart;                                        // readout only: in place over the first 64 partial sums
     float* s_c0 = reinterpret_cast<float*>(smem + SM_MISC);
     float* red_val = s_c0 + 16;
     int* red_idx = reinterpret_cast<int*>(s_c0 + 32);
@@ -349,6 +349,74 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     }
     if (c.warp < NWARPS && (int)blockIdx.x < B) load_inputs(blockIdx.x);
 
+    // ================= readout + argmax of one episode (mpnn.py:143-159; experiments/utils.py:57-66) =================
+    // Reads only qpart / ppart, which the next episode does not touch before its last layer: it is run while the workers
+    // would otherwise wait for the next episode's edge contraction.
+    auto readout = [&](const int be) {
+        float4 wpv[4] = {};
+        float wrf = 0.f;
+        if (c.tid < 256) {
+            const float4* wp = reinterpret_cast<const float4*>(w.w_pool + (c.tid >> 2) * 64 + (c.tid & 3) * 16);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) wpv[k4] = __ldg(wp + k4);
+            wrf = __ldg(w.w_read + (c.tid >> 2));
+        }
+        const float bread = __ldg(w.b_read);
+        if (c.tid < 64) {                 // (the layer-2 epilogues of both groups are behind a CTA barrier already)
+            float t = 0.f;
+            for (int k = 0; k < nchunks * SUBS; ++k) t += ppart[k * 64 + c.tid];
+            pooled[c.tid] = t / (float)N;
+        }
+        workers_sync();
+        if (c.tid < 256) {   // p = W_p pooled: 4 lanes per output feature, then c0 = w_r[0:64] . ReLU(p) + b
+            const int part = c.tid & 3;
+            float p = 0.f;
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+                const float4 wv = wpv[k4];
+                const float* pv = pooled + part * 16 + 4 * k4;
+                p = fmaf(wv.x, pv[0], p); p = fmaf(wv.y, pv[1], p); p = fmaf(wv.z, pv[2], p); p = fmaf(wv.w, pv[3], p);
+            }
+            p += __shfl_xor_sync(0xffffffffu, p, 1);
+            p += __shfl_xor_sync(0xffffffffu, p, 2);
+            float t = part == 0 ? wrf * fmaxf(p, 0.f) : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (c.lane == 0) s_c0[1 + c.warp] = t;
+        }
+        workers_sync();
+        float c0v = bread;                                  // every thread adds the 8 partials in the same order
+#pragma unroll
+        for (int ww = 0; ww < 8; ++ww) c0v += s_c0[1 + ww];
+        {
+            float bv = -INFINITY;
+            int bi = 0x7fffffff;
+            if (c.tid < N) {
+                const int i = c.tid;
+                bv = c0v + ((qpart[i] + qpart[NPMAX + i]) + (qpart[2 * NPMAX + i] + qpart[3 * NPMAX + i]));
+                bi = i;
+                if (q_out) q_out[(size_t)be * NP + i] = bv;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (c.lane == 0) { red_val[c.warp] = bv; red_idx[c.warp] = bi; }
+        }
+        workers_sync();
+        if (c.tid == 0 && act_out) {
+            float bv = red_val[0];
+            int bi = red_idx[0];
+            for (int ww = 1; ww < THREADS / 32; ++ww)
+                if (red_val[ww] > bv || (red_val[ww] == bv && red_idx[ww] < bi)) { bv = red_val[ww]; bi = red_idx[ww]; }
+            act_out[be] = bi;
+        }
+        workers_sync();                   // red_val / s_c0 / ppart may be reused
+    };
+    int last_b = -1;
+
     for (int b = blockIdx.x; b < B && c.warp < NWARPS; b += gridDim.x) {
         const float rdmax = 1.f / (norm_max < 0.f ? (float)max(gmaxdeg, 1) : dmax_set);
 
@@ -378,7 +446,6 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         cxa = fmaf(wxa[5], gl.y, cxa); cxb = fmaf(wxb[5], gl.y, cxb); cia = fmaf(wia[4], gl.y, cia); cib = fmaf(wib[4], gl.y, cib);
         cxa = fmaf(wxa[6], gl.z, cxa); cxb = fmaf(wxb[6], gl.z, cxb); cia = fmaf(wia[5], gl.z, cia); cib = fmaf(wib[5], gl.z, cib);
         cxa = fmaf(wxa[7], gl.w, cxa); cxb = fmaf(wxb[7], gl.w, cxb); cia = fmaf(wia[6], gl.w, cia); cib = fmaf(wib[6], gl.w, cib);
-        for (int i = c.tid; i < 4 * NPMAX; i += THREADS) qpart[i] = 0.f;
         uint4 wef[32 / (8 * SUBS)];
         ldg_weights<32>(c, pk + PK_WEF, wef);
         TL(2);
@@ -424,6 +491,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             uint4 wm[64 / (8 * SUBS)], wu[64 / (8 * SUBS)];
             ldg_weights<64>(c, pk + PK_WM, wm);
             ldg_weights<64>(c, pk + PK_WU, wu);
+            if (last_b >= 0) readout(last_b);       // the previous episode's readout, under this episode's edge contraction
             wait_all(c);
             TL(7);
             sttm_weights<64>(c, wm, T_WM);
@@ -615,74 +683,15 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         }
         TL(40);
 
-        // ================= stage 3: readout + argmax ========================================================
-        // the readout weights do not depend on the episode: request them ahead of the barriers
-        float4 wpv[4] = {};
-        float wrf = 0.f;
-        if (c.tid < 256) {
-            const float4* wp = reinterpret_cast<const float4*>(w.w_pool + (c.tid >> 2) * 64 + (c.tid & 3) * 16);
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) wpv[k4] = __ldg(wp + k4);
-            wrf = __ldg(w.w_read + (c.tid >> 2));
-        }
-        const float bread = __ldg(w.b_read);
-        if (b + (int)gridDim.x < B) load_inputs(b + gridDim.x);     // next episode's inputs: in flight during the readout
+        // ================= end of the episode's tensor work ==================================================
+        // (its readout runs later, under the next episode's edge contraction)
+        if (b + (int)gridDim.x < B) load_inputs(b + gridDim.x);     // next episode's inputs: in flight from here
         workers_sync();
         if (c.tid == 0 && b + (int)gridDim.x < B) fetch_ops(1, b + gridDim.x);   // H / E (which |A| overlays) have no reader left
-        if (c.tid < 64) {
-            float t = 0.f;
-            for (int k = 0; k < nchunks * SUBS; ++k) t += ppart[k * 64 + c.tid];
-            pooled[c.tid] = t / (float)N;
-        }
-        workers_sync();
-        if (c.tid < 256) {   // p = W_p pooled: 4 lanes per output feature, then c0 = w_r[0:64] . ReLU(p) + b
-            const int part = c.tid & 3;
-            float p = 0.f;
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-                const float4 wv = wpv[k4];
-                const float* pv = pooled + part * 16 + 4 * k4;
-                p = fmaf(wv.x, pv[0], p); p = fmaf(wv.y, pv[1], p); p = fmaf(wv.z, pv[2], p); p = fmaf(wv.w, pv[3], p);
-            }
-            p += __shfl_xor_sync(0xffffffffu, p, 1);
-            p += __shfl_xor_sync(0xffffffffu, p, 2);
-            float t = part == 0 ? wrf * fmaxf(p, 0.f) : 0.f;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-            if (c.lane == 0) s_c0[1 + c.warp] = t;
-        }
-        workers_sync();
-        float c0v = bread;                                  // every thread adds the 8 partials in the same order
-#pragma unroll
-        for (int ww = 0; ww < 8; ++ww) c0v += s_c0[1 + ww];
-        {
-            float bv = -INFINITY;
-            int bi = 0x7fffffff;
-            if (c.tid < N) {
-                const int i = c.tid;
-                bv = c0v + ((qpart[i] + qpart[NPMAX + i]) + (qpart[2 * NPMAX + i] + qpart[3 * NPMAX + i]));
-                bi = i;
-                if (q_out) q_out[(size_t)b * NP + i] = bv;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-            }
-            if (c.lane == 0) { red_val[c.warp] = bv; red_idx[c.warp] = bi; }
-        }
-        workers_sync();
-        if (c.tid == 0 && act_out) {
-            float bv = red_val[0];
-            int bi = red_idx[0];
-            for (int ww = 1; ww < THREADS / 32; ++ww)
-                if (red_val[ww] > bv || (red_val[ww] == bv && red_idx[ww] < bi)) { bv = red_val[ww]; bi = red_idx[ww]; }
-            act_out[b] = bi;
-        }
-        workers_sync();
+        last_b = b;
         TL(41);
     }
+    if (c.warp < NWARPS && last_b >= 0) readout(last_b);
 #undef TL
 
     tc_fence_before();
