@@ -172,7 +172,7 @@ def config_dict(world):
             "step": "one full rollout: reset + T x (MPNN Q-eval + argmax + env step) for the whole batch",
             "n_spins": N_SPINS, "episodes_per_gpu": B_PER_GPU, "env_steps_per_episode": 2 * N_SPINS,
             "graphs_per_gpu": B_PER_GPU, "weights": "pretrained eco/network_best_BA_200spin (reference checkpoint)",
-            "l2": "inputs larger than L2 (int8 adjacency set 164 MB + 50 MB state per GPU); no flush needed",
+            "l2": "inputs larger than L2 (per GPU: bf16 adjacency operand images 708 MB + int8 adjacency 177 MB + 50 MB state); no flush needed",
             "parallelism": "episodes sharded over %d GPU(s), no collective during rollout, all_gather of best cuts" % world}
 
 
