@@ -60,8 +60,8 @@ static void carve_graphs(eco_graphs_t* g, Carver& c, int G, int N) {
     g->deg = c.take<float>((size_t)G * NP);
     g->gstat = c.take<int32_t>((size_t)G * 4);
     g->dmax = c.take<float>(64);
-    g->gain_tab = c.take<float>((size_t)G * (2 * NP + 1));
-    g->dn_tab = c.take<double>((size_t)G * (2 * NP + 1));
+    g->gain_tab = c.take<float>((size_t)G * tab_stride(NP));
+    g->dn_tab = c.take<double>((size_t)G * tab_stride(NP));
     g->tc_ops = N <= 208 ? c.take<uint16_t>((size_t)G * 2 * NP * NP) : nullptr;
 }
 

@@ -10,6 +10,11 @@
 
 namespace eco {
 
+// row stride of the per-graph lookup tables gain_tab / dn_tab: entries k = -NP..NP at [NP + k], padded to a multiple of 4
+// entries so that every row (and the window around k = 0) is 16-byte aligned for bulk copies
+__host__ __device__ inline int tab_stride(int NP) { return 2 * NP + 4; }
+
+
 // ---- error plumbing -------------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);

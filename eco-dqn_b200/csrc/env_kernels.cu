@@ -78,6 +78,9 @@ __device__ __forceinline__ float feat_gain(int gain, double mlr) {
     // row 1: immediate_quality_changes / max_local_reward in fp64, then the driver's fp32 cast
     return (float)__ddiv_rn((double)gain, mlr);
 }
+// (An exact fp32 alternative exists -- __fdiv_rn((float)gain, (float)mlr) equals the fp64-then-fp32 result because double
+// rounding is innocuous for a division when 53 >= 2*24+2 -- but it costs more issue slots than the table lookup: measured
+// 448 us vs 330 us per launch in env_step_tma_kernel.)
 
 // ------------------------------------------------------------------------------------------------ step
 template <int TPE, bool BLOCK>
@@ -327,7 +330,7 @@ env_step_sw_kernel(const eco_graphs_t g, const eco_env_t env, const int policy, 
     if (has && active) j.v = *reinterpret_cast<const uint2*>(g.J + ((size_t)gi * NP + a) * NP + lane * 8);
     const double mlr = g.gscal[(size_t)gi * 4 + 0];
     const bool use_tab = (g.reserved & 1) != 0;       // couplings in {-1,0,1}: |gain| <= degree < NP
-    const float* gtab = g.gain_tab + (size_t)gi * (2 * NP + 1) + NP;
+    const float* gtab = g.gain_tab + (size_t)gi * tab_stride(NP) + NP;
     double qn = 1.0;
     ulonglong2 zob = make_ulonglong2(0, 0);
     uint32_t old_word = 0;
@@ -355,7 +358,7 @@ env_step_sw_kernel(const eco_graphs_t g, const eco_env_t env, const int policy, 
     double delta_n = 0.0;
     if (lane == 0 && active) {
         if (env.use_basin) tv = *reinterpret_cast<const ulonglong2*>(tab + 2 * slot);
-        if (use_tab) delta_n = __ldg(g.dn_tab + (size_t)gi * (2 * NP + 1) + NP + delta);   // requested early, used late
+        if (use_tab) delta_n = __ldg(g.dn_tab + (size_t)gi * tab_stride(NP) + NP + delta);   // requested early, used late
     }
 
     // ---- O(N) local-field update + per-vertex observables ----------------------------------------------
@@ -482,6 +485,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }  // namespace tma
 
 constexpr int TMA_STAGES = 3;
+constexpr int TMA_TSF_MAX = 1024;   // time-since-flip table entries kept in shared memory (T + 1 <= this, else read from global)
 constexpr int TMA_WARPS = 4;
 struct __align__(16) TmaStage {
     int8_t spins[256];
@@ -491,7 +495,7 @@ struct __align__(16) TmaStage {
     eco_episode_t ep;
 };
 
-__global__ void __launch_bounds__(TMA_WARPS * 32, 6)
+__global__ void __launch_bounds__(TMA_WARPS * 32, 4)
 env_step_tma_kernel(const eco_graphs_t g, const eco_env_t env, const int32_t* __restrict__ actions,
                     double* __restrict__ reward_out, uint8_t* __restrict__ done_out, int32_t* __restrict__ hist_a,
                     double* __restrict__ hist_r, double* __restrict__ hist_s) {
@@ -503,10 +507,19 @@ env_step_tma_kernel(const eco_graphs_t g, const eco_env_t env, const int32_t* __
     const int N = env.N, NP = env.NP, NCH = NP >> 3;
     const bool has = lane < NCH;
     const bool use_tab = (g.reserved & 1) != 0;
+    // the two tables every episode indexes with data-dependent addresses live in shared memory (L2 latency otherwise
+    // sits between the loads and the first feature store / the visited-set probe)
+    __shared__ __align__(16) uint64_t s_zob[2 * 256];
+    __shared__ float s_tsf[TMA_TSF_MAX];
+    for (int i = threadIdx.x; i < 2 * NP; i += blockDim.x) s_zob[i] = env.zobrist[i];
+    const bool tsf_shared = env.T + 1 <= TMA_TSF_MAX;
+    if (tsf_shared)
+        for (int i = threadIdx.x; i <= env.T; i += blockDim.x) s_tsf[i] = env.tsf_tab[i];
+    const float* tsf = tsf_shared ? s_tsf : env.tsf_tab;
     if (lane == 0)
         for (int s = 0; s < TMA_STAGES; ++s) tma::mbar_init(&bars[warp][s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncwarp();
+    __syncthreads();
 
     auto issue = [&](long long b, int a, int gi, int st) {          // lane 0: bulk copies of episode b into stage st
         TmaStage& S = ring[warp][st];
@@ -520,26 +533,31 @@ env_step_tma_kernel(const eco_graphs_t g, const eco_env_t env, const int32_t* __
     };
     auto clamp_action = [&](int a) { return (a < 0 || a >= N) ? 0 : a; };
 
-    // prologue: episodes e0, e0 + wtotal in flight; action / graph of the third one in registers
-    long long b0 = wglobal;
-    int a_cur = 0, gi_cur = 0, a_n1 = 0, gi_n1 = 0, a_n2 = 0, gi_n2 = 0;
-    if (b0 < env.B) { a_cur = actions[b0]; gi_cur = env.graph_idx[b0]; }
-    if (b0 + wtotal < env.B) { a_n1 = actions[b0 + wtotal]; gi_n1 = env.graph_idx[b0 + wtotal]; }
-    if (b0 + 2 * wtotal < env.B) { a_n2 = actions[b0 + 2 * wtotal]; gi_n2 = env.graph_idx[b0 + 2 * wtotal]; }
+    // prologue: the first D = TMA_STAGES - 1 episodes of this warp in flight; action / graph of the next one in registers
+    constexpr int D = TMA_STAGES - 1;
+    const long long b0 = wglobal;
+    int an[D + 1], gn[D + 1];       // action / graph index of episodes b, b + wtotal, ..., b + D * wtotal
+#pragma unroll
+    for (int k = 0; k <= D; ++k) {
+        an[k] = 0; gn[k] = 0;
+        if (b0 + k * wtotal < env.B) { an[k] = actions[b0 + k * wtotal]; gn[k] = env.graph_idx[b0 + k * wtotal]; }
+    }
     if (lane == 0) {
-        if (b0 < env.B) issue(b0, clamp_action(a_cur), gi_cur, 0);
-        if (b0 + wtotal < env.B) issue(b0 + wtotal, clamp_action(a_n1), gi_n1, 1);
+#pragma unroll
+        for (int k = 0; k < D; ++k)
+            if (b0 + k * wtotal < env.B) issue(b0 + k * wtotal, clamp_action(an[k]), gn[k], k);
     }
     uint32_t phase_bits = 0;      // parity per stage
     int st = 0;
 
     for (long long b = b0; b < env.B; b += wtotal) {
         TmaStage& S = ring[warp][st];
-        // ---- keep the pipeline full: bulk copies of episode b + 2*wtotal, action / graph of b + 3*wtotal -------
-        const long long b2 = b + 2 * wtotal, b3 = b + 3 * wtotal;
-        int a_n3 = 0, gi_n3 = 0;
-        if (b3 < env.B) { a_n3 = actions[b3]; gi_n3 = env.graph_idx[b3]; }
-        if (lane == 0 && b2 < env.B) issue(b2, clamp_action(a_n2), gi_n2, (st + 2) % TMA_STAGES);
+        // ---- keep the pipeline full: bulk copies of episode b + D*wtotal, action / graph of b + (D+1)*wtotal ----
+        const long long bD = b + D * wtotal, bN = b + (D + 1) * wtotal;
+        int a_new = 0, gi_new = 0;
+        if (bN < env.B) { a_new = actions[bN]; gi_new = env.graph_idx[bN]; }
+        if (lane == 0 && bD < env.B) issue(bD, clamp_action(an[D]), gn[D], (st + D) % TMA_STAGES);
+        const int a_cur = an[0], gi_cur = gn[0];
 
         tma::mbar_wait(&bars[warp][st], (phase_bits >> st) & 1u);
         phase_bits ^= 1u << st;
@@ -566,7 +584,7 @@ env_step_tma_kernel(const eco_graphs_t g, const eco_env_t env, const int32_t* __
         const int s_a_new = -s_a_old;
         const int delta = s_a_old * h_a_old;                            // spinsystem.py:393
         const double mlr = g.gscal[(size_t)gi * 4 + 0];
-        const float* gtab = g.gain_tab + (size_t)gi * (2 * NP + 1) + NP;
+        const float* gtab = g.gain_tab + (size_t)gi * tab_stride(NP) + NP;
 
         // lane 0: scalar state, dependent lookups requested now, used after the vertex loop
         double sc0 = 0, sc1 = 0, sc2 = 0, sc3 = 0, total_reward = 0, delta_n = 0, qn = 1.0;
@@ -576,9 +594,9 @@ env_step_tma_kernel(const eco_graphs_t g, const eco_env_t env, const int32_t* __
             sc0 = S.ep.score; sc1 = S.ep.nscore; sc2 = S.ep.best_score; sc3 = S.ep.best_nscore;
             key = make_ulonglong2(S.ep.key[0], S.ep.key[1]);
             total_reward = S.ep.total_reward;
-            zob = *reinterpret_cast<const ulonglong2*>(env.zobrist + 2 * a);
+            zob = *reinterpret_cast<const ulonglong2*>(s_zob + 2 * a);
             old_word = env.diff_bits[(size_t)b * env.NW + (a >> 5)];
-            if (use_tab) delta_n = __ldg(g.dn_tab + (size_t)gi * (2 * NP + 1) + NP + delta);
+            if (use_tab) delta_n = __ldg(g.dn_tab + (size_t)gi * tab_stride(NP) + NP + delta);
             else qn = g.gscal[(size_t)gi * 4 + 1];
         }
         const uint64_t k0 = key.x ^ zob.x, k1 = key.y ^ zob.y;
@@ -605,7 +623,7 @@ env_step_tma_kernel(const eco_graphs_t g, const eco_env_t env, const int32_t* __
                     nimp += gain > 0;
                     f0[kk] = (float)si;
                     f1[kk] = use_tab ? __ldg(gtab + gain) : feat_gain(gain, mlr);
-                    f2[kk] = __ldg(env.tsf_tab + (step_new - l.h[k]));
+                    f2[kk] = tsf[step_new - l.h[k]];
                 }
                 *reinterpret_cast<float4*>(x0 + 4 * half) = make_float4(f0[0], f0[1], f0[2], f0[3]);
                 *reinterpret_cast<float4*>(x0 + NP + 4 * half) = make_float4(f1[0], f1[1], f1[2], f1[3]);
@@ -679,7 +697,9 @@ env_step_tma_kernel(const eco_graphs_t g, const eco_env_t env, const int32_t* __
 
         __syncwarp();                 // every lane is done with this stage before it is refilled two iterations on
         st = (st + 1) % TMA_STAGES;
-        a_cur = a_n1; gi_cur = gi_n1; a_n1 = a_n2; gi_n1 = gi_n2; a_n2 = a_n3; gi_n2 = gi_n3;
+#pragma unroll
+        for (int k = 0; k < D; ++k) { an[k] = an[k + 1]; gn[k] = gn[k + 1]; }
+        an[D] = a_new; gn[D] = gi_new;
     }
 }
 
@@ -816,7 +836,7 @@ int launch_env_step(const eco_graphs_t* g, eco_env_t* env, int policy, const int
                 static int n_sm = 0;
                 if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
                 long long blocks = (B_ + TMA_WARPS - 1) / TMA_WARPS;
-                if (blocks > (long long)n_sm * 6) blocks = (long long)n_sm * 6;
+                if (blocks > (long long)n_sm * 4) blocks = (long long)n_sm * 4;
                 env_step_tma_kernel<<<(unsigned)blocks, TMA_WARPS * 32, 0, st>>>(*g, *env, actions, reward, done, ha, hr, hs);
             } else ECO_SW(32);
         }

@@ -105,9 +105,9 @@ __global__ void __launch_bounds__(256) graph_prepare_kernel(eco_graphs_t g, int 
     // observable row 1 as a table: immediate_quality_changes / max_local_reward in fp64, then the driver's fp32 cast
     // (spinsystem.py:490, experiments/utils.py:174), for every cut change k = -NP..NP a +-1 graph can produce
     const double mlr_d = (double)s_sum[0];
-    float* tab = g.gain_tab + (size_t)gi * (2 * NP + 1);
+    float* tab = g.gain_tab + (size_t)gi * tab_stride(NP);
     const double qn_d = fmax(1.0, (double)s_pos[0] / 2.0);
-    double* dtab = g.dn_tab + (size_t)gi * (2 * NP + 1);
+    double* dtab = g.dn_tab + (size_t)gi * tab_stride(NP);
     for (int k = threadIdx.x; k <= 2 * NP; k += blockDim.x) {
         tab[k] = (float)__ddiv_rn((double)(k - NP), mlr_d);
         dtab[k] = __ddiv_rn((double)(k - NP), qn_d);                  // delta_score / quality normaliser (spinsystem.py:394)

@@ -66,9 +66,9 @@ typedef struct {
     int32_t* gstat;      /* [G, 4]       max degree, nnz, max |row abs sum|, flags (bit0: weights outside {-1,0,1},
                                          bit1: all weighted degrees zero, bit2: not symmetric / non-zero diagonal)  */
     float*   dmax;       /* [1]          max degree over the whole set (default norm.max(), mpnn.py:102)     */
-    float*   gain_tab;   /* [G, 2*NP+1]  (float)((double)k / mlr) for k = -NP..NP: observable row 1 of a vertex whose
+    float*   gain_tab;   /* [G, 2*NP+4]  entry [NP + k] = (float)((double)k / mlr) for k = -NP..NP: observable row 1 of a vertex whose
                                          flip changes the cut by k (valid for couplings in {-1,0,1}; spinsystem.py:490) */
-    double*  dn_tab;     /* [G, 2*NP+1]  (double)k / qn: the normalised score change of such a flip (spinsystem.py:394) */
+    double*  dn_tab;     /* [G, 2*NP+4]  entry [NP + k] = (double)k / qn: the normalised score change of such a flip (spinsystem.py:394) */
     uint16_t* tc_ops;    /* [G, 2, NP*NP] bf16 images of J and |J| in the tensor-core kernel's shared-memory operand
                                          layout (8x8 core matrices), fetched per episode with one bulk copy each;
                                          NULL when N > 208 (no tcgen05 path)                                  */
