@@ -219,6 +219,50 @@ def test_env_random_actions_multi_graph_vs_oracle(eng, n, p, B, steps):
     assert np.array_equal(bs.cpu().numpy(), np.stack([e.best_spins for e in cpu]).astype(np.int8))
 
 
+@pytest.mark.parametrize("n", [129, 200, 241, 256])
+def test_env_step_bulk_copy_ring_matches_subwarp_kernel(eng, n):
+    """B >= 4096 with caller-supplied actions runs env_step_tma_kernel (persistent warps, bulk-copy ring); smaller batches
+    run the sub-warp kernel that the oracle tests pin.  Same episodes, same actions (out-of-range ones included): every
+    state array, observation, reward and done flag must be identical."""
+    rng = np.random.default_rng(1000 + n)
+    B, G, T, steps = 4096 + 37, 5, 24, 24       # T small: episodes finish inside the test, done episodes stay untouched
+    Js = _random_graphs(rng, G, n, 0.06)
+    gidx = rng.integers(0, G, size=B).astype(np.int32)
+    spins = (2 * rng.integers(0, 2, size=(B, n)) - 1).astype(np.int8)
+    gs = eng.GraphSet(Js)
+    big = eng.BatchedSpinSystem(gs, B, T, 1.0 / n)
+    big.reset(spins=spins, graph_idx=gidx)
+    parts = []
+    for lo in range(0, B, 2048):
+        hi = min(B, lo + 2048)
+        e = eng.BatchedSpinSystem(gs, hi - lo, T, 1.0 / n)
+        e.reset(spins=spins[lo:hi], graph_idx=gidx[lo:hi])
+        parts.append((lo, hi, e))
+    for t in range(steps):
+        a = rng.integers(0, n, size=B).astype(np.int32)
+        if t % 6 == 5:
+            a[::3] = prev[::3]                   # revisits: exercise the visited-set probe
+        if t == 7:
+            a[5] = -1; a[11] = n                 # invalid actions are ignored (episode left untouched, done reported)
+        prev = a
+        r, d = big.step(torch.from_numpy(a))
+        r, d = r.cpu().numpy(), d.cpu().numpy()
+        for lo, hi, e in parts:
+            rp, dp = e.step(torch.from_numpy(a[lo:hi]))
+            assert np.array_equal(r[lo:hi].view(np.uint64), rp.cpu().numpy().view(np.uint64)), ("reward", t)
+            assert np.array_equal(d[lo:hi], dp.cpu().numpy()), ("done", t)
+        if t % 5 == 0 or t == steps - 1:
+            ob = big.observation().cpu().numpy()
+            epb = big.episodes()
+            for lo, hi, e in parts:
+                assert np.array_equal(ob[lo:hi], e.observation().cpu().numpy()), ("obs", t)
+                assert epb[lo:hi].tobytes() == e.episodes().tobytes(), ("episode block", t)
+    bc, bs, st = big.results()
+    for lo, hi, e in parts:
+        bcp, bsp, stp = e.results()
+        assert torch.equal(bc[lo:hi], bcp) and torch.equal(bs[lo:hi], bsp) and torch.equal(st[lo:hi], stp)
+
+
 @pytest.mark.parametrize("n,p", [(24, 0.3), (200, 0.15), (500, 0.05)])
 def test_mpnn_simt_random_weights_multi_graph_vs_oracle(eng, n, p):
     from oracle.mpnn import mpnn_forward, KEYS
