@@ -37,6 +37,7 @@ namespace {
 using namespace tc;
 
 constexpr int NPMAX = 208;
+constexpr int PACK_NPMAX = 192;   // packed mode: K graphs of NP <= 96 vertices, K * NP <= 192 (leaves room behind the image)
 constexpr int CHUNK = 64;        // max vertices per linear-layer chunk (accumulator columns)
 constexpr int SUBS = 2;            // warps per (group, TMEM lane quadrant): they split the 16-column blocks of every epilogue
 constexpr int THREADS = 256 * SUBS;
@@ -214,10 +215,15 @@ __device__ __forceinline__ void issue_part(const Ctx& c, uint32_t acc_col, uint3
         mma_ts(c.tmem + acc_col, c.tmem + tw + 8 * (i >> 1), d + (uint64_t)(16 * i), idesc, accumulate || i > 0);
 }
 
+// PACKED: K = packK >= 2 small graphs (NP <= 96) are processed side by side as ONE block-diagonal graph of K * NP <= 192
+// vertices ("pack"): the tensor part below does not know about it; only the inputs (per-vertex episode), the operand
+// images (diagonal blocks), feature 63 and the readout (pooling / argmax per episode) are per episode.
+template <bool PACKED>
 __global__ void __launch_bounds__(LAUNCH_THREADS, 1)
 mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int32_t* __restrict__ graph_idx,
                const float* __restrict__ xn, const float* __restrict__ xg, const float norm_max,
-               float* __restrict__ q_out, int32_t* __restrict__ act_out, unsigned long long* __restrict__ dbg) {
+               float* __restrict__ q_out, int32_t* __restrict__ act_out, unsigned long long* __restrict__ dbg,
+               const int packK) {
     extern __shared__ __align__(128) unsigned char smem[];
     // optional timeline (tools/tc_timeline.py): CTA 0, lane 0 of every warp records (event id << 48 | clock)
     int dbg_n = 0;
@@ -236,8 +242,17 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     c.warp = __shfl_sync(0xffffffffu, c.tid >> 5, 0);     // warp-uniform: MMA issue code stays on the uniform datapath
     c.q = c.warp & 3; c.sub = (c.warp >> 2) % SUBS; c.grp = c.warp / (4 * SUBS);
     c.bar_all = &bars[0]; c.bar_grp = &bars[1 + c.grp];
-    c.N = g.N; c.NP = g.NP; c.NB = g.NP >> 3;
+    const int K = PACKED ? packK : 1;                     // episodes per pack
+    const int NPs = g.NP, Ns = g.N;                       // per-episode sizes; NP / N below are the pack's
+    c.NP = K * NPs; c.NB = c.NP >> 3; c.N = PACKED ? c.NP : g.N;
     const int N = c.N, NP = c.NP, NB = c.NB;
+    const int npacks = (B + K - 1) / K;
+    auto vertex_ok = [&](int n) { return PACKED ? (n % NPs) < Ns : n < N; };     // not a padding vertex
+    // PACKED extras live behind the (at most 192 x 192) adjacency image
+    float* rdmaxv = reinterpret_cast<float*>(smem + SM_A + PACK_NPMAX * PACK_NPMAX * 2);   // [192] 1 / deg_max of the vertex's graph
+    float* pp_blk = rdmaxv + PACK_NPMAX;                  // [12][64] pooled partial sums per 16-vertex block
+    float* pooled_e = pp_blk + (PACK_NPMAX / 16) * 64;    // [K][64]
+    float* tef = pooled_e + (PACK_NPMAX / 16) * 64;       // [K][64] w_r[f] ReLU(p_f) per episode
 
     float* xf = reinterpret_cast<float*>(smem + SM_XF);
     float* rdeg = reinterpret_cast<float*>(smem + SM_DEG);      // 1 / deg
@@ -282,13 +297,36 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     // The adjacency operands come ready-made (graph_prepare.cu: bf16 images of J and |J| in this kernel's core-matrix
     // layout): one bulk copy each, issued as soon as the previous episode's last reader of the destination retired, so
     // the transfer of episode e+1 runs under the layers / readout of episode e.
-    const uint32_t ops_bytes = (uint32_t)NP * NP * 2;
-    auto fetch_ops = [&](int which, int episode) {          // one thread
-        const uint16_t* src = g.tc_ops + ((size_t)graph_idx[episode] * 2 + which) * NP * NP;
-        mbar_expect_tx(&bar_ops[which], ops_bytes);
-        bulk_g2s(which ? smem + SM_ABS : smem + SM_A, src, ops_bytes, &bar_ops[which]);
+    // PACKED: graph j of the pack goes to diagonal block j of the image: its NP/8 column-block runs (NP/8 core matrices
+    // = NP * 16 bytes each, contiguous in both layouts) are copied one by one; the off-diagonal blocks stay zero.
+    auto fetch_ops = [&](int which, int pack) {             // one thread
+        unsigned char* dst = which ? smem + SM_ABS : smem + SM_A;
+        if (!PACKED) {
+            const uint32_t ops_bytes = (uint32_t)NP * NP * 2;
+            const uint16_t* src = g.tc_ops + ((size_t)graph_idx[pack] * 2 + which) * NP * NP;
+            mbar_expect_tx(&bar_ops[which], ops_bytes);
+            bulk_g2s(dst, src, ops_bytes, &bar_ops[which]);
+        } else {
+            const int kk = min(K, B - pack * K), NBs = NPs >> 3;
+            mbar_expect_tx(&bar_ops[which], (uint32_t)kk * NPs * NPs * 2);
+            for (int j = 0; j < kk; ++j) {
+                const uint16_t* src = g.tc_ops + ((size_t)graph_idx[pack * K + j] * 2 + which) * NPs * NPs;
+                for (int cb = 0; cb < NBs; ++cb)
+                    bulk_g2s(dst + ((size_t)(j * NBs + cb) * NB + j * NBs) * 128, src + (size_t)cb * NBs * 64, NBs * 128,
+                             &bar_ops[which]);
+            }
+        }
     };
-    if (c.tid == 0 && (int)blockIdx.x < B) { fetch_ops(0, blockIdx.x); fetch_ops(1, blockIdx.x); }
+    auto zero_image = [&](unsigned char* dst) {             // all worker threads; generic proxy, fenced for the bulk copies
+        for (int off = c.tid * 16; off < NP * NP * 2; off += THREADS * 16)
+            *reinterpret_cast<uint4*>(dst + off) = make_uint4(0, 0, 0, 0);
+        fence_proxy_async();
+    };
+    if (PACKED) {
+        if (c.warp < NWARPS) { zero_image(smem + SM_A); zero_image(smem + SM_ABS); }
+        __syncthreads();
+    }
+    if (c.tid == 0 && (int)blockIdx.x < npacks) { fetch_ops(0, blockIdx.x); fetch_ops(1, blockIdx.x); }
 
     // per-episode inputs, requested one episode ahead (during the previous readout): this thread's vertex observations
     // and degree, the four graph-level observations, the graph's maximum degree
@@ -296,21 +334,36 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     float xin0 = 0.f, xin1 = 0.f, xin2 = 0.f, degv = 1.f;
     float4 gl = make_float4(0.f, 0.f, 0.f, 0.f);
     int gmaxdeg = 1;
-    auto load_inputs = [&](int e) {
-        const int ge = graph_idx[e];
-        if (has_v) {
-            xin0 = xn[((size_t)e * 3 + 0) * NP + c.tid];
-            xin1 = xn[((size_t)e * 3 + 1) * NP + c.tid];
-            xin2 = xn[((size_t)e * 3 + 2) * NP + c.tid];
-            degv = g.deg[(size_t)ge * NP + c.tid];
+    auto load_inputs = [&](int e) {                         // e: episode, or pack of K episodes
+        if (!PACKED) {
+            const int ge = graph_idx[e];
+            if (has_v) {
+                xin0 = xn[((size_t)e * 3 + 0) * NP + c.tid];
+                xin1 = xn[((size_t)e * 3 + 1) * NP + c.tid];
+                xin2 = xn[((size_t)e * 3 + 2) * NP + c.tid];
+                degv = g.deg[(size_t)ge * NP + c.tid];
+            }
+            gl = *reinterpret_cast<const float4*>(xg + (size_t)e * 4);
+            gmaxdeg = g.gstat[(size_t)ge * 4];
+        } else {                                            // this thread's vertex belongs to episode e * K + tid / NPs
+            const int be = e * K + c.tid / NPs, v = c.tid % NPs;
+            xin0 = xin1 = xin2 = 0.f; degv = 1.f; gmaxdeg = 1;
+            gl = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_v && be < B) {
+                const int ge = graph_idx[be];
+                xin0 = xn[((size_t)be * 3 + 0) * NPs + v];
+                xin1 = xn[((size_t)be * 3 + 1) * NPs + v];
+                xin2 = xn[((size_t)be * 3 + 2) * NPs + v];
+                degv = g.deg[(size_t)ge * NPs + v];
+                gl = *reinterpret_cast<const float4*>(xg + (size_t)be * 4);
+                gmaxdeg = g.gstat[(size_t)ge * 4];
+            }
         }
-        gl = *reinterpret_cast<const float4*>(xg + (size_t)e * 4);
-        gmaxdeg = g.gstat[(size_t)ge * 4];
     };
     if (c.warp == NWARPS) {
         // ================= contraction issuer ===============================================================
         uint32_t sp0 = 0, sp1 = 0, op = 0;
-        for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        for (int b = blockIdx.x; b < npacks; b += gridDim.x) {
             mbar_wait(&sig[0], sp0); sp0 ^= 1u;
             mbar_wait(&bar_ops[0], op);               // A and |A| of this episode have landed (async proxy -> async proxy)
             mbar_wait(&bar_ops[1], op); op ^= 1u;
@@ -347,12 +400,66 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             }
         }
     }
-    if (c.warp < NWARPS && (int)blockIdx.x < B) load_inputs(blockIdx.x);
+    if (c.warp < NWARPS && (int)blockIdx.x < npacks) load_inputs(blockIdx.x);
 
     // ================= readout + argmax of one episode (mpnn.py:143-159; experiments/utils.py:57-66) =================
     // Reads only qpart / ppart, which the next episode does not touch before its last layer: it is run while the workers
     // would otherwise wait for the next episode's edge contraction.
     auto readout = [&](const int be) {
+        if (PACKED) {
+            // be = pack.  All K episodes at once, every sum in a fixed order.
+            const float bread = __ldg(w.b_read);
+            const int bpe = NPs >> 4;                     // 16-vertex blocks per episode
+            for (int idx = c.tid; idx < K * 64; idx += THREADS) {          // pooled[e][f] = mean_i h_i[f]
+                const int e = idx >> 6, f = idx & 63;
+                float t = 0.f;
+                for (int j = 0; j < bpe; ++j) t += pp_blk[(e * bpe + j) * 64 + f];
+                pooled_e[idx] = t / (float)Ns;
+            }
+            workers_sync();
+            for (int idx = c.tid; idx < K * 64; idx += THREADS) {          // tef[e][f] = w_r[f] ReLU(W_p[f,:] pooled[e])
+                const int e = idx >> 6, f = idx & 63;
+                const float4* wp = reinterpret_cast<const float4*>(w.w_pool + f * 64);
+                const float* pv = pooled_e + e * 64;
+                float p = 0.f;
+#pragma unroll 4
+                for (int k4 = 0; k4 < 16; ++k4) {
+                    const float4 wv = __ldg(wp + k4);
+                    p = fmaf(wv.x, pv[4 * k4], p); p = fmaf(wv.y, pv[4 * k4 + 1], p);
+                    p = fmaf(wv.z, pv[4 * k4 + 2], p); p = fmaf(wv.w, pv[4 * k4 + 3], p);
+                }
+                tef[idx] = __ldg(w.w_read + f) * fmaxf(p, 0.f);
+            }
+            workers_sync();
+            if (c.tid < NP) {                             // Q of this thread's vertex; the final value goes to qpart row 0
+                const int i = c.tid, e = i / NPs, v = i % NPs, ep = be * K + e;
+                float c0v = bread;
+                for (int f = 0; f < 64; ++f) c0v += tef[e * 64 + f];
+                const float qv = c0v + ((qpart[i] + qpart[NPMAX + i]) + (qpart[2 * NPMAX + i] + qpart[3 * NPMAX + i]));
+                const bool ok = v < Ns && ep < B;
+                if (ok && q_out) q_out[(size_t)ep * NPs + v] = qv;
+                qpart[i] = ok ? qv : -INFINITY;
+            }
+            workers_sync();
+            for (int e = c.warp; e < K; e += NWARPS) {    // argmax of episode e by one warp, lowest index on ties
+                const int ep = be * K + e;
+                float bv = -INFINITY;
+                int bi = 0x7fffffff;
+                for (int v = c.lane; v < Ns; v += 32) {
+                    const float qv = qpart[e * NPs + v];
+                    if (qv > bv) { bv = qv; bi = v; }     // (v ascending: the first maximum stays)
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                }
+                if (c.lane == 0 && ep < B && act_out) act_out[ep] = bi;
+            }
+            workers_sync();               // qpart / pp_blk / tef may be reused
+            return;
+        }
         float4 wpv[4] = {};
         float wrf = 0.f;
         if (c.tid < 256) {
@@ -417,7 +524,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     };
     int last_b = -1;
 
-    for (int b = blockIdx.x; b < B && c.warp < NWARPS; b += gridDim.x) {
+    for (int b = blockIdx.x; b < npacks && c.warp < NWARPS; b += gridDim.x) {
         const float rdmax = 1.f / (norm_max < 0.f ? (float)max(gmaxdeg, 1) : dmax_set);
 
         TL(1);
@@ -434,11 +541,18 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         for (int k = 0; k < 7; ++k) { wia[k] = __ldg(w.w_init + fa * 7 + k); wib[k] = __ldg(w.w_init + fb * 7 + k); }
         if (has_v) {
             const int i = c.tid;
-            const bool ok = i < N;
+            const bool ok = vertex_ok(i);
             xf[0 * NPMAX + i] = ok ? xin0 : 0.f;
             xf[1 * NPMAX + i] = ok ? xin1 : 0.f;
             xf[2 * NPMAX + i] = ok ? xin2 : 0.f;
             rdeg[i] = __fdividef(1.f, degv);
+            if (PACKED) {                      // the graph-level observations and deg_max differ from vertex to vertex
+                xf[3 * NPMAX + i] = ok ? gl.x : 0.f;
+                xf[4 * NPMAX + i] = ok ? gl.y : 0.f;
+                xf[5 * NPMAX + i] = ok ? gl.z : 0.f;
+                xf[6 * NPMAX + i] = ok ? gl.w : 0.f;
+                rdmaxv[i] = 1.f / (norm_max < 0.f ? (float)max(gmaxdeg, 1) : dmax_set);
+            }
         }
         // observations 3..6 are the same for every vertex: their share of W_x x and W_init x is one constant per feature
         // (padded vertices get it too; nothing reads their columns: no edges, masked out of the pooling and the argmax)
@@ -446,6 +560,8 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         cxa = fmaf(wxa[5], gl.y, cxa); cxb = fmaf(wxb[5], gl.y, cxb); cia = fmaf(wia[4], gl.y, cia); cib = fmaf(wib[4], gl.y, cib);
         cxa = fmaf(wxa[6], gl.z, cxa); cxb = fmaf(wxb[6], gl.z, cxb); cia = fmaf(wia[5], gl.z, cia); cib = fmaf(wib[5], gl.z, cib);
         cxa = fmaf(wxa[7], gl.w, cxa); cxb = fmaf(wxb[7], gl.w, cxb); cia = fmaf(wia[6], gl.w, cia); cib = fmaf(wib[6], gl.w, cib);
+        if (PACKED) { cxa = 0.f; cxb = 0.f; cia = 0.f; cib = 0.f; }      // (all 7 observations come from xf)
+        constexpr int NOBS = PACKED ? 7 : 3;
         uint4 wef[32 / (8 * SUBS)];
         ldg_weights<32>(c, pk + PK_WEF, wef);
         TL(2);
@@ -460,7 +576,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                     const int n0 = 16 * blk + 8 * half + 2 * (c.lane & 3);
                     float pa0 = cxa, pa1 = cxa, pb0 = cxb, pb1 = cxb;
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) {
+                    for (int k = 0; k < NOBS; ++k) {
                         const float2 x = *reinterpret_cast<const float2*>(xf + k * NPMAX + n0);
                         pa0 = fmaf(wxa[1 + k], x.x, pa0); pa1 = fmaf(wxa[1 + k], x.y, pa1);
                         pb0 = fmaf(wxb[1 + k], x.x, pb0); pb1 = fmaf(wxb[1 + k], x.y, pb1);
@@ -507,7 +623,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                     const int n0 = 16 * blk + 8 * half + 2 * (c.lane & 3);
                     float a0 = cia, a1 = cia, b0 = cib, b1 = cib;
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) {
+                    for (int k = 0; k < NOBS; ++k) {
                         const float2 x = *reinterpret_cast<const float2*>(xf + k * NPMAX + n0);
                         a0 = fmaf(wia[k], x.x, a0); a1 = fmaf(wia[k], x.y, a1);
                         b0 = fmaf(wib[k], x.x, b0); b1 = fmaf(wib[k], x.y, b1);
@@ -530,7 +646,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                 for (int i = 0; i < 8; ++i) {
                     const int n = c0 + bc + 8 * (i >> 2) + 2 * (c.lane & 3) + (i & 1);
                     const int f = 16 * c.q + (c.lane >> 2) + 8 * ((i >> 1) & 1);
-                    v[i] = f == 63 ? __fdividef(rdmax, rdeg[n]) : (0.5f * v[i]) * rdeg[n];
+                    v[i] = f == 63 ? __fdividef(PACKED ? rdmaxv[n] : rdmax, rdeg[n]) : (0.5f * v[i]) * rdeg[n];
                 }
                 store_block(c, sT, bc, v);
             });
@@ -587,7 +703,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             }
             TL(23);
             // A has no reader left once the LAST half retired (the halves retire in order)
-            if (l == 2 && c.tid == (chunk_split < nchunks ? THREADS / 2 : 0) && b + (int)gridDim.x < B) fetch_ops(0, b + gridDim.x);
+            if (l == 2 && c.tid == (chunk_split < nchunks ? THREADS / 2 : 0) && b + (int)gridDim.x < npacks) fetch_ops(0, b + gridDim.x);
             while (ci < ce) {
                 int c0, width;
                 chunk_span(ci, nblocks, nchunks, c0, width);
@@ -655,8 +771,17 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                             const int ia = 4 * (j >> 1) + (j & 1), ib = ia + 2;
                             const int n = c0 + bc + 8 * (j >> 1) + 2 * (c.lane & 3) + (j & 1);
                             const float ha = fmaxf(v[ia], 0.f), hb = fmaxf(v[ib], 0.f);
-                            if (n < N) { pool_a += ha; pool_b += hb; }
+                            if (vertex_ok(n)) { pool_a += ha; pool_b += hb; }
                             qv[j] = fmaf(wa, ha, wb * hb);
+                        }
+                        if (PACKED) {             // a 16-vertex block lies inside one graph: its pooled partial on its own
+                            pool_a += __shfl_xor_sync(0xffffffffu, pool_a, 1); pool_a += __shfl_xor_sync(0xffffffffu, pool_a, 2);
+                            pool_b += __shfl_xor_sync(0xffffffffu, pool_b, 1); pool_b += __shfl_xor_sync(0xffffffffu, pool_b, 2);
+                            if ((c.lane & 3) == 0) {
+                                pp_blk[((c0 + bc) >> 4) * 64 + fa] = pool_a;
+                                pp_blk[((c0 + bc) >> 4) * 64 + fa + 8] = pool_b;
+                            }
+                            pool_a = 0.f; pool_b = 0.f;
                         }
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
@@ -672,7 +797,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                     });
                     pool_a += __shfl_xor_sync(0xffffffffu, pool_a, 1); pool_a += __shfl_xor_sync(0xffffffffu, pool_a, 2);
                     pool_b += __shfl_xor_sync(0xffffffffu, pool_b, 1); pool_b += __shfl_xor_sync(0xffffffffu, pool_b, 2);
-                    if ((c.lane & 3) == 0) {
+                    if (!PACKED && (c.lane & 3) == 0) {
                         ppart[(ci * SUBS + c.sub) * 64 + fa] = pool_a;
                         ppart[(ci * SUBS + c.sub) * 64 + fa + 8] = pool_b;
                     }
@@ -685,9 +810,13 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
 
         // ================= end of the episode's tensor work ==================================================
         // (its readout runs later, under the next episode's edge contraction)
-        if (b + (int)gridDim.x < B) load_inputs(b + gridDim.x);     // next episode's inputs: in flight from here
+        if (b + (int)gridDim.x < npacks) load_inputs(b + gridDim.x);     // next episode's inputs: in flight from here
         workers_sync();
-        if (c.tid == 0 && b + (int)gridDim.x < B) fetch_ops(1, b + gridDim.x);   // H / E (which |A| overlays) have no reader left
+        if (PACKED && b + (int)gridDim.x < npacks) {      // the off-diagonal blocks of |A| were overwritten by H / E: clear
+            zero_image(smem + SM_ABS);
+            workers_sync();
+        }
+        if (c.tid == 0 && b + (int)gridDim.x < npacks) fetch_ops(1, b + gridDim.x);   // H / E (which |A| overlays) have no reader left
         last_b = b;
         TL(41);
     }
@@ -716,18 +845,23 @@ int launch_mpnn_tc(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int3
     static bool attr_set = false;
     static int n_sm = 148;
     if (!attr_set) {
-        ECO_CUDA(cudaFuncSetAttribute(mpnn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+        ECO_CUDA(cudaFuncSetAttribute(mpnn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+        ECO_CUDA(cudaFuncSetAttribute(mpnn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
         int dev = 0;
         ECO_CUDA(cudaGetDevice(&dev));
         ECO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         attr_set = true;
     }
-    const int grid = B < n_sm ? B : n_sm;
+    const int packK = PACK_NPMAX / g->NP;                  // small graphs: several per CTA iteration
+    const bool packed = packK >= 2 && B >= 2;
+    const int units = packed ? (B + packK - 1) / packK : B;
+    const int grid = units < n_sm ? units : n_sm;
     prof_begin(ECO_PROF_MPNN, st);
     static const bool timeline = getenv("ECO_TC_TIMELINE") != nullptr;
     if (timeline) ECO_CUDA(cudaMemsetAsync(scratch, 0, (NWARPS + 1) * 1024 * 8, st));
-    mpnn_tc_kernel<<<grid, LAUNCH_THREADS, SM_TOTAL, st>>>(*g, *w, B, gidx, xn, xg, norm_max, q, actions,
-                                                    timeline ? (unsigned long long*)scratch : nullptr);
+    unsigned long long* dbg = timeline ? (unsigned long long*)scratch : nullptr;
+    if (packed) mpnn_tc_kernel<true><<<grid, LAUNCH_THREADS, SM_TOTAL, st>>>(*g, *w, B, gidx, xn, xg, norm_max, q, actions, dbg, packK);
+    else mpnn_tc_kernel<false><<<grid, LAUNCH_THREADS, SM_TOTAL, st>>>(*g, *w, B, gidx, xn, xg, norm_max, q, actions, dbg, 1);
     prof_end(ECO_PROF_MPNN, st);
     ECO_LAUNCH_CHECK();
     return ECO_OK;
