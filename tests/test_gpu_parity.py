@@ -290,6 +290,45 @@ def test_mpnn_simt_random_weights_multi_graph_vs_oracle(eng, n, p):
     assert np.array_equal(a.cpu().numpy(), q.argmax(1))
 
 
+@pytest.mark.parametrize("n,B", [(5, 40), (17, 29), (20, 13), (33, 10), (48, 9), (64, 7), (90, 5), (96, 2)])
+@pytest.mark.parametrize("norm_max", [None, -1.0])
+def test_mpnn_tc_packed_small_graphs_vs_oracle(eng, n, B, norm_max):
+    """Small graphs are processed K = 192 / NP at a time as one block-diagonal graph (packed mode): several DIFFERENT
+    graphs per pack, ragged N, a partial last pack, per-episode graph-level observations; norm_max < 0 = the per-graph
+    degree normalisation the single-env facade uses."""
+    from oracle.mpnn import mpnn_forward, KEYS
+    from eco_dqn_b200 import _lib
+    rng = np.random.default_rng(7 * n + B)
+    G = min(B, 5)
+    Js = _random_graphs(rng, G, n, 0.8, pm1=False) if n < 10 else _random_graphs(rng, G, n, 0.3 if n < 40 else 0.1)
+    gidx = rng.integers(0, G, size=B).astype(np.int32)
+    shapes = eng.STATE_DICT_SHAPES
+    wd = {k: (rng.standard_normal(s) * (0.3 if len(s) > 1 else 0.1)).astype(np.float32) for k, s in zip(KEYS, shapes)}
+    gs = eng.GraphSet(Js)
+    env = eng.BatchedSpinSystem(gs, B, 2 * n, 1.0 / n)
+    env.reset(spins=(2 * rng.integers(0, 2, size=(B, n)) - 1).astype(np.int8), graph_idx=gidx)
+    for t in range(1 + n // 4):                  # different step counts of progress per episode are not possible; vary spins
+        env.step(torch.from_numpy(rng.integers(0, n, size=B).astype(np.int32)))
+    w = eng.MPNNWeights(wd)
+    if norm_max is None:                         # the reference's norm.max() over the batch it is given (mpnn.py:102)
+        norm_max = float(max((Js[g] != 0).sum(1).max() for g in gidx))
+        per_graph = False
+    else:
+        per_graph = True
+    q, a = env.q_values(w, impl=_lib.MPNN_TCGEN05, norm_max=norm_max)
+    q2, a2 = env.q_values(w, impl=_lib.MPNN_TCGEN05, norm_max=norm_max)
+    assert torch.equal(q, q2) and torch.equal(a, a2)          # run-to-run deterministic
+    q, a = q.cpu().numpy(), a.cpu().numpy()
+    obs7 = env.observation().cpu().numpy()
+    full = np.concatenate([obs7, Js[gidx].astype(np.float32)], axis=1)
+    if not per_graph:
+        ref = mpnn_forward(wd, full).numpy()
+    else:
+        ref = np.stack([mpnn_forward(wd, full[b:b + 1]).numpy().reshape(-1) for b in range(B)])   # per-episode norm.max()
+    assert np.allclose(q, ref, rtol=Q_RTOL, atol=Q_ATOL_FRAC * np.abs(ref).max())
+    assert np.array_equal(a, q.argmax(1))
+
+
 def test_full_size_invariants_ba200(eng):
     """BASELINE config 2 size (B=4096, N=200): size-independent properties after a greedy + random walk."""
     gsets = np.load(os.path.join(GOLDEN, "graphsets.npz"))
