@@ -73,7 +73,8 @@ def readout(w, h):
 
 @torch.no_grad()
 def mpnn_forward(weights, obs):
-    """obs: float32 [B, 7+N, N] (rows 0..6 features, rows 7.. adjacency) -> Q float32 [B, N].
+    """obs: float32 [B, n_obs+N, N] (rows 0..n_obs-1 features, then the adjacency) -> Q float32 [B, N]; n_obs is taken from
+    the weights (7, or 1 for the S2V-DQN networks).
 
     Unlike the reference this does not transpose the caller's tensor in place (mpnn.py:44, quirk A.4-2)
     and always returns [B, N] (the reference squeezes B == 1 away, mpnn.py:75)."""
@@ -82,8 +83,9 @@ def mpnn_forward(weights, obs):
     if obs.dim() == 2:
         obs = obs.unsqueeze(0)
     obs = obs.transpose(-1, -2)
-    x = obs[:, :, :7]
-    adj = obs[:, :, 7:]
+    n_obs = w[KEYS[0]].shape[1]                            # 7 (ECO-DQN) or 1 (S2V-DQN: the spin only)
+    x = obs[:, :, :n_obs]
+    adj = obs[:, :, n_obs:]
     norm = degree_norm(adj)
     h = F.relu(F.linear(x, w[KEYS[0]]))                    # mpnn.py:55
     e = edge_embedding(w, x, adj, norm)

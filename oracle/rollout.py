@@ -60,6 +60,35 @@ def rollout(J, weights, init_spins, max_steps, basin_reward=None, forced_actions
                 obs=obs_rec, env_steps=B * T, seconds=seconds)
 
 
+def rollout_s2v(J, weights, max_steps, forced_actions=None, q_hook=None):
+    """One S2V-DQN episode (experiments/pretrained_agent/test_s2v.py with SpinBasis.SIGNED): spins start at -1, are
+    flipped at most once, observation = [spin row; adjacency], dense reward, argmax over the spins still at -1
+    (experiments/utils.py:67-74: the others are filled with -1000), done when none is left or after max_steps."""
+    w = as_torch_weights(weights)
+    env = MaxCutEnv(J, max_steps, None, reversible=False, dense_reward=True)
+    env.reset()
+    actions, rewards, scores, dones = [], [], [env.score], []
+    done = False
+    t = 0
+    while not done:
+        ob = torch.FloatTensor(np.vstack((env.state[0:1], env.J)))[None]
+        if forced_actions is None or q_hook is not None:
+            qs = mpnn_forward(w, ob)
+            if q_hook is not None:
+                q_hook(t, qs)
+        if forced_actions is None:
+            mask = torch.from_numpy(env.state[0] != -1)[None]
+            a = int(qs.masked_fill(mask, -1000).argmax(1, True).squeeze(1).numpy()[0])
+        else:
+            a = int(forced_actions[t])
+        _, r, done, _ = env.step(a)
+        actions.append(a); rewards.append(r); scores.append(env.score); dones.append(done)
+        t += 1
+    return dict(actions=np.array(actions, dtype=np.int32), rewards=np.array(rewards, dtype=np.float64),
+                scores=np.array(scores, dtype=np.float64), dones=np.array(dones, dtype=np.uint8),
+                best_cut=float(env.best_solution), best_spins=env.best_spins.astype(np.int8))
+
+
 def greedy_baseline(J, init_spins, max_steps, basin_reward=None):
     """reference experiments/utils.py:218-227 + src/agents/solver.py:105-131."""
     cuts, spins, steps = [], [], []

@@ -53,12 +53,16 @@ class VisitedSets:
 
 
 class MaxCutEnv:
-    def __init__(self, J, max_steps, basin_reward=None):
+    def __init__(self, J, max_steps, basin_reward=None, reversible=True, dense_reward=False):
+        """reversible=False, dense_reward=True, basin_reward=None is the S2V-DQN configuration of
+        experiments/pretrained_agent/test_s2v.py (observables=[SPIN_STATE], RewardSignal.DENSE, irreversible spins)."""
         self.J = np.asarray(J, dtype=np.float64)
         self.n = self.J.shape[0]
         self.max_steps = int(max_steps)
         self.horizon = self.max_steps                       # spinsystem.py:163
         self.basin_reward = basin_reward
+        self.reversible = reversible
+        self.dense_reward = dense_reward
         self.state = None
 
     # ------------------------------------------------------------------ scorer pieces
@@ -87,7 +91,10 @@ class MaxCutEnv:
 
         state = np.zeros((N_OBS, n))                        # spinsystem.py:289
         if spins is None:
-            state[0, :] = 2 * np.random.randint(2, size=n) - 1    # spinsystem.py:294
+            if self.reversible:
+                state[0, :] = 2 * np.random.randint(2, size=n) - 1    # spinsystem.py:294
+            else:
+                state[0, :] = -1                                       # spinsystem.py:296-297
         else:
             spins = np.asarray(spins)
             if not np.isin(spins, [-1, 1]).all():           # spinsystem.py:604-606
@@ -131,8 +138,10 @@ class MaxCutEnv:
         s = new_state[0]
         gains = flip_gains(s, J)                            # spinsystem.py:414-416
 
-        if self.score > self.best_obs_score:                # spinsystem.py:418-424 (BLS, norm_rewards)
+        if self.score > self.best_obs_score and not self.dense_reward:   # spinsystem.py:418-424 (BLS, norm_rewards)
             rew = self.nscore - self.best_obs_nscore
+        if self.dense_reward:                               # spinsystem.py:435-436 (norm_rewards)
+            rew = delta_n
         if self.basin_reward is not None:                   # spinsystem.py:443-457
             is_new = self.visited.visit(int(action))
             if np.all(gains <= 0) and is_new:
@@ -156,6 +165,8 @@ class MaxCutEnv:
         st[6, :] = max(0, ((self.step_count - self.max_steps) / self.horizon) + 1)
 
         done = self.step_count == self.max_steps            # spinsystem.py:541-544
+        if not self.reversible and np.count_nonzero(s < 0) == 0:         # spinsystem.py:552-556
+            done = True
         return self.observation(), rew, done, None
 
     # ------------------------------------------------------------------ views
@@ -173,7 +184,12 @@ class MaxCutEnv:
         done = False
         while not done:
             gains = flip_gains(self.state[0], self.J)
-            a = gains.argmax()
+            if self.reversible:
+                a = gains.argmax()
+            else:                                           # solver.py:116-121: only spins still at -1
+                masked = gains.copy()
+                np.putmask(masked, self.state[0] != -1, np.finfo(np.float64).min)
+                a = masked.argmax()
             if gains[a] < 0:
                 break
             _, _, done, _ = self.step(a)

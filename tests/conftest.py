@@ -20,4 +20,11 @@ def golden_dir():
 
 
 def golden_cases():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f not in ("graphsets.npz", "generators.npz", "dqn_er40.npz"))
+    """ECO-DQN rollout cases (one graph, several attempts)."""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith("s2v_")
+                  and f not in ("graphsets.npz", "generators.npz", "dqn_er40.npz"))
+
+
+def s2v_cases():
+    """S2V-DQN cases: irreversible spins, spin-only observation, dense reward, one attempt from all -1."""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f.startswith("s2v_"))

@@ -188,6 +188,89 @@ def run_case(name, graph, net, weights, seed, n_attempts, n_obs_eps, obs_steps, 
     print("wrote %s (%.1f kB): best cuts %s" % (path, os.path.getsize(path) / 1e3, best_cut[:6]))
 
 
+def run_case_s2v(name, graph, net_path):
+    """S2V-DQN configuration (reference experiments/pretrained_agent/test_s2v.py, with SpinBasis.SIGNED because the
+    BINARY basis is broken in the reference's own driver): irreversible spins starting at -1, one observable (the spin),
+    dense reward, masked argmax (experiments/utils.py:67-74), T = N steps, a single attempt."""
+    from copy import deepcopy
+    from src.envs.utils import Observable
+    n = graph.shape[0]
+    T = n
+    env_args = {'observables': [Observable.SPIN_STATE], 'reward_signal': RewardSignal.DENSE,
+                'extra_action': ExtraAction.NONE, 'optimisation_target': OptimisationTarget.CUT,
+                'spin_basis': SpinBasis.SIGNED, 'norm_rewards': True, 'memory_length': None, 'horizon_length': None,
+                'stag_punishment': None, 'basin_reward': None, 'reversible_spins': False}
+    net = MPNN(n_obs_in=1, n_layers=3, n_features=64, n_hid_readout=[], tied_weights=False)
+    sd = torch.load(net_path, map_location="cpu")
+    net.load_state_dict(sd)
+    net.eval()
+    for p in net.parameters():
+        p.requires_grad = False
+    weights = {k: v.numpy().astype(np.float32) for k, v in sd.items()}
+    with open(os.devnull, "w") as devnull:
+        old = sys.stdout
+        sys.stdout = devnull
+        try:
+            res, raw, hist = test_network(net, env_args, [graph], "cpu", 1, n_attempts=50, return_raw=True,
+                                          return_history=True)
+        finally:
+            sys.stdout = old
+    env = ising_env.make("SpinSystem", SingleGraphGenerator(graph), T, **env_args)
+    g_env = deepcopy(env)
+    g_env.reset(spins=np.array([-1] * n))
+    Greedy(g_env).solve()
+    obs = env.reset()
+    init_score = env.score
+    actions, rewards, scores, dones, qs_rec, spins_rec = [], [], [env.score], [], [], [obs[0].copy()]
+    done = False
+    while not done:
+        ob = torch.FloatTensor(np.array([obs]))
+        qs = net(ob)                                     # transposes `ob` in place (mpnn.py:44)
+        qs_rec.append(qs[0].numpy().copy() if qs.dim() == 2 else qs.numpy().copy())
+        q2 = qs if qs.dim() == 2 else qs[None]
+        mask = (ob[:, :, 0] != -1)                       # experiments/utils.py:71-73
+        a = int(q2.masked_fill(mask, -1000).argmax(1, True).squeeze(1).numpy()[0])
+        obs, r, done, _ = env.step(a)
+        actions.append(a); rewards.append(r); scores.append(env.score); dones.append(done)
+        spins_rec.append(obs[0].copy())
+    assert [int(a) for a in hist["actions"][0][0][1:]] == actions, "driver diverged from reference test_network"
+    assert np.array_equal(np.array([float(x) for x in hist["rewards"][0][0][1:]]), np.array(rewards))
+    assert res["cut"][0] == env.best_solution and res["greedy (+1 init) cut"][0] == g_env.best_solution
+    sc = env.scorer
+    out = dict(J=graph.astype(np.int8), n=np.int32(n), T=np.int32(T),
+               mlr=np.float64(sc._max_local_reward), qn=np.float64(sc._solution_quality_normalizer),
+               lb=np.float64(sc._lower_bound), init_score=np.float64(init_score),
+               actions=np.array(actions, dtype=np.int32), rewards=np.array(rewards, dtype=np.float64),
+               scores=np.array(scores, dtype=np.float64), dones=np.array(dones, dtype=np.uint8),
+               q=np.stack(qs_rec).astype(np.float32), spins=np.stack(spins_rec).astype(np.int8),
+               best_cut=np.float64(env.best_solution), best_spins=np.array(env.best_spins).astype(np.int8),
+               greedy_cut=np.float64(g_env.best_solution), greedy_spins=np.array(g_env.best_spins).astype(np.int8),
+               greedy_steps=np.int32(g_env.current_step))
+    for k, v in weights.items():
+        out["w::" + k] = v
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print("wrote %s: %d steps, best cut %s, greedy %s" % (path, len(actions), env.best_solution, g_env.best_solution))
+
+
+def main_s2v():
+    s2v = os.path.join(REF, "experiments/pretrained_agent/networks/s2v")
+    val = os.path.join(REF, "_graphs/validation")
+    with open(os.devnull, "w") as dn:
+        old = sys.stdout
+        sys.stdout = dn
+        try:
+            er20 = load_graph_set(os.path.join(val, "ER_20spin_p15_100graphs.pkl"))
+            ba40 = load_graph_set(os.path.join(val, "BA_40spin_m4_100graphs.pkl"))
+            er200 = load_graph_set(os.path.join(REF, "_graphs/testing/ER_200spin_p15_50graphs.pkl"))
+        finally:
+            sys.stdout = old
+    run_case_s2v("s2v_er20_g0", er20[0], os.path.join(s2v, "network_best_ER_20spin.pth"))
+    run_case_s2v("s2v_er20_g5", er20[5], os.path.join(s2v, "network_best_ER_20spin.pth"))
+    run_case_s2v("s2v_ba40_g1", ba40[1], os.path.join(s2v, "network_best_BA_40spin.pth"))
+    run_case_s2v("s2v_er200_g0", er200[0], os.path.join(s2v, "network_best_ER_200spin.pth"))
+
+
 def main():
     nets = os.path.join(REF, "experiments/pretrained_agent/networks/eco")
     val = os.path.join(REF, "_graphs/validation")
@@ -314,4 +397,7 @@ def dqn_case(graphs, net_path):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "s2v":      # only the S2V cases (added later in round 1)
+        main_s2v()
+        sys.exit(0)
     main()

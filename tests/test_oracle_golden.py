@@ -101,3 +101,36 @@ def test_known_answer_upper_bounds():
             gi = int(name.split("_g")[1])
             assert np.array_equal(gs["er20"][gi], z["J"])
             assert z["best_cut"].max() <= gs["er20_opt"][gi]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# S2V-DQN configuration (irreversible spins, spin-only observation, dense reward): SURVEY.md section 8(f)3
+# ---------------------------------------------------------------------------------------------------------------
+from conftest import s2v_cases            # noqa: E402
+from oracle.rollout import rollout_s2v   # noqa: E402
+
+
+@pytest.mark.parametrize("name", s2v_cases())
+def test_s2v_teacher_forced_bit_exact(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    qs = []
+    out = rollout_s2v(z["J"].astype(np.float64), weights_from_npz(z), int(z["T"]), forced_actions=z["actions"],
+                      q_hook=lambda t, q: qs.append(q.numpy()[0]))
+    assert np.array_equal(out["rewards"], z["rewards"])          # numerically (a zero-gain flip gives -0.0 in both)
+    assert np.array_equal(np.signbit(out["rewards"]), np.signbit(z["rewards"]))
+    assert np.array_equal(out["scores"], z["scores"]) and np.array_equal(out["dones"], z["dones"])
+    assert out["best_cut"] == float(z["best_cut"]) and np.array_equal(out["best_spins"], z["best_spins"])
+    q = np.stack(qs)
+    assert np.allclose(q, z["q"], rtol=1e-4, atol=1e-5 * np.abs(z["q"]).max())
+
+
+@pytest.mark.parametrize("name", s2v_cases())
+def test_s2v_free_running_and_greedy(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    out = rollout_s2v(z["J"].astype(np.float64), weights_from_npz(z), int(z["T"]))
+    assert np.array_equal(out["actions"], z["actions"]) and out["best_cut"] == float(z["best_cut"])
+    env = MaxCutEnv(z["J"].astype(np.float64), int(z["T"]), None, reversible=False, dense_reward=True)
+    env.reset(np.array([-1] * int(z["n"])))
+    steps = env.greedy_solve()
+    assert env.best_solution == float(z["greedy_cut"]) and steps == int(z["greedy_steps"])
+    assert np.array_equal(env.best_spins.astype(np.int8), z["greedy_spins"])
