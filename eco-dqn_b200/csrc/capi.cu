@@ -283,11 +283,16 @@ int eco_env_results(const eco_env_t* env, int32_t* best_cut, int8_t* best_spins,
 }
 
 // ------------------------------------------------------------------------------------------------ mpnn
-size_t eco_mpnn_scratch_bytes(int32_t B, int32_t N, int32_t impl) {
-    if (B < 1 || !shape_ok(N)) return 0;
+// kernel scratch, followed by a [B, NP] fp32 Q buffer (eco_rollout needs the Q-values themselves when the argmax is
+// masked: irreversible spins)
+static size_t mpnn_kernel_scratch_bytes(int32_t B, int32_t N, int32_t impl) {
     size_t a = mpnn_simt_scratch_bytes(B, N);
     size_t b = (impl == ECO_MPNN_SIMT) ? 0 : mpnn_tc_scratch_bytes(B, N);
-    return a > b ? a : b;
+    return align256(a > b ? a : b);
+}
+size_t eco_mpnn_scratch_bytes(int32_t B, int32_t N, int32_t impl) {
+    if (B < 1 || !shape_ok(N)) return 0;
+    return mpnn_kernel_scratch_bytes(B, N, impl) + align256((size_t)B * padded_n(N) * sizeof(float));
 }
 
 size_t eco_mpnn_packed_bytes(void) { return mpnn_tc_packed_bytes(); }
@@ -324,6 +329,11 @@ int eco_mpnn_forward(const eco_graphs_t* g, const eco_mpnn_t* w, int32_t B, cons
 }
 
 // ------------------------------------------------------------------------------------------------ rollout
+int eco_env_masked_argmax(const eco_env_t* env, const float* q, int32_t* actions, void* stream) {
+    ECO_CHECK_ARG(env && q && actions && env->spins, ECO_ERR_INVALID, "eco_env_masked_argmax: null argument");
+    return launch_masked_argmax(env, q, actions, (cudaStream_t)stream);
+}
+
 int eco_rollout(const eco_graphs_t* g, eco_env_t* env, const eco_mpnn_t* w, int32_t n_steps, int32_t policy,
                 float norm_max, int32_t* act, void* scratch, int32_t impl, int32_t* ha, double* hr, double* hs,
                 void* stream) {
@@ -343,10 +353,16 @@ int eco_rollout(const eco_graphs_t* g, eco_env_t* env, const eco_mpnn_t* w, int3
     ECO_CHECK_ARG(act && scratch, ECO_ERR_INVALID, "eco_rollout: network policy needs actions and mpnn scratch buffers");
     rc = check_weights(w, "eco_rollout");
     if (rc) return rc;
+    const bool masked = (env->reserved & ECO_ENV_IRREVERSIBLE) != 0;   // argmax over the spins still at -1 only
+    float* qbuf = masked ? (float*)((char*)scratch + mpnn_kernel_scratch_bytes(env->B, env->N, impl)) : nullptr;
     for (int t = 0; t < n_steps; ++t) {
-        rc = eco_mpnn_forward(g, w, env->B, env->graph_idx, env->xn, env->xg, norm_max, nullptr, act, scratch, impl,
-                              stream);
+        rc = eco_mpnn_forward(g, w, env->B, env->graph_idx, env->xn, env->xg, norm_max, qbuf, masked ? nullptr : act,
+                              scratch, impl, stream);
         if (rc) return rc;
+        if (masked) {
+            rc = launch_masked_argmax(env, qbuf, act, st);
+            if (rc) return rc;
+        }
         rc = launch_env_step(g, env, ECO_POLICY_ACTIONS, act, nullptr, nullptr, ha, hr, hs, st);
         if (rc) return rc;
     }

@@ -81,6 +81,7 @@ int launch_env_reset(const eco_graphs_t* g, eco_env_t* env, const int32_t* gidx,
 int launch_env_step(const eco_graphs_t* g, eco_env_t* env, int policy, const int32_t* actions, double* reward,
                     uint8_t* done, int32_t* ha, double* hr, double* hs, cudaStream_t st);
 int launch_env_observation(const eco_env_t* env, float* obs7, cudaStream_t st);
+int launch_masked_argmax(const eco_env_t* env, const float* q, int32_t* actions, cudaStream_t st);
 int launch_env_results(const eco_env_t* env, int32_t* best_cut, int8_t* best_spins, int32_t* steps, cudaStream_t st);
 int launch_mpnn_simt(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int32_t* gidx, const float* xn,
                      const float* xg, float norm_max, float* q, int32_t* actions, void* scratch, cudaStream_t st);

@@ -95,6 +95,8 @@ env_step_kernel(const eco_graphs_t g, const eco_env_t env, const int policy, con
     const bool in_range = b < env.B;
     if (!in_range) b = env.B - 1;  // keep every lane alive for the group shuffles
     const int N = env.N, NP = env.NP, NCH = NP / 8;
+    const bool irreversible = (env.reserved & ECO_ENV_IRREVERSIBLE) != 0;   // S2V-DQN: spins are flipped at most once
+    const bool dense_reward = (env.reserved & ECO_ENV_DENSE_REWARD) != 0;   // reward = normalised score change
 
     eco_episode_t* ep = env.ep + b;
     const int flags = ep->flags;
@@ -122,14 +124,14 @@ env_step_kernel(const eco_graphs_t g, const eco_env_t env, const int policy, con
             for (int k = 0; k < 8; ++k) {
                 const int i = c * 8 + k;
                 // key = (gain + 32768) : (65535 - i) as an unsigned pair, biased so that signed max orders it
-                if (i < N)
+                if (i < N && (!irreversible || s.b[k] < 0))      // solver.py:116-121: irreversible -> only spins still at -1
                     best = max(best, (int)((((uint32_t)(s.b[k] * h.h[k] + 32768) << 16) | (uint32_t)(0xFFFF - i)) ^ 0x80000000u));
             }
         }
         best = G::maxv(best, sm);
         const uint32_t ukey = (uint32_t)best ^ 0x80000000u;
         a = 0xFFFF - (int)(ukey & 0xFFFFu);
-        if (active && ((int)(ukey >> 16) - 32768) < 0) {  // solver.py:124: stop only if the best gain is < 0
+        if (active && (best == INT_MIN || ((int)(ukey >> 16) - 32768) < 0)) {  // solver.py:124: stop only if the best gain is < 0
             active = false;
             if (lane == 0) ep->flags = flags | FLAG_STOPPED;
         }
@@ -145,7 +147,7 @@ env_step_kernel(const eco_graphs_t g, const eco_env_t env, const int policy, con
     G::sync();  // everyone has read the pre-flip values before anyone writes
 
     // ---- O(N) local-field update + per-vertex observables ------------------------------------------
-    int nimp = 0;
+    int nimp = 0, nneg = 0;
     if (active) {
         const int8_t* Jrow = Jg + (size_t)a * NP;
         float* x0 = env.xn + (size_t)b * 3 * NP;
@@ -167,6 +169,7 @@ env_step_kernel(const eco_graphs_t g, const eco_env_t env, const int policy, con
                 h.h[k] = (int16_t)hi;
                 const int gain = si * hi;
                 nimp += gain > 0;
+                nneg += (i < N && si < 0);
                 f0[k] = (float)si;
                 f1[k] = feat_gain(gain, mlr);
                 f2[k] = env.tsf_tab[step_new - l.h[k]];
@@ -185,19 +188,23 @@ env_step_kernel(const eco_graphs_t g, const eco_env_t env, const int policy, con
         }
     }
     nimp = G::sum(nimp, sm);
+    if (irreversible) nneg = G::sum(nneg, sm);          // spins that can still be flipped (spinsystem.py:552-556)
 
     // ---- scalar bookkeeping, lane 0, in the reference's fp64 operation order (appendix A.2) ---------
     int new_best = 0;
     if (lane == 0 && active) {
         const double qn = g.gscal[(size_t)gi * 4 + 1];
         const int delta = s_a_old * h_a_old;                            // spinsystem.py:393
-        const double delta_n = __ddiv_rn((double)delta, qn);            // :394
+        // the reference multiplies in fp64: a zero field times a spin of -1 is -0.0 (visible in the dense reward)
+        const double delta_d = (delta == 0 && s_a_old < 0) ? -0.0 : (double)delta;
+        const double delta_n = __ddiv_rn(delta_d, qn);                  // :394
         const double score = __dadd_rn(ep->score, (double)delta);       // :399
         const double nscore = __dadd_rn(ep->nscore, delta_n);           // :400
         const double best_score = ep->best_score, best_nscore = ep->best_nscore;
         const int cut = ep->cut + delta;
         double rew = 0.0;
-        if (score > best_score) rew = __dsub_rn(nscore, best_nscore);   // :418-424 (BLS, normalised)
+        if (dense_reward) rew = delta_n;                                // :435-436 (DENSE, normalised)
+        else if (score > best_score) rew = __dsub_rn(nscore, best_nscore);   // :418-424 (BLS, normalised)
 
         uint64_t k0 = ep->key[0] ^ env.zobrist[2 * a], k1 = ep->key[1] ^ env.zobrist[2 * a + 1];
         int n_visited = ep->n_visited;
@@ -220,7 +227,7 @@ env_step_kernel(const eco_graphs_t g, const eco_env_t env, const int policy, con
         if (score > best_score) {                                       // :459-463
             nbs = score; nbn = nscore; best_cut = cut; dist = 0; new_best = 1;
         }
-        const int done = step_new == env.T;                             // :541-544
+        const int done = step_new == env.T || (irreversible && nneg == 0);   // :541-544, :552-556
         ep->step = step_new; ep->cut = cut; ep->best_cut = best_cut; ep->dist = dist;
         ep->n_improving = nimp; ep->flags = flags | (done ? FLAG_DONE : 0); ep->n_visited = n_visited;
         ep->score = score; ep->nscore = nscore; ep->best_score = nbs; ep->best_nscore = nbn;
@@ -824,7 +831,9 @@ __global__ void env_results_kernel(const eco_env_t env, int32_t* __restrict__ be
 int launch_env_step(const eco_graphs_t* g, eco_env_t* env, int policy, const int32_t* actions, double* reward,
                     uint8_t* done, int32_t* ha, double* hr, double* hs, cudaStream_t st) {
     prof_begin(ECO_PROF_ENV_STEP, st);
-    {
+    if (env->reserved != 0) {       // S2V-DQN modes (irreversible spins / dense reward): the general kernel
+        ECO_ENV_DISPATCH(env_step_kernel, *g, *env, policy, actions, reward, done, ha, hr, hs);
+    } else {
         const int NP_ = env->NP;
         const long long B_ = env->B;
 #define ECO_SW(TPE) env_step_sw_kernel<TPE><<<(unsigned)((B_ * TPE + 127) / 128), 128, 0, st>>>(*g, *env, policy, actions, reward, done, ha, hr, hs)
@@ -854,6 +863,34 @@ int launch_env_reset(const eco_graphs_t* g, eco_env_t* env, const int32_t* gidx,
     if (env->use_basin)
         ECO_CUDA(cudaMemsetAsync(env->visited, 0, (size_t)env->B * env->HCAP * 16, st));
     ECO_ENV_DISPATCH(env_reset_kernel, *g, *env, gidx, spins);
+    ECO_LAUNCH_CHECK();
+    return ECO_OK;
+}
+
+// argmax_i Q_i over the spins still at -1, lowest index on ties (experiments/utils.py:67-74, irreversible spins: the
+// reference fills the others with -1000 before its argmax); one warp per episode.  No spin left: action 0.
+__global__ void masked_argmax_kernel(const eco_env_t env, const float* __restrict__ q, int32_t* __restrict__ actions) {
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= env.B) return;
+    const int8_t* s = env.spins + (size_t)b * env.NP;
+    const float* qb = q + (size_t)b * env.NP;
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = lane; i < env.N; i += 32) {
+        const float v = s[i] < 0 ? qb[i] : -1000.f;
+        if (v > bv) { bv = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) actions[b] = bi == 0x7fffffff ? 0 : bi;
+}
+
+int launch_masked_argmax(const eco_env_t* env, const float* q, int32_t* actions, cudaStream_t st) {
+    masked_argmax_kernel<<<(env->B + 7) / 8, 256, 0, st>>>(*env, q, actions);
     ECO_LAUNCH_CHECK();
     return ECO_OK;
 }

@@ -159,12 +159,18 @@ class MPNNWeights:
     def __init__(self, state_dict, device=None, pack=True):
         self.device = _require_cuda(device)
         self.tensors = []
-        for k, shp in zip(STATE_DICT_KEYS, STATE_DICT_SHAPES):
+        self.n_obs_in = 7
+        for i, (k, shp) in enumerate(zip(STATE_DICT_KEYS, STATE_DICT_SHAPES)):
             if k not in state_dict:
-                raise KeyError("state_dict is missing %r (expected the reference MPNN layout, n_obs_in=7, 3 layers, 64 "
-                               "features, untied, no hidden readout)" % k)
+                raise KeyError("state_dict is missing %r (expected the reference MPNN layout, n_obs_in=7 or 1, 3 layers, "
+                               "64 features, untied, no hidden readout)" % k)
             t = torch.as_tensor(np.asarray(state_dict[k]) if not torch.is_tensor(state_dict[k]) else state_dict[k])
             t = t.detach().to(self.device, torch.float32).contiguous()
+            # S2V-DQN networks (n_obs_in = 1: the spin only; shipped under networks/s2v): W_init is [64, 1] and W_e is
+            # [63, 2].  The kernels always see 7 observables; zero columns for the other six give the same result.
+            if i < 2 and tuple(t.shape) == (shp[0], shp[1] - 6):
+                self.n_obs_in = 1
+                t = torch.cat([t, torch.zeros(shp[0], 6, dtype=torch.float32, device=self.device)], dim=1).contiguous()
             if tuple(t.shape) != shp:
                 raise ValueError("%s has shape %s, expected %s" % (k, tuple(t.shape), shp))
             self.tensors.append(t)
@@ -193,7 +199,11 @@ class BatchedSpinSystem:
     """B independent Max-Cut ECO-DQN episodes on the device (DEFAULT_OBSERVABLES, BLS reward, normalised,
     reversible spins, infinite memory, Stopping.NORMAL -- the configuration every reference script uses)."""
 
-    def __init__(self, graphset, n_envs, max_steps, basin_reward=None, mpnn_impl=_lib.MPNN_AUTO):
+    def __init__(self, graphset, n_envs, max_steps, basin_reward=None, mpnn_impl=_lib.MPNN_AUTO, reversible_spins=True,
+                 dense_reward=False):
+        """reversible_spins=False, dense_reward=True, basin_reward=None is the S2V-DQN configuration of the reference
+        (experiments/pretrained_agent/test_s2v.py): spins start at -1 and are flipped at most once, the reward is the
+        normalised score change, the network / greedy policies choose among the spins still at -1."""
         self.gs = graphset
         self.device = graphset.device
         self.B, self.N, self.T = int(n_envs), graphset.N, int(max_steps)
@@ -211,6 +221,8 @@ class BatchedSpinSystem:
             check(L.eco_env_bind(C.byref(self.c), _ptr(self._ws), self.B, self.N, self.T,
                                  float(basin_reward) if basin_reward is not None else -1.0))
             self.NP, self.NW = int(self.c.NP), int(self.c.NW)
+            self.reversible_spins, self.dense_reward = bool(reversible_spins), bool(dense_reward)
+            self.c.reserved = (0 if reversible_spins else _lib.ENV_IRREVERSIBLE) | (_lib.ENV_DENSE_REWARD if dense_reward else 0)
             zob = np.ascontiguousarray(zobrist_keys(self.NP))
             tsf = time_since_flip_table(self.T).astype(np.float32)
             imm = immanency_table(self.T).astype(np.float32)
@@ -240,7 +252,10 @@ class BatchedSpinSystem:
         global numpy RNG, like spinsystem.py:294).  graph_idx: [B] (None: episode b uses graph b % G)."""
         B, N = self.B, self.N
         if spins is None:
-            spins = np.stack([2 * np.random.randint(2, size=N) - 1 for _ in range(B)])
+            if self.reversible_spins:
+                spins = np.stack([2 * np.random.randint(2, size=N) - 1 for _ in range(B)])
+            else:
+                spins = -np.ones((B, N), dtype=np.int8)        # spinsystem.py:296-297: irreversible spins start at -1
         if torch.is_tensor(spins):
             sp = spins.to(self.device)
             if sp.shape != (B, N):
@@ -316,6 +331,10 @@ class BatchedSpinSystem:
                                          _ptr(self.xn), _ptr(self.xg), nm, _ptr(q), _ptr(acts),
                                          _ptr(self._scratch_for(self.B)), self.mpnn_impl if impl is None else impl,
                                          _stream()))
+        if acts is not None and not self.reversible_spins:
+            # irreversible spins: argmax over the spins still at -1 (experiments/utils.py:67-74)
+            with torch.cuda.device(self.device):
+                check(lib().eco_env_masked_argmax(C.byref(self.c), _ptr(q), _ptr(acts), _stream()))
         return q[:, :self.N], acts
 
     def rollout(self, weights=None, n_steps=None, policy="network", norm_max=None, record_history=False, impl=None):

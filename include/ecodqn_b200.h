@@ -44,6 +44,13 @@ extern "C" {
 #define ECO_POLICY_NETWORK     1   /* argmax_i Q_i, lowest index on ties (experiments/utils.py:57-66)      */
 #define ECO_POLICY_GREEDY      2   /* argmax_i s_i h_i, stop when the best gain < 0 (src/agents/solver.py:105-131) */
 
+/* eco_env_t.reserved mode bits: the S2V-DQN configuration of the reference (experiments/pretrained_agent/test_s2v.py) is
+ * ECO_ENV_IRREVERSIBLE | ECO_ENV_DENSE_REWARD with use_basin = 0 */
+#define ECO_ENV_IRREVERSIBLE   1   /* reversible_spins=False: done when no spin is left at -1 (spinsystem.py:552-556);
+                                      ECO_POLICY_GREEDY / ECO_POLICY_NETWORK choose among the spins still at -1
+                                      (solver.py:116-121, experiments/utils.py:67-74)                       */
+#define ECO_ENV_DENSE_REWARD   2   /* RewardSignal.DENSE: reward = normalised score change (spinsystem.py:435-436) */
+
 /* MPNN implementations */
 #define ECO_MPNN_AUTO          0
 #define ECO_MPNN_SIMT          1   /* fp32 CUDA-core kernel: any int8 weights, any N <= ECO_MAX_SPINS      */
@@ -107,7 +114,7 @@ typedef struct {          /* 96 bytes per episode                               
 
 typedef struct {
     int32_t  B, N, NP, NW;          /* NW = NP/32 rounded up: words of the best-diff bitmask                 */
-    int32_t  T, HCAP, use_basin, reserved;
+    int32_t  T, HCAP, use_basin, reserved;   /* reserved: ECO_ENV_* mode bits, set by the caller after eco_env_bind (0 = ECO-DQN) */
     double   basin_reward;          /* added when a NEW local optimum is reached (spinsystem.py:450-457)     */
     int8_t*        spins;           /* [B, NP]                                                               */
     int16_t*       hfield;          /* [B, NP]  local fields h = J s                                         */
@@ -147,6 +154,11 @@ int eco_env_step(const eco_graphs_t* g, eco_env_t* env, int32_t policy, const in
 /* observation rows 0..6 as the reference's get_observation() returns them, cast to fp32 exactly as the
  * reference's drivers cast them (spinsystem.py:561-574; experiments/utils.py:174).  obs7_dev [B, 7, N]. */
 int eco_env_observation(const eco_env_t* env, float* obs7_dev, void* stream);
+
+/* argmax_i Q_i over the spins still at -1, lowest index on ties: the action selection of the reference's drivers for
+ * irreversible spins (experiments/utils.py:67-74; the spins already flipped are filled with -1000).  q_dev [B, NP] fp32
+ * (as written by eco_mpnn_forward), actions_dev [B] int32. */
+int eco_env_masked_argmax(const eco_env_t* env, const float* q_dev, int32_t* actions_dev, void* stream);
 
 /* best spins = current spins with the best-diff bits flipped.  best_spins_dev [B, N] int8. */
 int eco_env_best_spins(const eco_env_t* env, int8_t* best_spins_dev, void* stream);

@@ -414,3 +414,57 @@ def test_mpnn_tc_is_run_to_run_deterministic(eng):
         qs, _ = env.q_values(w, impl=_lib.MPNN_SIMT)
         assert torch.allclose(q1, qs, rtol=Q_RTOL, atol=Q_ATOL_FRAC * float(qs.abs().max()))
         env.step(a1)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# S2V-DQN configuration: irreversible spins, spin-only observation, dense reward
+# ---------------------------------------------------------------------------------------------------------------
+from conftest import s2v_cases            # noqa: E402
+
+
+@pytest.mark.parametrize("name", s2v_cases())
+def test_s2v_teacher_forced_and_q_values(eng, name):
+    z = load(name)
+    n, T = int(z["n"]), int(z["T"])
+    gs = eng.GraphSet(z["J"][None])
+    w = eng.MPNNWeights(weights_dict(z))
+    assert w.n_obs_in == 1
+    env = eng.BatchedSpinSystem(gs, 1, T, None, reversible_spins=False, dense_reward=True)
+    env.reset()
+    assert np.array_equal(env.spins[0, :n].cpu().numpy(), -np.ones(n, dtype=np.int8))
+    assert env.episodes()["score"][0] == float(z["init_score"])
+    for t, a in enumerate(z["actions"]):
+        q, act = env.q_values(w, norm_max=-1.0)              # one episode: norm.max() is this graph's max degree
+        q = q.cpu().numpy()[0]
+        assert np.allclose(q, z["q"][t], rtol=Q_RTOL, atol=Q_ATOL_FRAC * np.abs(z["q"][t]).max()), ("q", t)
+        assert int(act[0]) == int(a), ("masked argmax", t)
+        r, d = env.step(torch.tensor([int(a)], dtype=torch.int32))
+        r = r.cpu().numpy()
+        assert r[0] == z["rewards"][t] and np.signbit(r[0]) == np.signbit(z["rewards"][t]), ("reward", t)
+        assert int(d[0]) == int(z["dones"][t]) and env.episodes()["score"][0] == z["scores"][t + 1]
+        assert np.array_equal(env.spins[0, :n].cpu().numpy(), z["spins"][t + 1])
+    bc, bs, st = env.results()
+    assert float(bc[0]) == float(z["best_cut"]) and np.array_equal(bs[0].cpu().numpy(), z["best_spins"])
+
+
+@pytest.mark.parametrize("name", s2v_cases())
+def test_s2v_device_rollout_and_greedy(eng, name):
+    z = load(name)
+    n, T = int(z["n"]), int(z["T"])
+    gs = eng.GraphSet(z["J"][None])
+    w = eng.MPNNWeights(weights_dict(z))
+    env = eng.BatchedSpinSystem(gs, 3, T, None, reversible_spins=False, dense_reward=True)   # 3 identical episodes
+    env.reset(graph_idx=np.zeros(3, dtype=np.int32))
+    ha, hr, hs = env.rollout(w, record_history=True)
+    ha, hr = ha.cpu().numpy(), hr.cpu().numpy()
+    k = len(z["actions"])
+    for b in range(3):
+        assert np.array_equal(ha[b, :k], z["actions"]) and np.array_equal(hr[b, :k], z["rewards"])
+    bc, bs, st = env.results()
+    assert float(bc[0]) == float(z["best_cut"]) and int(st[0]) == k
+    g = eng.BatchedSpinSystem(gs, 2, T, None, reversible_spins=False, dense_reward=True)
+    g.reset(graph_idx=np.zeros(2, dtype=np.int32))
+    g.rollout(policy="greedy")
+    bc, bs, st = g.results()
+    assert float(bc[1]) == float(z["greedy_cut"]) and np.array_equal(bs[1].cpu().numpy(), z["greedy_spins"])
+    assert int(st[1]) == int(z["greedy_steps"])
