@@ -44,7 +44,13 @@ class Greedy(SpinSolver):
 
     def step(self):
         rewards_available = self.env.scorer.get_score_mask(self.env.state[0, :self.env.n_spins], self.env.matrix)
-        action = rewards_available.argmax()
+        if self.env.reversible_spins:
+            action = rewards_available.argmax()
+        else:                                   # solver.py:116-121: only the spins that have not been flipped yet
+            masked = rewards_available.copy()
+            np.putmask(masked, self.env.get_observation()[0, :] != self.env.get_allowed_action_states(),
+                       np.finfo(np.float64).min)
+            action = masked.argmax()
         if rewards_available[action] < 0:
             return 0, True
         _, reward, done, _ = self.env.step(action)
@@ -95,9 +101,12 @@ class Network(SpinSolver):
         qs, act = env._env.q_values(self.network.engine_weights(self.device))
         qs = qs[0]
         if np.random.uniform(0, 1) >= self.epsilon:
-            action = int(act[0])
-        else:
+            action = int(act[0])                 # (irreversible spins: q_values already masked the flipped ones)
+        elif env.reversible_spins:
             action = np.random.randint(0, env.action_space.n)
+        else:                                    # solver.py:234-240: a random spin among those still at -1
+            x = (env.state[0, :env.n_spins] == env.get_allowed_action_states()).nonzero()[0]
+            action = int(x[np.random.randint(0, len(x))])
         _, reward, done, _ = env.step(action)
         self._record(action, reward, qs.tolist())
         return reward, done

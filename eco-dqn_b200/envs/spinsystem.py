@@ -86,15 +86,24 @@ class SpinSystemFactory(object):
 
 def check_supported(observables, reward_signal, extra_action, optimisation_target, spin_basis, norm_rewards,
                     memory_length, horizon_length, stag_punishment, reversible_spins, init_snap, stopping, max_steps):
-    """The accelerated configuration = what every reference script uses."""
+    """The accelerated configurations: ECO-DQN as every reference script uses it, and S2V-DQN as
+    experiments/pretrained_agent/test_s2v.py configures it (observables=[SPIN_STATE], RewardSignal.DENSE, irreversible
+    spins, no basin reward) -- with SpinBasis.SIGNED, because BINARY is broken in the reference's own drivers."""
     assert observables[0] == Observable.SPIN_STATE, "First observable must be Observation.SPIN_STATE."
     problems = []
-    if list(observables) != DEFAULT_OBSERVABLES:
-        problems.append("observables must be DEFAULT_OBSERVABLES")
+    s2v = not reversible_spins
+    if s2v:
+        if list(observables) != [Observable.SPIN_STATE]:
+            problems.append("irreversible spins (S2V-DQN): observables must be [Observable.SPIN_STATE]")
+        if reward_signal != RewardSignal.DENSE:
+            problems.append("irreversible spins (S2V-DQN): reward_signal must be RewardSignal.DENSE")
+    else:
+        if list(observables) != DEFAULT_OBSERVABLES:
+            problems.append("observables must be DEFAULT_OBSERVABLES")
+        if reward_signal != RewardSignal.BLS:
+            problems.append("reward_signal must be RewardSignal.BLS")
     if optimisation_target != OptimisationTarget.CUT:
         problems.append("optimisation_target must be OptimisationTarget.CUT (got %s)" % optimisation_target)
-    if reward_signal != RewardSignal.BLS:
-        problems.append("reward_signal must be RewardSignal.BLS")
     if not norm_rewards:
         problems.append("norm_rewards must be True")
     if extra_action != ExtraAction.NONE:
@@ -107,14 +116,12 @@ def check_supported(observables, reward_signal, extra_action, optimisation_targe
         problems.append("horizon_length must be None or max_steps")
     if stag_punishment is not None:
         problems.append("stag_punishment must be None")
-    if not reversible_spins:
-        problems.append("reversible_spins must be True (S2V-DQN mode is not on the accelerated path)")
     if init_snap is not None:
         problems.append("init_snap is not supported (it is broken in the reference as well)")
     if stopping != Stopping.NORMAL:
         problems.append("stopping must be Stopping.NORMAL")
     if problems:
-        raise NotImplementedError("configuration outside the accelerated Max-Cut ECO-DQN path: " + "; ".join(problems))
+        raise NotImplementedError("configuration outside the accelerated Max-Cut ECO-DQN / S2V-DQN paths: " + "; ".join(problems))
 
 
 class SpinSystemBase:
@@ -125,6 +132,8 @@ class SpinSystemBase:
                  reversible_spins=False, init_snap=None, seed=None, stopping=Stopping.NORMAL, device=None):
         check_supported(observables, reward_signal, extra_action, optimisation_target, spin_basis, norm_rewards,
                         memory_length, horizon_length, stag_punishment, reversible_spins, init_snap, stopping, max_steps)
+        if not reversible_spins and basin_reward is not None:
+            raise NotImplementedError("irreversible spins (S2V-DQN): basin_reward must be None")
         if seed is not None:
             np.random.seed(seed)
         self.observables = list(enumerate(observables))
@@ -167,11 +176,16 @@ class SpinSystemBase:
         if self._graphset is None or key != self._graph_key:
             self._graphset = engine.GraphSet(np.asarray(matrix)[None], device=self._device)
             self._graph_key = key
-            self._env = engine.BatchedSpinSystem(self._graphset, 1, self.max_steps, self.basin_reward)
+            self._env = self._new_env()
             sc = self._graphset.gscal.cpu().numpy()[0]
             self.scorer.set_constants(sc[0], sc[1], sc[2])
         self.matrix = matrix
         self.matrix_obs = matrix
+
+    def _new_env(self):
+        return engine.BatchedSpinSystem(self._graphset, 1, self.max_steps, self.basin_reward,
+                                        reversible_spins=self.reversible_spins,
+                                        dense_reward=self.reward_signal == RewardSignal.DENSE)
 
     def _episode(self):
         if self._ep is None:
@@ -183,7 +197,10 @@ class SpinSystemBase:
         self._bind_graph(self.gg.get())
         n = self.n_spins
         if spins is None:
-            spins = 2 * np.random.randint(2, size=n) - 1          # spinsystem.py:294
+            if self.reversible_spins:
+                spins = 2 * np.random.randint(2, size=n) - 1      # spinsystem.py:294
+            else:
+                spins = -np.ones(n, dtype=np.int64)               # spinsystem.py:296-297
         else:
             spins = np.asarray(spins)
             if not np.isin(spins, [-1, 1]).all():                 # spinsystem.py:604-606
@@ -210,15 +227,15 @@ class SpinSystemBase:
 
     def get_observation(self):
         rows = self._env.observation()[0].double().cpu().numpy()
-        return np.vstack((rows, self.matrix_obs))
+        return np.vstack((rows[:len(self.observables)], self.matrix_obs))     # S2V-DQN: the spin row only
 
     def get_allowed_action_states(self):
-        return (-1, 1)
+        return (-1, 1) if self.reversible_spins else -1                       # spinsystem.py:576-594 (SIGNED)
 
     # ------------------------------------------------------------------ attributes callers read
     @property
     def state(self):
-        return self._env.observation()[0].double().cpu().numpy()
+        return self._env.observation()[0].double().cpu().numpy()[:len(self.observables)]
 
     @property
     def current_step(self):
@@ -265,7 +282,7 @@ class SpinSystemBase:
         new.gg = self.gg                      # generators are shared like the graphs they hold
         new._graphset, new._graph_key = self._graphset, self._graph_key
         new.matrix, new.matrix_obs = self.matrix, self.matrix_obs
-        new._env = engine.BatchedSpinSystem(self._graphset, 1, self.max_steps, self.basin_reward)
+        new._env = new._new_env()
         new._env._ws.copy_(self._env._ws)
         new._env.current_step = self._env.current_step
         new._env._is_reset = self._env._is_reset

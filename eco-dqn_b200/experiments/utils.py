@@ -56,14 +56,22 @@ def test_network(network, env_args, graphs_test, device=None, step_factor=1, bat
     graphs_test = [np.asarray(g) for g in graphs_test]
     n_graphs = len(graphs_test)
     results, results_raw, history = [None] * n_graphs, [None] * n_graphs, [None] * n_graphs
+    # irreversible spins (S2V-DQN): every episode starts from all -1, so there is a single attempt per graph and no
+    # random-start greedy baseline (experiments/utils.py:87, 218, 253-260); nothing is drawn from the RNG
+    reversible = env_args.get('reversible_spins', True)
+    if not reversible:
+        n_attempts = 1
 
     # The reference walks the graphs in order and, per graph, draws (1 + n_attempts) x N random spins from numpy's
     # global RNG: N for the constructor's reset (spinsystem.py:168,294), then N per episode (experiments/utils.py:154).
     init = []
     for g in graphs_test:
         n = g.shape[0]
-        np.random.randint(2, size=n)
-        init.append(np.stack([2 * np.random.randint(2, size=n) - 1 for _ in range(n_attempts)]).astype(np.int8))
+        if reversible:
+            np.random.randint(2, size=n)
+            init.append(np.stack([2 * np.random.randint(2, size=n) - 1 for _ in range(n_attempts)]).astype(np.int8))
+        else:
+            init.append(-np.ones((1, n), dtype=np.int8))
 
     # group graphs of equal size: one graph set, one batch of len(group) x n_attempts episodes
     groups = {}
@@ -78,25 +86,28 @@ def test_network(network, env_args, graphs_test, device=None, step_factor=1, bat
         gidx = np.repeat(np.arange(G, dtype=np.int32), n_attempts)
         spins = np.concatenate([init[j] for j in idxs])
 
-        env = engine.BatchedSpinSystem(gs, B, n_steps, args["basin_reward"])
+        mode = dict(reversible_spins=reversible, dense_reward=args["reward_signal"] == RewardSignal.DENSE)
+        env = engine.BatchedSpinSystem(gs, B, n_steps, args["basin_reward"], **mode)
         env.reset(spins=spins, graph_idx=gidx)
         scores0 = env.episodes()["score"].copy() if return_history else None
         torch.cuda.synchronize(dev)
         t_start = time.time()
         hist = env.rollout(weights, record_history=return_history)
-        best_cut, best_spins, _ = env.results()
+        best_cut, best_spins, steps_taken = env.results()
         torch.cuda.synchronize(dev)
         t_total = time.time() - t_start
+        steps_taken = steps_taken.cpu().numpy()
         best_cut = best_cut.cpu().numpy().astype(np.float64)
         best_spins = best_spins.cpu().numpy().astype(np.float64)
 
         # Greedy baselines (experiments/utils.py:100-111, 218-227): from the same random starts, and from all -1
-        env.reset(spins=spins, graph_idx=gidx)
-        env.rollout(policy="greedy")
-        g_cut, g_spins, _ = env.results()
-        g_cut = g_cut.cpu().numpy().astype(np.float64)
-        g_spins = g_spins.cpu().numpy().astype(np.float64)
-        env1 = engine.BatchedSpinSystem(gs, G, n_steps, args["basin_reward"])
+        if reversible:
+            env.reset(spins=spins, graph_idx=gidx)
+            env.rollout(policy="greedy")
+            g_cut, g_spins, _ = env.results()
+            g_cut = g_cut.cpu().numpy().astype(np.float64)
+            g_spins = g_spins.cpu().numpy().astype(np.float64)
+        env1 = engine.BatchedSpinSystem(gs, G, n_steps, args["basin_reward"], **mode)
         env1.reset(spins=-np.ones((G, n), dtype=np.int8), graph_idx=np.arange(G, dtype=np.int32))
         env1.rollout(policy="greedy")
         s_cut, s_spins, _ = env1.results()
@@ -109,20 +120,26 @@ def test_network(network, env_args, graphs_test, device=None, step_factor=1, bat
             sl = slice(k * n_attempts, (k + 1) * n_attempts)
             cuts = best_cut[sl]
             i_best = int(np.argmax(cuts))
-            ig = int(np.argmax(g_cut[sl]))
+            if reversible:
+                ig = int(np.argmax(g_cut[sl]))
+                gr_cut, gr_spins, gr_mean = g_cut[sl][ig], g_spins[sl][ig], np.mean(g_cut[sl])
+                raw_g = [list(g_cut[sl]), list(g_spins[sl])]
+            else:                                   # experiments/utils.py:257-260: the single -1 start stands in
+                gr_cut, gr_spins, gr_mean = s_cut[k], s_spins[k], s_cut[k]
+                raw_g = [[], []]
             results[j] = [cuts[i_best], best_spins[sl][i_best], np.mean(cuts),
                           s_cut[k], s_spins[k],
-                          g_cut[sl][ig], g_spins[sl][ig], np.mean(g_cut[sl]),
+                          gr_cut, gr_spins, gr_mean,
                           t_total / B]
-            results_raw[j] = [[s.astype(np.float64) for s in init[j]], list(cuts), list(best_spins[sl]),
-                              list(g_cut[sl]), list(g_spins[sl])]
+            results_raw[j] = [[s.astype(np.float64) for s in init[j]], list(cuts), list(best_spins[sl])] + raw_g
             if return_history:
-                acts = [[None] + [int(a) for a in row] for row in ha[sl]]
-                rews = [[None] + [float(r) for r in row] for row in hr[sl]]
-                scs = [[float(s0)] + [float(s) for s in row] for s0, row in zip(scores0[sl], hs[sl])]
+                st = steps_taken[sl]                # an irreversible episode ends once every spin is flipped
+                acts = [[None] + [int(a) for a in row[:t]] for row, t in zip(ha[sl], st)]
+                rews = [[None] + [float(r) for r in row[:t]] for row, t in zip(hr[sl], st)]
+                scs = [[float(s0)] + [float(s) for s in row[:t]] for s0, row, t in zip(scores0[sl], hs[sl], st)]
                 history[j] = [acts, scs, rews]
             print('Graph {}, best(mean) cut: {}({}), greedy cut (rand init / +1 init) : {} / {}.  ({} attempts in {}s)'.format(
-                j, cuts[i_best], np.mean(cuts), g_cut[sl][ig], s_cut[k], n_attempts, np.round(t_total * n_attempts / B, 4)))
+                j, cuts[i_best], np.mean(cuts), gr_cut, s_cut[k], n_attempts, np.round(t_total * n_attempts / B, 4)))
 
     results = pd.DataFrame(data=results, columns=["cut", "sol", "mean cut",
                                                   "greedy (+1 init) cut", "greedy (+1 init) sol",

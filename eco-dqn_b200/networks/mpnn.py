@@ -110,10 +110,10 @@ class MPNN(nn.Module):
     def engine_weights(self, device=None):
         """Device-pointer view of the parameters for the CUDA kernels (re-packed only when a parameter changed)."""
         from .. import engine
-        if self.n_obs_in != 7 or self.n_layers != 3 or self.n_features != 64 or self.tied_weights or \
+        if self.n_obs_in not in (1, 7) or self.n_layers != 3 or self.n_features != 64 or self.tied_weights or \
                 len(self.readout_layer.layers_readout) != 1:
-            raise NotImplementedError("the CUDA kernels implement the reference configuration: n_obs_in=7, 3 untied "
-                                      "layers, 64 features, no hidden readout layer")
+            raise NotImplementedError("the CUDA kernels implement the reference configurations: n_obs_in=7 (ECO-DQN) or "
+                                      "1 (S2V-DQN), 3 untied layers, 64 features, no hidden readout layer")
         version = tuple(p._version for p in self.parameters()) + tuple(p.data_ptr() for p in self.parameters())
         if self._engine_cache is None or self._engine_cache[0] != version:
             self._engine_cache = (version, engine.MPNNWeights(self.state_dict(), device=device))

@@ -133,3 +133,75 @@ def test_make_rejects_configurations_outside_the_path():
             ising_env.make("SpinSystem", gg, 40, **dict(env_args_for(z), **{key: bad}))
     with pytest.raises(NotImplementedError):
         ising_env.make("Other")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# S2V-DQN configuration through the reference-facing surface (experiments/pretrained_agent/test_s2v.py, SIGNED basis)
+# ---------------------------------------------------------------------------------------------------------------
+def s2v_env_args():
+    from eco_dqn_b200.envs.utils import Observable, RewardSignal, ExtraAction, OptimisationTarget, SpinBasis
+    return {'observables': [Observable.SPIN_STATE], 'reward_signal': RewardSignal.DENSE, 'extra_action': ExtraAction.NONE,
+            'optimisation_target': OptimisationTarget.CUT, 'spin_basis': SpinBasis.SIGNED, 'norm_rewards': True,
+            'memory_length': None, 'horizon_length': None, 'stag_punishment': None, 'basin_reward': None,
+            'reversible_spins': False}
+
+
+def s2v_network_for(z):
+    from eco_dqn_b200.networks.mpnn import MPNN
+    from oracle.mpnn import weights_from_npz
+    net = MPNN(n_obs_in=1, n_layers=3, n_features=64, n_hid_readout=[], tied_weights=False)
+    net.load_state_dict({k: torch.tensor(v) for k, v in weights_from_npz(z).items()})
+    return net.cuda().eval()
+
+
+@pytest.mark.parametrize("name", ["s2v_er20_g0", "s2v_ba40_g1"])
+def test_s2v_test_network_matches_reference(name):
+    from eco_dqn_b200.experiments.utils import test_network
+    z = load(name)
+    res, raw, hist = test_network(s2v_network_for(z), s2v_env_args(), [z["J"].astype(np.float64)], "cuda", 1,
+                                  n_attempts=50, return_raw=True, return_history=True)
+    assert res["cut"][0] == float(z["best_cut"]) and res["mean cut"][0] == float(z["best_cut"])
+    assert res["greedy (+1 init) cut"][0] == float(z["greedy_cut"])
+    assert res["greedy (rand init) cut"][0] == float(z["greedy_cut"])          # experiments/utils.py:257-260
+    assert np.array_equal(res["sol"][0], z["best_spins"].astype(np.float64))
+    assert hist["actions"][0][0][1:] == [int(a) for a in z["actions"]]
+    assert np.array_equal(np.array(hist["rewards"][0][0][1:]), z["rewards"])
+    assert np.array_equal(np.array(hist["scores"][0][0]), z["scores"])
+    assert len(raw["cuts"][0]) == 1 and raw["greedy cuts"][0] == []
+
+
+def test_s2v_facade_and_solvers_follow_the_reference():
+    import eco_dqn_b200.envs.core as ising_env
+    from eco_dqn_b200.envs.utils import SingleGraphGenerator
+    from eco_dqn_b200.agents.solver import Greedy, Network
+    z = load("s2v_er20_g5")
+    n = int(z["n"])
+    env = ising_env.make("SpinSystem", SingleGraphGenerator(z["J"].astype(np.float64)), n, **s2v_env_args())
+    obs = env.reset()
+    assert obs.shape == (1 + n, n) and np.array_equal(obs[0], -np.ones(n)) and env.get_allowed_action_states() == -1
+    assert env.observation_space.shape[1] == 1
+    for t, a in enumerate(z["actions"]):
+        obs, r, d, _ = env.step(int(a))
+        assert r == z["rewards"][t] and d == bool(z["dones"][t]) and env.score == z["scores"][t + 1]
+        assert np.array_equal(obs[0], z["spins"][t + 1].astype(np.float64))
+    assert env.best_solution == float(z["best_cut"])
+    g = deepcopy(env)
+    g.reset(spins=np.array([-1] * n))
+    Greedy(g).solve()
+    assert g.best_solution == float(z["greedy_cut"]) and np.array_equal(g.best_spins, z["greedy_spins"].astype(np.float64))
+    g2 = deepcopy(env)                       # step-by-step greedy (the host decides): same descent
+    g2.reset()
+    agent = Greedy(g2)
+    done = False
+    while not done:
+        _, done = agent.step()
+    assert g2.best_solution == float(z["greedy_cut"])
+    e3 = deepcopy(env)
+    net_agent = Network(s2v_network_for(z), e3)
+    net_agent.reset()
+    done = False
+    acts = []
+    while not done:
+        _, done = net_agent.step()
+        acts.append(int(net_agent.history[-1][0]))
+    assert acts == [int(a) for a in z["actions"]] and e3.best_solution == float(z["best_cut"])
