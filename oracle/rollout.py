@@ -15,7 +15,7 @@ from .mpnn import as_torch_weights, mpnn_forward
 
 
 def rollout(J, weights, init_spins, max_steps, basin_reward=None, forced_actions=None, record_obs=False,
-            q_hook=None):
+            q_hook=None, min_cut=False):
     """Greedy-Q (or teacher-forced) rollout of len(init_spins) episodes on graph J.
 
     Returns dict(actions[B,T], rewards[B,T] f64, scores[B,T+1] f64, best_cut[B], best_spins[B,N],
@@ -23,7 +23,7 @@ def rollout(J, weights, init_spins, max_steps, basin_reward=None, forced_actions
     t_total (experiments/utils.py:164,214)."""
     w = as_torch_weights(weights) if weights is not None else None
     B, T = len(init_spins), int(max_steps)
-    envs = [MaxCutEnv(J, T, basin_reward) for _ in range(B)]
+    envs = [MaxCutEnv(J, T, basin_reward, min_cut=min_cut) for _ in range(B)]
     obs = [e.reset(s) for e, s in zip(envs, init_spins)]
     n = envs[0].n
     actions = np.zeros((B, T), dtype=np.int32)
@@ -89,11 +89,11 @@ def rollout_s2v(J, weights, max_steps, forced_actions=None, q_hook=None):
                 best_cut=float(env.best_solution), best_spins=env.best_spins.astype(np.int8))
 
 
-def greedy_baseline(J, init_spins, max_steps, basin_reward=None):
+def greedy_baseline(J, init_spins, max_steps, basin_reward=None, min_cut=False):
     """reference experiments/utils.py:218-227 + src/agents/solver.py:105-131."""
     cuts, spins, steps = [], [], []
     for s in init_spins:
-        e = MaxCutEnv(J, max_steps, basin_reward)
+        e = MaxCutEnv(J, max_steps, basin_reward, min_cut=min_cut)
         e.reset(s)
         steps.append(e.greedy_solve())
         cuts.append(e.best_solution)

@@ -53,7 +53,7 @@ class VisitedSets:
 
 
 class MaxCutEnv:
-    def __init__(self, J, max_steps, basin_reward=None, reversible=True, dense_reward=False):
+    def __init__(self, J, max_steps, basin_reward=None, reversible=True, dense_reward=False, min_cut=False):
         """reversible=False, dense_reward=True, basin_reward=None is the S2V-DQN configuration of
         experiments/pretrained_agent/test_s2v.py (observables=[SPIN_STATE], RewardSignal.DENSE, irreversible spins)."""
         self.J = np.asarray(J, dtype=np.float64)
@@ -63,10 +63,20 @@ class MaxCutEnv:
         self.basin_reward = basin_reward
         self.reversible = reversible
         self.dense_reward = dense_reward
+        # OptimisationTarget.MIN_CUT (score_solver.py:423-505): every mask is the negated cut change, the quality is
+        # normaliser - cut, the normaliser is |sum of the negative weights| over the whole matrix
+        self.min_cut = min_cut
         self.state = None
+
+    def _gains(self, spins):
+        """get_score_mask / get_solution_quality_mask (score_solver.py:389-413 resp. :472-490)."""
+        g = flip_gains(spins, self.J)
+        return -g if self.min_cut else g
 
     # ------------------------------------------------------------------ scorer pieces
     def _quality(self, spins):
+        if self.min_cut:                                    # score_solver.py:219-222: max(0, normaliser) - measure
+            return max(0, self.qn) - cut_value(spins, self.J)
         # score_solver.py:196-200: measure + |min(0, lower_bound)|
         return cut_value(spins, self.J) + abs(min(0, self.lb))
 
@@ -83,7 +93,7 @@ class MaxCutEnv:
         n, J = self.n, self.J
         self.step_count = 0
         empty = np.array([-1] * n, dtype=np.float64)
-        g0 = flip_gains(empty, J)                           # spinsystem.py:200-206
+        g0 = self._gains(empty)                             # spinsystem.py:200-206
         nz = g0[np.nonzero(g0)]
         if nz.size == 0:
             raise ValueError("graph has no non-zero weighted degree (the reference recurses forever here)")
@@ -100,12 +110,15 @@ class MaxCutEnv:
             if not np.isin(spins, [-1, 1]).all():           # spinsystem.py:604-606
                 raise Exception("SpinSystem is configured for signed spins ([-1,1]).")
             state[0, :] = spins
-        gains = flip_gains(state[0], J)
+        gains = self._gains(state[0])
         state[1, :] = gains / self.mlr                      # spinsystem.py:311-312
         state[5, :] = np.sum(gains > 0) / n                 # spinsystem.py:321-322
         self.state = state
 
-        self.qn = max(1, np.sum(np.multiply(J, (J > 0))) / 2)   # score_solver.py:353-357
+        if self.min_cut:
+            self.qn = max(1, abs(np.sum(np.multiply(J, (J < 0)))))   # score_solver.py:439-443
+        else:
+            self.qn = max(1, np.sum(np.multiply(J, (J > 0))) / 2)   # score_solver.py:353-357
         self.lb = min(0, np.sum(np.multiply(J, (J < 0))) / 2)   # score_solver.py:359-365
 
         s = state[0]
@@ -129,14 +142,14 @@ class MaxCutEnv:
         new_state = np.copy(self.state)
 
         old = self.state[0]
-        delta = flip_gains(old, J)[action]                  # spinsystem.py:393
-        delta_n = (flip_gains(old, J) / self.qn)[action]    # spinsystem.py:394
+        delta = self._gains(old)[action]                    # spinsystem.py:393
+        delta_n = (self._gains(old) / self.qn)[action]      # spinsystem.py:394
         new_state[0, action] = -old[action]
         self.score += delta                                 # spinsystem.py:399-400
         self.nscore += delta_n
         self.state = new_state
         s = new_state[0]
-        gains = flip_gains(s, J)                            # spinsystem.py:414-416
+        gains = self._gains(s)                              # spinsystem.py:414-416
 
         if self.score > self.best_obs_score and not self.dense_reward:   # spinsystem.py:418-424 (BLS, norm_rewards)
             rew = self.nscore - self.best_obs_nscore
@@ -183,7 +196,7 @@ class MaxCutEnv:
         (zero-gain moves are taken) or the step budget ends.  Returns number of steps taken."""
         done = False
         while not done:
-            gains = flip_gains(self.state[0], self.J)
+            gains = self._gains(self.state[0])
             if self.reversible:
                 a = gains.argmax()
             else:                                           # solver.py:116-121: only spins still at -1

@@ -21,8 +21,13 @@ def golden_dir():
 
 def golden_cases():
     """ECO-DQN rollout cases (one graph, several attempts)."""
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith("s2v_")
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith(("s2v_", "mincut_"))
                   and f not in ("graphsets.npz", "generators.npz", "dqn_er40.npz"))
+
+
+def mincut_cases():
+    """ECO-DQN configuration with OptimisationTarget.MIN_CUT (same file layout as golden_cases)."""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f.startswith("mincut_"))
 
 
 def s2v_cases():

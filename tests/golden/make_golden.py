@@ -50,11 +50,11 @@ from experiments.utils import test_network, load_graph_set  # noqa: E402
 torch.set_num_threads(8)
 
 
-def env_args_for(n, basin=True):
+def env_args_for(n, basin=True, target=OptimisationTarget.CUT):
     return {'observables': DEFAULT_OBSERVABLES,
             'reward_signal': RewardSignal.BLS,
             'extra_action': ExtraAction.NONE,
-            'optimisation_target': OptimisationTarget.CUT,
+            'optimisation_target': target,
             'spin_basis': SpinBasis.SIGNED,
             'norm_rewards': True,
             'memory_length': None,
@@ -75,12 +75,12 @@ def load_net(path):
     return net, {k: v.numpy().astype(np.float32) for k, v in sd.items()}
 
 
-def run_case(name, graph, net, weights, seed, n_attempts, n_obs_eps, obs_steps, basin=True):
+def run_case(name, graph, net, weights, seed, n_attempts, n_obs_eps, obs_steps, basin=True, target=OptimisationTarget.CUT):
     """Reference rollout on one graph: B=n_attempts episodes, greedy-Q, T=2N steps."""
     from copy import deepcopy
     n = graph.shape[0]
     T = 2 * n
-    env_args = env_args_for(n, basin)
+    env_args = env_args_for(n, basin, target)
 
     # --- 1. the reference's own test_network for this seed ------------------------------------
     np.random.seed(seed)
@@ -166,7 +166,7 @@ def run_case(name, graph, net, weights, seed, n_attempts, n_obs_eps, obs_steps, 
 
     sc = test_env.scorer
     out = dict(
-        J=graph.astype(np.int8), n=np.int32(n), T=np.int32(T), seed=np.int32(seed),
+        J=graph.astype(np.int8), n=np.int32(n), T=np.int32(T), seed=np.int32(seed), min_cut=np.int32(target == OptimisationTarget.MIN_CUT),
         basin_reward=np.float64(1. / n if basin else -1.0),
         mlr=np.float64(sc._max_local_reward), qn=np.float64(sc._solution_quality_normalizer),
         lb=np.float64(sc._lower_bound),
@@ -251,6 +251,29 @@ def run_case_s2v(name, graph, net_path):
     path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **out)
     print("wrote %s: %d steps, best cut %s, greedy %s" % (path, len(actions), env.best_solution, g_env.best_solution))
+
+
+def main_mincut():
+    """ECO-DQN configuration with OptimisationTarget.MIN_CUT (score_solver.py:423-505): same driver, same networks."""
+    nets = os.path.join(REF, "experiments/pretrained_agent/networks/eco")
+    val = os.path.join(REF, "_graphs/validation")
+    with open(os.devnull, "w") as dn:
+        old = sys.stdout
+        sys.stdout = dn
+        try:
+            er20 = load_graph_set(os.path.join(val, "ER_20spin_p15_100graphs.pkl"))
+            ba40 = load_graph_set(os.path.join(val, "BA_40spin_m4_100graphs.pkl"))
+            bau = load_graph_set(os.path.join(val, "BA_40spin_m4_uniform_100graphs.pkl"))
+        finally:
+            sys.stdout = old
+    net20, w20 = load_net(os.path.join(nets, "network_best_ER_20spin.pth"))
+    netb40, wb40 = load_net(os.path.join(nets, "network_best_BA_40spin.pth"))
+    run_case("mincut_er20_g0", er20[0], net20, w20, seed=300, n_attempts=6, n_obs_eps=3, obs_steps=range(0, 41),
+             target=OptimisationTarget.MIN_CUT)
+    run_case("mincut_ba40_g2", ba40[2], netb40, wb40, seed=301, n_attempts=4, n_obs_eps=2, obs_steps=range(0, 81, 4),
+             target=OptimisationTarget.MIN_CUT)
+    run_case("mincut_ba40u_g1", bau[1], netb40, wb40, seed=302, n_attempts=4, n_obs_eps=2, obs_steps=range(0, 81, 4),
+             target=OptimisationTarget.MIN_CUT)      # all weights +1: negative max_local_reward, quality normaliser 1
 
 
 def main_s2v():
@@ -399,5 +422,8 @@ def dqn_case(graphs, net_path):
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "s2v":      # only the S2V cases (added later in round 1)
         main_s2v()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "mincut":   # only the Min-Cut cases (added later in round 1)
+        main_mincut()
         sys.exit(0)
     main()

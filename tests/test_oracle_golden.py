@@ -134,3 +134,33 @@ def test_s2v_free_running_and_greedy(name):
     steps = env.greedy_solve()
     assert env.best_solution == float(z["greedy_cut"]) and steps == int(z["greedy_steps"])
     assert np.array_equal(env.best_spins.astype(np.int8), z["greedy_spins"])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# OptimisationTarget.MIN_CUT: ECO-DQN configuration, minimisation scorer
+# ---------------------------------------------------------------------------------------------------------------
+from conftest import mincut_cases            # noqa: E402
+
+
+@pytest.mark.parametrize("name", mincut_cases())
+def test_mincut_env_scalars_greedy_and_rollout(name):
+    z = load(name)
+    assert int(z["min_cut"]) == 1
+    J, T = z["J"].astype(np.float64), int(z["T"])
+    e = MaxCutEnv(J, T, basin(z), min_cut=True)
+    e.reset(z["init_spins"][0])
+    assert e.mlr == float(z["mlr"]) and e.qn == float(z["qn"]) and e.lb == float(z["lb"])
+    assert e.score == z["init_score"][0] and e.best_solution == z["init_cut"][0]
+    out = rollout(J, None, z["init_spins"], T, basin(z), forced_actions=z["actions"], record_obs=True, min_cut=True)
+    assert np.array_equal(out["rewards"].view(np.uint64), z["rewards"].view(np.uint64)), "fp64 rewards differ"
+    assert np.array_equal(out["scores"], z["scores"]) and np.array_equal(out["best_cut"], z["best_cut"])
+    assert np.array_equal(out["best_spins"], z["best_spins"])
+    k = z["obs"].shape[0]
+    assert np.array_equal(out["obs"][:k][:, z["obs_steps"]], z["obs"])
+    cuts, spins, steps = greedy_baseline(J, z["init_spins"], T, basin(z), min_cut=True)
+    assert np.array_equal(cuts, z["greedy_cuts"]) and np.array_equal(spins, z["greedy_spins"])
+    assert np.array_equal(steps, z["greedy_steps"])
+    c1, s1, _ = greedy_baseline(J, -np.ones((1, int(z["n"])), dtype=np.int8), T, basin(z), min_cut=True)
+    assert c1[0] == float(z["greedy_single_cut"]) and np.array_equal(s1[0], z["greedy_single_spins"])
+    free = rollout(J, weights_from_npz(z), z["init_spins"], T, basin(z), min_cut=True)
+    assert np.array_equal(free["actions"], z["actions"]) and np.array_equal(free["best_cut"], z["best_cut"])
