@@ -10,6 +10,7 @@ ECO_OK, ECO_ERR_INVALID, ECO_ERR_UNSUPPORTED, ECO_ERR_CUDA, ECO_ERR_STATE = 0, -
 POLICY_ACTIONS, POLICY_NETWORK, POLICY_GREEDY = 0, 1, 2
 MPNN_AUTO, MPNN_SIMT, MPNN_TCGEN05 = 0, 1, 2
 ENV_IRREVERSIBLE, ENV_DENSE_REWARD = 1, 2      # eco_env_t.reserved mode bits (include/ecodqn_b200.h)
+GRAPHS_MIN_CUT = 2                              # eco_graphs_t.reserved: OptimisationTarget.MIN_CUT
 MAX_SPINS = 2048
 
 vp = C.c_void_p

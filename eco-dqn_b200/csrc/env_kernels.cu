@@ -95,6 +95,7 @@ env_step_kernel(const eco_graphs_t g, const eco_env_t env, const int policy, con
     const bool in_range = b < env.B;
     if (!in_range) b = env.B - 1;  // keep every lane alive for the group shuffles
     const int N = env.N, NP = env.NP, NCH = NP / 8;
+    const int sgn = (g.reserved & ECO_GRAPHS_MIN_CUT) ? -1 : 1;             // Min-Cut: every mask is the negated cut change
     const bool irreversible = (env.reserved & ECO_ENV_IRREVERSIBLE) != 0;   // S2V-DQN: spins are flipped at most once
     const bool dense_reward = (env.reserved & ECO_ENV_DENSE_REWARD) != 0;   // reward = normalised score change
 
@@ -125,7 +126,7 @@ env_step_kernel(const eco_graphs_t g, const eco_env_t env, const int policy, con
                 const int i = c * 8 + k;
                 // key = (gain + 32768) : (65535 - i) as an unsigned pair, biased so that signed max orders it
                 if (i < N && (!irreversible || s.b[k] < 0))      // solver.py:116-121: irreversible -> only spins still at -1
-                    best = max(best, (int)((((uint32_t)(s.b[k] * h.h[k] + 32768) << 16) | (uint32_t)(0xFFFF - i)) ^ 0x80000000u));
+                    best = max(best, (int)((((uint32_t)(sgn * s.b[k] * h.h[k] + 32768) << 16) | (uint32_t)(0xFFFF - i)) ^ 0x80000000u));
             }
         }
         best = G::maxv(best, sm);
@@ -167,7 +168,7 @@ env_step_kernel(const eco_graphs_t g, const eco_env_t env, const int policy, con
                 if (i == a) { si = s_a_new; s.b[k] = (int8_t)si; l.h[k] = (uint16_t)step_new; }
                 const int hi = h.h[k] + 2 * j.b[k] * s_a_new;  // J_aa == 0, so h_a is unchanged
                 h.h[k] = (int16_t)hi;
-                const int gain = si * hi;
+                const int gain = sgn * si * hi;
                 nimp += gain > 0;
                 nneg += (i < N && si < 0);
                 f0[k] = (float)si;
@@ -194,14 +195,16 @@ env_step_kernel(const eco_graphs_t g, const eco_env_t env, const int policy, con
     int new_best = 0;
     if (lane == 0 && active) {
         const double qn = g.gscal[(size_t)gi * 4 + 1];
-        const int delta = s_a_old * h_a_old;                            // spinsystem.py:393
-        // the reference multiplies in fp64: a zero field times a spin of -1 is -0.0 (visible in the dense reward)
-        const double delta_d = (delta == 0 && s_a_old < 0) ? -0.0 : (double)delta;
+        const int dcut = s_a_old * h_a_old;                             // change of the cut value
+        const int delta = sgn * dcut;                                   // spinsystem.py:393 (score mask at the action)
+        // the reference multiplies in fp64: a zero field times a spin of -1 is -0.0 (visible in the dense reward);
+        // the Min-Cut scorer negates it once more
+        const double delta_d = (delta == 0 && (s_a_old < 0) == (sgn > 0)) ? -0.0 : (double)delta;
         const double delta_n = __ddiv_rn(delta_d, qn);                  // :394
         const double score = __dadd_rn(ep->score, (double)delta);       // :399
         const double nscore = __dadd_rn(ep->nscore, delta_n);           // :400
         const double best_score = ep->best_score, best_nscore = ep->best_nscore;
-        const int cut = ep->cut + delta;
+        const int cut = ep->cut + dcut;
         double rew = 0.0;
         if (dense_reward) rew = delta_n;                                // :435-436 (DENSE, normalised)
         else if (score > best_score) rew = __dsub_rn(nscore, best_nscore);   // :418-424 (BLS, normalised)
@@ -739,6 +742,7 @@ env_reset_kernel(const eco_graphs_t g, const eco_env_t env, const int32_t* __res
     G::sync();
     __threadfence_block();
 
+    const bool min_cut = (g.reserved & ECO_GRAPHS_MIN_CUT) != 0;
     int nimp = 0, ssh = 0;
     if (in_range) {
         float* x0 = env.xn + (size_t)b * 3 * NP;
@@ -749,9 +753,9 @@ env_reset_kernel(const eco_graphs_t g, const eco_env_t env, const int32_t* __res
             for (int w = 0; w < NP / 4; ++w) acc = __dp4a(jw[w], sw[w], acc);  // h_i = sum_j J_ij s_j
             hf[i] = (int16_t)acc;
             const int si = spins[i];
-            const int gain = si * acc;
+            ssh += si * acc;
+            const int gain = min_cut ? -(si * acc) : si * acc;         // score mask (score_solver.py:409-413 / :486-490)
             nimp += gain > 0;
-            ssh += gain;
             x0[i] = (float)si;                                         // spinsystem.py:294/299
             x0[NP + i] = i < N ? feat_gain(gain, mlr) : 0.f;           // :311-312
             x0[2 * NP + i] = 0.f;
@@ -763,7 +767,8 @@ env_reset_kernel(const eco_graphs_t g, const eco_env_t env, const int32_t* __res
         const double qn = g.gscal[(size_t)gi * 4 + 1], lb = g.gscal[(size_t)gi * 4 + 2];
         const int sumJ = (int)g.gscal[(size_t)gi * 4 + 3];
         const int cut = (sumJ - ssh) / 4;                              // utils.py:90-94, exact in integers
-        const double score = __dadd_rn((double)cut, fabs(fmin(0.0, lb)));   // score_solver.py:182-200
+        // quality: cut + |min(0, lb)| (score_solver.py:196-200) or, minimising, max(0, qn) - cut (:219-222)
+        const double score = min_cut ? __dsub_rn(fmax(0.0, qn), (double)cut) : __dadd_rn((double)cut, fabs(fmin(0.0, lb)));
         const double nscore = __ddiv_rn(score, qn);                    // :190-194
         eco_episode_t e;
         e.step = 0; e.cut = cut; e.best_cut = cut; e.dist = 0; e.n_improving = nimp; e.flags = 0;
@@ -831,7 +836,7 @@ __global__ void env_results_kernel(const eco_env_t env, int32_t* __restrict__ be
 int launch_env_step(const eco_graphs_t* g, eco_env_t* env, int policy, const int32_t* actions, double* reward,
                     uint8_t* done, int32_t* ha, double* hr, double* hs, cudaStream_t st) {
     prof_begin(ECO_PROF_ENV_STEP, st);
-    if (env->reserved != 0) {       // S2V-DQN modes (irreversible spins / dense reward): the general kernel
+    if (env->reserved != 0 || (g->reserved & ECO_GRAPHS_MIN_CUT)) {   // S2V-DQN modes, Min-Cut: the general kernel
         ECO_ENV_DISPATCH(env_step_kernel, *g, *env, policy, actions, reward, done, ha, hr, hs);
     } else {
         const int NP_ = env->NP;

@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(256) graph_prepare_kernel(eco_graphs_t g, int 
 
     __shared__ int s_sum[8], s_pos[8], s_neg[8], s_mlr[8], s_maxdeg[8], s_nnz[8], s_maxabs[8], s_flags[8];
     int t_sum = 0, t_pos = 0, t_neg = 0, t_mlr = INT_MIN, t_maxdeg = 0, t_nnz = 0, t_maxabs = 0, t_flags = 0;
+    const bool min_cut = (g.reserved & ECO_GRAPHS_MIN_CUT) != 0;     // score_solver.py:423-505
 
     for (int i = warp; i < NP; i += nwarp) {
         int rs = 0, ra = 0, rp = 0, rn = 0, cnt = 0, bad = 0;
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(256) graph_prepare_kernel(eco_graphs_t g, int 
         t_flags |= bad;
         t_maxdeg = max(t_maxdeg, cnt);
         t_maxabs = max(t_maxabs, ra);
-        if (i < N && rs != 0) t_mlr = max(t_mlr, rs);
+        if (i < N && rs != 0) t_mlr = max(t_mlr, min_cut ? -rs : rs);   // max non-zero score-mask entry of the all -1 state
     }
     if (lane == 0) {
         s_sum[warp] = t_sum; s_pos[warp] = t_pos; s_neg[warp] = t_neg; s_mlr[warp] = t_mlr;
@@ -93,20 +94,21 @@ __global__ void __launch_bounds__(256) graph_prepare_kernel(eco_graphs_t g, int 
         if (mlr == INT_MIN) { flags |= 2; mlr = 1; }
         double* gs = g.gscal + (size_t)gi * 4;
         gs[0] = (double)mlr;
-        gs[1] = fmax(1.0, (double)pos / 2.0);
+        gs[1] = min_cut ? fmax(1.0, fabs((double)neg)) : fmax(1.0, (double)pos / 2.0);   // :439-443 / :353-357
         gs[2] = fmin(0.0, (double)neg / 2.0);
         gs[3] = (double)sum;
         int32_t* st = g.gstat + (size_t)gi * 4;
         st[0] = maxdeg; st[1] = nnz; st[2] = maxabs; st[3] = flags;
         s_sum[0] = mlr;
         s_pos[0] = pos;
+        s_neg[0] = neg;
     }
     __syncthreads();
     // observable row 1 as a table: immediate_quality_changes / max_local_reward in fp64, then the driver's fp32 cast
     // (spinsystem.py:490, experiments/utils.py:174), for every cut change k = -NP..NP a +-1 graph can produce
     const double mlr_d = (double)s_sum[0];
     float* tab = g.gain_tab + (size_t)gi * tab_stride(NP);
-    const double qn_d = fmax(1.0, (double)s_pos[0] / 2.0);
+    const double qn_d = min_cut ? fmax(1.0, fabs((double)s_neg[0])) : fmax(1.0, (double)s_pos[0] / 2.0);
     double* dtab = g.dn_tab + (size_t)gi * tab_stride(NP);
     for (int k = threadIdx.x; k <= 2 * NP; k += blockDim.x) {
         tab[k] = (float)__ddiv_rn((double)(k - NP), mlr_d);

@@ -108,8 +108,11 @@ def graphs_to_int8(graphs):
 
 
 class GraphSet:
-    def __init__(self, graphs, device=None, validate=True):
+    def __init__(self, graphs, device=None, validate=True, min_cut=False):
+        """min_cut=True: the scorer constants (and every mask the env kernels derive from the graphs) are those of
+        OptimisationTarget.MIN_CUT (reference score_solver.py:423-505) instead of CUT."""
         self.device = _require_cuda(device)
+        self.min_cut = bool(min_cut)
         J = graphs_to_int8(graphs)
         self.G, self.N = int(J.shape[0]), int(J.shape[1])
         if self.N > _lib.MAX_SPINS:
@@ -120,6 +123,7 @@ class GraphSet:
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             self.c = Graphs()
             check(L.eco_graphs_bind(C.byref(self.c), _ptr(self._ws), self.G, self.N))
+            self.c.reserved = _lib.GRAPHS_MIN_CUT if self.min_cut else 0     # read by the prepare kernel
             Jd = torch.from_numpy(J).to(self.device, non_blocking=False)
             check(L.eco_graphs_load_dev(C.byref(self.c), _ptr(Jd), _stream()))
             self.NP = int(self.c.NP)
@@ -130,7 +134,8 @@ class GraphSet:
             stat = self.gstat.cpu().numpy()
         self.max_degree = int(stat[:, 0].max())
         self.pm1_only = not bool((stat[:, 3] & 1).any())
-        self.c.reserved = 1 if self.pm1_only else 0       # bit0: couplings in {-1,0,1} -> tcgen05 MPNN path allowed
+        # bit0: couplings in {-1,0,1} -> tcgen05 MPNN path allowed
+        self.c.reserved = (1 if self.pm1_only else 0) | (_lib.GRAPHS_MIN_CUT if self.min_cut else 0)
         if validate:
             if (stat[:, 3] & 4).any():
                 raise ValueError("graph %d is not symmetric with a zero diagonal" % int(np.nonzero(stat[:, 3] & 4)[0][0]))

@@ -59,6 +59,22 @@ class MaxCutScorer:
         return True
 
 
+class MinCutScorer(MaxCutScorer):
+    """Host-side view of MinimumCutUnbiasedSolver (reference src/envs/score_solver.py:423-505): every mask is the negated
+    cut change, the quality is normaliser - cut."""
+
+    def get_solution_quality(self, spins, matrix):
+        return max(0, self._solution_quality_normalizer) - self.get_solution(spins, matrix)     # :219-222
+
+    def get_score_mask(self, spins, matrix):
+        return -calculate_cut_changes(spins, matrix)
+
+    get_solution_quality_mask = get_score_mask
+
+    def get_normalized_score_mask(self, spins, matrix):
+        return self.get_score_mask(spins, matrix) / self._solution_quality_normalizer
+
+
 class _ActionSpace:
     def __init__(self, n_actions):
         self.n = n_actions
@@ -102,8 +118,8 @@ def check_supported(observables, reward_signal, extra_action, optimisation_targe
             problems.append("observables must be DEFAULT_OBSERVABLES")
         if reward_signal != RewardSignal.BLS:
             problems.append("reward_signal must be RewardSignal.BLS")
-    if optimisation_target != OptimisationTarget.CUT:
-        problems.append("optimisation_target must be OptimisationTarget.CUT (got %s)" % optimisation_target)
+    if optimisation_target not in (OptimisationTarget.CUT, OptimisationTarget.MIN_CUT):
+        problems.append("optimisation_target must be OptimisationTarget.CUT or MIN_CUT (got %s)" % optimisation_target)
     if not norm_rewards:
         problems.append("norm_rewards must be True")
     if extra_action != ExtraAction.NONE:
@@ -154,7 +170,7 @@ class SpinSystemBase:
         self.observation_space = _ObservationSpace(self.n_spins, len(self.observables))
         self.stopping_type = stopping
         self.optimisation_target = optimisation_target
-        self.scorer = MaxCutScorer()
+        self.scorer = MinCutScorer() if optimisation_target == OptimisationTarget.MIN_CUT else MaxCutScorer()
         self.spin_basis = spin_basis
         self.memory_length = memory_length
         self.horizon_length = horizon_length if horizon_length is not None else self.max_steps
@@ -174,7 +190,8 @@ class SpinSystemBase:
     def _bind_graph(self, matrix):
         key = (id(matrix), matrix.shape)
         if self._graphset is None or key != self._graph_key:
-            self._graphset = engine.GraphSet(np.asarray(matrix)[None], device=self._device)
+            self._graphset = engine.GraphSet(np.asarray(matrix)[None], device=self._device,
+                                             min_cut=self.optimisation_target == OptimisationTarget.MIN_CUT)
             self._graph_key = key
             self._env = self._new_env()
             sc = self._graphset.gscal.cpu().numpy()[0]

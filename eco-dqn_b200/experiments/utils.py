@@ -80,7 +80,8 @@ def test_network(network, env_args, graphs_test, device=None, step_factor=1, bat
     for n, idxs in groups.items():
         n_steps = int(n * step_factor)
         args = _check_env_args(env_args, n_steps)
-        gs = engine.GraphSet(np.stack([graphs_test[j] for j in idxs]), device=dev)
+        gs = engine.GraphSet(np.stack([graphs_test[j] for j in idxs]), device=dev,
+                             min_cut=args["optimisation_target"] == OptimisationTarget.MIN_CUT)
         G = len(idxs)
         B = G * n_attempts
         gidx = np.repeat(np.arange(G, dtype=np.int32), n_attempts)

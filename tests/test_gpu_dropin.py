@@ -205,3 +205,21 @@ def test_s2v_facade_and_solvers_follow_the_reference():
         _, done = net_agent.step()
         acts.append(int(net_agent.history[-1][0]))
     assert acts == [int(a) for a in z["actions"]] and e3.best_solution == float(z["best_cut"])
+
+
+@pytest.mark.parametrize("name", ["mincut_er20_g0", "mincut_ba40u_g1"])
+def test_mincut_test_network_matches_reference_frames(name):
+    """OptimisationTarget.MIN_CUT through test_network: same seed -> the reference's result frame."""
+    from eco_dqn_b200.experiments.utils import test_network
+    from eco_dqn_b200.envs.utils import OptimisationTarget
+    z = load(name)
+    args = dict(env_args_for(z), optimisation_target=OptimisationTarget.MIN_CUT)
+    np.random.seed(int(z["seed"]))
+    res, raw = test_network(network_for(z), args, [z["J"].astype(np.float64)], "cuda", 2,
+                            n_attempts=z["init_spins"].shape[0], return_raw=True)
+    assert np.array_equal(np.array(raw["init spins"][0]).astype(np.int8), z["init_spins"])
+    assert np.array_equal(np.array(raw["cuts"][0]), z["best_cut"])
+    assert res["cut"][0] == float(z["res_cut"]) and res["mean cut"][0] == float(z["res_mean_cut"])
+    assert res["greedy (+1 init) cut"][0] == float(z["greedy_single_cut"])
+    assert res["greedy (rand init) cut"][0] == float(z["res_greedy_rand_cut"])
+    assert res["greedy (rand init) mean cut"][0] == float(z["res_greedy_rand_mean_cut"])

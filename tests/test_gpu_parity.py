@@ -468,3 +468,47 @@ def test_s2v_device_rollout_and_greedy(eng, name):
     bc, bs, st = g.results()
     assert float(bc[1]) == float(z["greedy_cut"]) and np.array_equal(bs[1].cpu().numpy(), z["greedy_spins"])
     assert int(st[1]) == int(z["greedy_steps"])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# OptimisationTarget.MIN_CUT
+# ---------------------------------------------------------------------------------------------------------------
+from conftest import mincut_cases            # noqa: E402
+
+
+@pytest.mark.parametrize("name", mincut_cases())
+def test_mincut_env_and_rollout_bit_exact(eng, name):
+    z = load(name)
+    T, n = int(z["T"]), int(z["n"])
+    gs = eng.GraphSet(z["J"][None], min_cut=True)
+    assert float(gs.mlr[0]) == float(z["mlr"]) and float(gs.qn[0]) == float(z["qn"]) and float(gs.lb[0]) == float(z["lb"])
+    B = z["init_spins"].shape[0]
+    env = eng.BatchedSpinSystem(gs, B, T, basin(z))
+    env.reset(spins=z["init_spins"], graph_idx=np.zeros(B, dtype=np.int32))
+    ep = env.episodes()
+    assert np.array_equal(ep["score"], z["init_score"]) and np.array_equal(ep["cut"].astype(np.float64), z["init_cut"])
+    k = z["obs"].shape[0]
+    obs_steps = list(z["obs_steps"])
+    w = eng.MPNNWeights(weights_dict(z))
+    for t in range(T):
+        if t in obs_steps:
+            got = env.observation().cpu().numpy()[:k]
+            assert np.array_equal(got, z["obs"][:, obs_steps.index(t)]), ("obs", t)
+            q, _ = env.q_values(w)
+            ref = z["q"][:, obs_steps.index(t)]
+            assert np.allclose(q.cpu().numpy()[:k], ref, rtol=Q_RTOL, atol=Q_ATOL_FRAC * np.abs(ref).max())
+        r, d = env.step(torch.from_numpy(z["actions"][:, t].copy()))
+        assert np.array_equal(r.cpu().numpy().view(np.uint64), z["rewards"][:, t].view(np.uint64)), ("reward", t)
+        assert np.array_equal(env.episodes()["score"], z["scores"][:, t + 1])
+    bc, bs, _ = env.results()
+    assert np.array_equal(bc.cpu().numpy().astype(np.float64), z["best_cut"])
+    assert np.array_equal(bs.cpu().numpy(), z["best_spins"])
+    # free-running network rollout and the greedy baselines
+    env.reset(spins=z["init_spins"], graph_idx=np.zeros(B, dtype=np.int32))
+    ha, hr, hs = env.rollout(w, record_history=True)
+    assert np.array_equal(ha.cpu().numpy(), z["actions"])
+    env.reset(spins=z["init_spins"], graph_idx=np.zeros(B, dtype=np.int32))
+    env.rollout(policy="greedy")
+    gc, gsp, gst = env.results()
+    assert np.array_equal(gc.cpu().numpy().astype(np.float64), z["greedy_cuts"])
+    assert np.array_equal(gsp.cpu().numpy(), z["greedy_spins"]) and np.array_equal(gst.cpu().numpy(), z["greedy_steps"])
