@@ -228,8 +228,9 @@ int  eco_session_rollout(eco_session_t* s, const int8_t* J_host /*[G,N,N]*/, con
                          int32_t* best_cut_host /*[B]*/, int8_t* best_spins_host /*[B,N] or NULL*/, void* stream);
 /* counters for bench.py: kernels launched by this library since the last reset */
 int64_t eco_launch_count(int reset);
-/* Per-kernel device timing for bench.py's roofline: while enabled, every MPNN forward kernel (kind 0) and every
- * env-step kernel (kind 1) is bracketed by CUDA events on its launch stream.  eco_profile_read synchronises the
+/* Per-kernel device timing for bench.py's roofline: while enabled with on = k >= 1, every k-th MPNN forward kernel
+ * (kind 0) and every k-th env-step kernel (kind 1) is bracketed by CUDA events on its launch stream (an event record
+ * between two kernels costs about as much as a small kernel, so bench.py samples).  eco_profile_read synchronises the
  * device and returns the summed duration (ms) and the number of launches recorded since enabling. */
 #define ECO_PROF_MPNN 0
 #define ECO_PROF_ENV_STEP 1
