@@ -80,7 +80,7 @@ __device__ __forceinline__ float feat_gain(int gain, double mlr) {
 }
 // (An exact fp32 alternative exists -- __fdiv_rn((float)gain, (float)mlr) equals the fp64-then-fp32 result because double
 // rounding is innocuous for a division when 53 >= 2*24+2 -- but it costs more issue slots than the table lookup: measured
-// 448 us vs 330 us per launch in env_step_tma_kernel.)
+// 448 us vs 330 us per launch in env_step_ring_kernel.)
 
 // ------------------------------------------------------------------------------------------------ step
 template <int TPE, bool BLOCK>
@@ -465,33 +465,14 @@ env_step_sw_kernel(const eco_graphs_t g, const eco_env_t env, const int policy, 
 }
 
 // ------------------------------------------------------------------------------------------------ step, 128 < N <= 256
-// Bulk-copy (TMA) staged variant: persistent warps, one episode per warp at a time, a 3-deep shared-memory ring per
-// warp.  While episode e is processed from shared memory, the 1-D bulk copies (cp.async.bulk, completion on an
-// mbarrier) of episode e+2 -- spins, local fields, last-flip steps, the scalar block and row `a` of its adjacency -- and
-// the visited-set slot of episode e+1 are already in flight, so no global-load latency sits on the per-episode path.
+// Staged variant: persistent warps, two episode streams per warp (one per half-warp), a 3-deep shared-memory ring per
+// stream filled with 16-byte asynchronous copies (cp.async, one commit group per episode).  While episode e is processed
+// from shared memory, the copies of episode e+2 -- spins, local fields, last-flip steps, the scalar block and row `a` of
+// its adjacency -- are already in flight, so no global-load latency sits on the per-episode path.
 // Same arithmetic as env_step_kernel (bit-exact); caller-supplied actions only (the greedy policy needs the fields to
 // pick the row).
 namespace tma {
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok = 0;
-    const long long t0 = clock64();
-    while (!ok) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
-        if (!ok && clock64() - t0 > 4000000000ll) __trap();
-    }
-}
 }  // namespace tma
 
 constexpr int TMA_STAGES = 3;
@@ -505,17 +486,19 @@ struct __align__(16) TmaStage {
     eco_episode_t ep;
 };
 
+// Two episodes per warp: each half-warp (16 lanes, 16 vertices per lane in two 8-vertex chunks) runs its own episode
+// stream with its own ring, so the scalar bookkeeping of two episodes -- done by lanes 0 and 16 -- issues ONCE.
+constexpr int TMA_STREAMS = TMA_WARPS * 2;
 __global__ void __launch_bounds__(TMA_WARPS * 32, 4)
-env_step_tma_kernel(const eco_graphs_t g, const eco_env_t env, const int32_t* __restrict__ actions,
+env_step_ring_kernel(const eco_graphs_t g, const eco_env_t env, const int32_t* __restrict__ actions,
                     double* __restrict__ reward_out, uint8_t* __restrict__ done_out, int32_t* __restrict__ hist_a,
                     double* __restrict__ hist_r, double* __restrict__ hist_s) {
-    __shared__ TmaStage ring[TMA_WARPS][TMA_STAGES];
-    __shared__ uint64_t bars[TMA_WARPS][TMA_STAGES];
+    __shared__ TmaStage ring[TMA_STREAMS][TMA_STAGES];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long wglobal = (long long)blockIdx.x * TMA_WARPS + warp;
-    const long long wtotal = (long long)gridDim.x * TMA_WARPS;
+    const int l16 = lane & 15, stream = warp * 2 + (lane >> 4);
+    const long long sglobal = (long long)blockIdx.x * TMA_STREAMS + stream;
+    const long long stotal = (long long)gridDim.x * TMA_STREAMS;
     const int N = env.N, NP = env.NP, NCH = NP >> 3;
-    const bool has = lane < NCH;
     const bool use_tab = (g.reserved & 1) != 0;
     // the two tables every episode indexes with data-dependent addresses live in shared memory (L2 latency otherwise
     // sits between the loads and the first feature store / the visited-set probe)
@@ -526,81 +509,80 @@ env_step_tma_kernel(const eco_graphs_t g, const eco_env_t env, const int32_t* __
     if (tsf_shared)
         for (int i = threadIdx.x; i <= env.T; i += blockDim.x) s_tsf[i] = env.tsf_tab[i];
     const float* tsf = tsf_shared ? s_tsf : env.tsf_tab;
-    if (lane == 0)
-        for (int s = 0; s < TMA_STAGES; ++s) tma::mbar_init(&bars[warp][s], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
-    auto issue = [&](long long b, int a, int gi, int st) {          // lane 0: bulk copies of episode b into stage st
-        TmaStage& S = ring[warp][st];
-        uint64_t* bar = &bars[warp][st];
-        tma::mbar_expect_tx(bar, (uint32_t)(NP + 2 * NP + 2 * NP + NP + sizeof(eco_episode_t)));
-        tma::bulk_g2s(S.spins, env.spins + (size_t)b * NP, NP, bar);
-        tma::bulk_g2s(S.h, env.hfield + (size_t)b * NP, 2 * NP, bar);
-        tma::bulk_g2s(S.lf, env.last_flip + (size_t)b * NP, 2 * NP, bar);
-        tma::bulk_g2s(S.jrow, g.J + ((size_t)gi * NP + a) * NP, NP, bar);
-        tma::bulk_g2s(&S.ep, env.ep + b, sizeof(eco_episode_t), bar);
+    // all 16 lanes of the stream: 16-byte asynchronous copies (cp.async) of episode b into stage st, one commit group.
+    // (Five small bulk copies per episode kept the SM's single TMA unit busy ~70 cycles each -- that, not HBM or the
+    //  issue slots, bounded the first version of this kernel.)
+    const int p1 = NP >> 4, p2 = 3 * p1, p3 = 5 * p1, p4 = 6 * p1, p5 = p4 + (int)(sizeof(eco_episode_t) >> 4);
+    auto issue = [&](long long b, int a, int gi, int st, bool go) {
+        TmaStage& S = ring[stream][st];
+        if (go) {
+            for (int p = l16; p < p5; p += 16) {
+                const char* src;
+                char* dst;
+                if (p < p1) { src = (const char*)(env.spins + (size_t)b * NP) + 16 * p; dst = (char*)S.spins + 16 * p; }
+                else if (p < p2) { src = (const char*)(env.hfield + (size_t)b * NP) + 16 * (p - p1); dst = (char*)S.h + 16 * (p - p1); }
+                else if (p < p3) { src = (const char*)(env.last_flip + (size_t)b * NP) + 16 * (p - p2); dst = (char*)S.lf + 16 * (p - p2); }
+                else if (p < p4) { src = (const char*)(g.J + ((size_t)gi * NP + a) * NP) + 16 * (p - p3); dst = (char*)S.jrow + 16 * (p - p3); }
+                else { src = (const char*)(env.ep + b) + 16 * (p - p4); dst = (char*)&S.ep + 16 * (p - p4); }
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tma::smem_addr(dst)), "l"(src) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");     // (an empty group keeps the group count uniform)
     };
     auto clamp_action = [&](int a) { return (a < 0 || a >= N) ? 0 : a; };
 
-    // prologue: the first D = TMA_STAGES - 1 episodes of this warp in flight; action / graph of the next one in registers
+    // prologue: the first D = TMA_STAGES - 1 episodes of this stream in flight; action / graph of the next one in registers
     constexpr int D = TMA_STAGES - 1;
-    const long long b0 = wglobal;
-    int an[D + 1], gn[D + 1];       // action / graph index of episodes b, b + wtotal, ..., b + D * wtotal
+    const long long b0 = sglobal;
+    int an[D + 1], gn[D + 1];       // action / graph index of episodes b, b + stotal, ..., b + D * stotal
 #pragma unroll
     for (int k = 0; k <= D; ++k) {
         an[k] = 0; gn[k] = 0;
-        if (b0 + k * wtotal < env.B) { an[k] = actions[b0 + k * wtotal]; gn[k] = env.graph_idx[b0 + k * wtotal]; }
+        if (b0 + k * stotal < env.B) { an[k] = actions[b0 + k * stotal]; gn[k] = env.graph_idx[b0 + k * stotal]; }
     }
-    if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < D; ++k)
-            if (b0 + k * wtotal < env.B) issue(b0 + k * wtotal, clamp_action(an[k]), gn[k], k);
-    }
-    uint32_t phase_bits = 0;      // parity per stage
+    for (int k = 0; k < D; ++k) issue(b0 + k * stotal, clamp_action(an[k]), gn[k], k, b0 + k * stotal < env.B);
     int st = 0;
 
-    for (long long b = b0; b < env.B; b += wtotal) {
-        TmaStage& S = ring[warp][st];
-        // ---- keep the pipeline full: bulk copies of episode b + D*wtotal, action / graph of b + (D+1)*wtotal ----
-        const long long bD = b + D * wtotal, bN = b + (D + 1) * wtotal;
+    for (long long b = b0; __any_sync(0xffffffffu, b < env.B); b += stotal) {
+        const bool valid = b < env.B;                 // (the two streams of a warp may differ by one episode at the end)
+        TmaStage& S = ring[stream][st];
+        // ---- keep the pipeline full: bulk copies of episode b + D*stotal, action / graph of b + (D+1)*stotal ----
+        const long long bD = b + D * stotal, bN = b + (D + 1) * stotal;
         int a_new = 0, gi_new = 0;
         if (bN < env.B) { a_new = actions[bN]; gi_new = env.graph_idx[bN]; }
-        if (lane == 0 && bD < env.B) issue(bD, clamp_action(an[D]), gn[D], (st + D) % TMA_STAGES);
+        issue(bD, clamp_action(an[D]), gn[D], (st + D) % TMA_STAGES, bD < env.B);
         const int a_cur = an[0], gi_cur = gn[0];
 
-        tma::mbar_wait(&bars[warp][st], (phase_bits >> st) & 1u);
-        phase_bits ^= 1u << st;
+        asm volatile("cp.async.wait_group %0;" ::"n"(D) : "memory");   // this episode's group (D newer ones may be in flight)
+        __syncwarp();                                                  // ... of every lane of the stream
 
         // ---- episode b from shared memory ---------------------------------------------------------------------
         const int gi = gi_cur;
         int a = a_cur;
-        const int4 e0 = *reinterpret_cast<const int4*>(&S.ep);
-        const int4 e1 = *(reinterpret_cast<const int4*>(&S.ep) + 1);
+        int4 e0 = make_int4(0, 0, 0, 0), e1 = make_int4(0, FLAG_DONE, 0, 0);
+        if (valid) {
+            e0 = *reinterpret_cast<const int4*>(&S.ep);
+            e1 = *(reinterpret_cast<const int4*>(&S.ep) + 1);
+        }
         const int flags = e1.y;
         const int step_new = e0.x + 1;
-        bool active = !(flags & (FLAG_DONE | FLAG_STOPPED)) && step_new <= env.T;
+        bool active = valid && !(flags & (FLAG_DONE | FLAG_STOPPED)) && step_new <= env.T;
         if (a < 0 || a >= N) { a = 0; active = false; }
-        V8s s, j; V8h h; V8u l;
-        s.v = make_uint2(0, 0); j.v = make_uint2(0, 0); h.v = make_uint4(0, 0, 0, 0); l.v = make_uint4(0, 0, 0, 0);
-        if (has) {
-            s.v = *reinterpret_cast<const uint2*>(S.spins + lane * 8);
-            j.v = *reinterpret_cast<const uint2*>(S.jrow + lane * 8);
-            h.v = *reinterpret_cast<const uint4*>(S.h + lane * 8);
-            l.v = *reinterpret_cast<const uint4*>(S.lf + lane * 8);
-        }
-        const int s_a_old = S.spins[a];
-        const int h_a_old = S.h[a];
+        const int s_a_old = valid ? S.spins[a] : 1;
+        const int h_a_old = valid ? S.h[a] : 0;
         const int s_a_new = -s_a_old;
         const int delta = s_a_old * h_a_old;                            // spinsystem.py:393
         const double mlr = g.gscal[(size_t)gi * 4 + 0];
         const float* gtab = g.gain_tab + (size_t)gi * tab_stride(NP) + NP;
 
-        // lane 0: scalar state, dependent lookups requested now, used after the vertex loop
+        // lanes 0 / 16: scalar state, dependent lookups requested now, used after the vertex loop
         double sc0 = 0, sc1 = 0, sc2 = 0, sc3 = 0, total_reward = 0, delta_n = 0, qn = 1.0;
         ulonglong2 key = make_ulonglong2(0, 0), zob = make_ulonglong2(0, 0);
         uint32_t old_word = 0;
-        if (lane == 0) {
+        if (l16 == 0 && valid) {
             sc0 = S.ep.score; sc1 = S.ep.nscore; sc2 = S.ep.best_score; sc3 = S.ep.best_nscore;
             key = make_ulonglong2(S.ep.key[0], S.ep.key[1]);
             total_reward = S.ep.total_reward;
@@ -610,46 +592,56 @@ env_step_tma_kernel(const eco_graphs_t g, const eco_env_t env, const int32_t* __
             else qn = g.gscal[(size_t)gi * 4 + 1];
         }
         const uint64_t k0 = key.x ^ zob.x, k1 = key.y ^ zob.y;
-        uint64_t* tab = env.visited + (size_t)b * env.HCAP * 2;
+        uint64_t* tab = env.visited + (size_t)(valid ? b : 0) * env.HCAP * 2;
         uint32_t slot = (uint32_t)(k0 ^ (k0 >> 29)) & (env.HCAP - 1);
         ulonglong2 tv = make_ulonglong2(0, 0);
-        if (lane == 0 && active && env.use_basin) tv = *reinterpret_cast<const ulonglong2*>(tab + 2 * slot);
+        if (l16 == 0 && active && env.use_basin) tv = *reinterpret_cast<const ulonglong2*>(tab + 2 * slot);
 
         int nimp = 0;
-        if (has && active) {
-            float* x0 = env.xn + (size_t)b * 3 * NP + lane * 8;
+        if (active) {
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                float f0[4], f1[4], f2[4];
+            for (int cc = 0; cc < 2; ++cc) {
+                const int ch = l16 + 16 * cc;             // this lane's 8-vertex chunk
+                if (ch >= NCH) continue;
+                V8s s, j; V8h h; V8u l;
+                s.v = *reinterpret_cast<const uint2*>(S.spins + ch * 8);
+                j.v = *reinterpret_cast<const uint2*>(S.jrow + ch * 8);
+                h.v = *reinterpret_cast<const uint4*>(S.h + ch * 8);
+                l.v = *reinterpret_cast<const uint4*>(S.lf + ch * 8);
+                float* x0 = env.xn + (size_t)b * 3 * NP + ch * 8;
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    const int k = half * 4 + kk;
-                    const int i = lane * 8 + k;
-                    int si = s.b[k];
-                    if (i == a) { si = s_a_new; s.b[k] = (int8_t)si; l.h[k] = (uint16_t)step_new; }
-                    const int hi = h.h[k] + 2 * j.b[k] * s_a_new;
-                    h.h[k] = (int16_t)hi;
-                    const int gain = si * hi;
-                    nimp += gain > 0;
-                    f0[kk] = (float)si;
-                    f1[kk] = use_tab ? __ldg(gtab + gain) : feat_gain(gain, mlr);
-                    f2[kk] = tsf[step_new - l.h[k]];
+                for (int half = 0; half < 2; ++half) {
+                    float f0[4], f1[4], f2[4];
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const int k = half * 4 + kk;
+                        const int i = ch * 8 + k;
+                        int si = s.b[k];
+                        if (i == a) { si = s_a_new; s.b[k] = (int8_t)si; l.h[k] = (uint16_t)step_new; }
+                        const int hi = h.h[k] + 2 * j.b[k] * s_a_new;
+                        h.h[k] = (int16_t)hi;
+                        const int gain = si * hi;
+                        nimp += gain > 0;
+                        f0[kk] = (float)si;
+                        f1[kk] = use_tab ? __ldg(gtab + gain) : feat_gain(gain, mlr);
+                        f2[kk] = tsf[step_new - l.h[k]];
+                    }
+                    *reinterpret_cast<float4*>(x0 + 4 * half) = make_float4(f0[0], f0[1], f0[2], f0[3]);
+                    *reinterpret_cast<float4*>(x0 + NP + 4 * half) = make_float4(f1[0], f1[1], f1[2], f1[3]);
+                    *reinterpret_cast<float4*>(x0 + 2 * NP + 4 * half) = make_float4(f2[0], f2[1], f2[2], f2[3]);
                 }
-                *reinterpret_cast<float4*>(x0 + 4 * half) = make_float4(f0[0], f0[1], f0[2], f0[3]);
-                *reinterpret_cast<float4*>(x0 + NP + 4 * half) = make_float4(f1[0], f1[1], f1[2], f1[3]);
-                *reinterpret_cast<float4*>(x0 + 2 * NP + 4 * half) = make_float4(f2[0], f2[1], f2[2], f2[3]);
-            }
-            *reinterpret_cast<uint4*>(env.hfield + (size_t)b * NP + lane * 8) = h.v;
-            if ((a >> 3) == lane) {
-                *reinterpret_cast<uint2*>(env.spins + (size_t)b * NP + lane * 8) = s.v;
-                *reinterpret_cast<uint4*>(env.last_flip + (size_t)b * NP + lane * 8) = l.v;
+                *reinterpret_cast<uint4*>(env.hfield + (size_t)b * NP + ch * 8) = h.v;
+                if ((a >> 3) == ch) {
+                    *reinterpret_cast<uint2*>(env.spins + (size_t)b * NP + ch * 8) = s.v;
+                    *reinterpret_cast<uint4*>(env.last_flip + (size_t)b * NP + ch * 8) = l.v;
+                }
             }
         }
-        nimp = group_sum<32>(nimp);
+        nimp = group_sum<16>(nimp);
 
         int new_best = 0;
-        eco_episode_t* ep = env.ep + b;
-        if (lane == 0 && active) {
+        eco_episode_t* ep = env.ep + (valid ? b : 0);
+        if (l16 == 0 && active) {
             if (!use_tab) delta_n = __ddiv_rn((double)delta, qn);           // :394
             const double score = __dadd_rn(sc0, (double)delta);             // :399
             const double nscore = __dadd_rn(sc1, delta_n);                  // :400
@@ -698,12 +690,12 @@ env_step_tma_kernel(const eco_graphs_t g, const eco_env_t env, const int32_t* __
             if (hist_r) hist_r[hidx] = rew;
             if (hist_s) hist_s[hidx] = score;
             if (!new_best) env.diff_bits[(size_t)b * env.NW + (a >> 5)] = old_word ^ (1u << (a & 31));
-        } else if (lane == 0) {
+        } else if (l16 == 0 && valid) {
             if (reward_out) reward_out[b] = 0.0;
             if (done_out) done_out[b] = 1;
         }
-        new_best = __shfl_sync(0xffffffffu, new_best, 0);
-        if (new_best && active && lane < env.NW) env.diff_bits[(size_t)b * env.NW + lane] = 0u;
+        new_best = __shfl_sync(0xffffffffu, new_best, 0, 16);
+        if (new_best && active && l16 < env.NW) env.diff_bits[(size_t)b * env.NW + l16] = 0u;
 
         __syncwarp();                 // every lane is done with this stage before it is refilled two iterations on
         st = (st + 1) % TMA_STAGES;
@@ -849,9 +841,9 @@ int launch_env_step(const eco_graphs_t* g, eco_env_t* env, int policy, const int
             if (policy == ECO_POLICY_ACTIONS && B_ >= 4096) {      // bulk-copy staged, persistent warps
                 static int n_sm = 0;
                 if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
-                long long blocks = (B_ + TMA_WARPS - 1) / TMA_WARPS;
+                long long blocks = (B_ + TMA_STREAMS - 1) / TMA_STREAMS;
                 if (blocks > (long long)n_sm * 4) blocks = (long long)n_sm * 4;
-                env_step_tma_kernel<<<(unsigned)blocks, TMA_WARPS * 32, 0, st>>>(*g, *env, actions, reward, done, ha, hr, hs);
+                env_step_ring_kernel<<<(unsigned)blocks, TMA_WARPS * 32, 0, st>>>(*g, *env, actions, reward, done, ha, hr, hs);
             } else ECO_SW(32);
         }
         else if (NP_ <= 1024) env_step_kernel<128, true><<<(unsigned)B_, 128, 0, st>>>(*g, *env, policy, actions, reward, done, ha, hr, hs);

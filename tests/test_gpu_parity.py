@@ -220,8 +220,8 @@ def test_env_random_actions_multi_graph_vs_oracle(eng, n, p, B, steps):
 
 
 @pytest.mark.parametrize("n", [129, 200, 241, 256])
-def test_env_step_bulk_copy_ring_matches_subwarp_kernel(eng, n):
-    """B >= 4096 with caller-supplied actions runs env_step_tma_kernel (persistent warps, bulk-copy ring); smaller batches
+def test_env_step_staged_ring_matches_subwarp_kernel(eng, n):
+    """B >= 4096 with caller-supplied actions runs env_step_ring_kernel (persistent warps, async-copy ring); smaller batches
     run the sub-warp kernel that the oracle tests pin.  Same episodes, same actions (out-of-range ones included): every
     state array, observation, reward and done flag must be identical."""
     rng = np.random.default_rng(1000 + n)
