@@ -177,6 +177,8 @@ int eco_env_best_spins(const eco_env_t* env, int8_t* best_spins_dev, void* strea
 typedef struct {
     const float* w_init;      /* node_init_embedding_layer.0.weight          (64, 7)   */
     const float* w_edge;      /* edge_embedding_layer.edge_embedding_NN.weight (63, 8) */
+                              /* (S2V-DQN networks, n_obs_in = 1: (64, 1) and (63, 2) -- zero-pad the six missing
+                               *  observable columns, the result is the same)                                   */
     const float* w_edge_feat; /* edge_embedding_layer.edge_feature_NN.weight (64, 64)  */
     const float* w_msg[3];    /* update_node_embedding_layer.l.message_layer.weight (64, 128) */
     const float* w_upd[3];    /* update_node_embedding_layer.l.update_layer.weight  (64, 128) */
@@ -191,7 +193,9 @@ size_t eco_mpnn_packed_bytes(void);
 /* pre-split the weights into the bf16 hi/lo operand layout the tcgen05 kernel consumes (device -> device) */
 int    eco_mpnn_pack(const eco_mpnn_t* w, void* packed_dev, void* stream);
 
-/* Q[b, i] for b < B from features xn [B,3,NP] / xg [B,4] and graph_idx [B] (use env->xn etc. for live
+/* ECO_MPNN_TCGEN05 / AUTO with couplings in {-1,0,1}: N <= 208 on the tensor cores (graphs with NP <= 96 are processed
+ * 192/NP at a time as one block-diagonal graph); larger graphs and other weights run on the CUDA-core kernel.
+ * Q[b, i] for b < B from features xn [B,3,NP] / xg [B,4] and graph_idx [B] (use env->xn etc. for live
  * episodes, or replayed features for training).  norm_max: the batch-wide max degree the reference divides
  * by (mpnn.py:102); 0 means "max degree over the whole graph set", < 0 means "each episode's own graph" (what the
  * reference computes when it evaluates one environment at a time, e.g. DQN.act).
@@ -203,7 +207,8 @@ int eco_mpnn_forward(const eco_graphs_t* g, const eco_mpnn_t* w, int32_t B, cons
 /* ---------------------------------------------------------------------------------------------------------
  * Rollout: n_steps x [Q-eval + argmax -> env step] with no host round trip.  Replaces the hot loop of
  * __test_network_batched (reference experiments/utils.py:169-207) and, with ECO_POLICY_GREEDY, the Greedy
- * baseline (experiments/utils.py:218-227).  actions_scratch_dev [B] int32.
+ * baseline (experiments/utils.py:218-227).  actions_scratch_dev [B] int32.  With ECO_ENV_IRREVERSIBLE the network
+ * policy takes the argmax over the spins still at -1 (eco_env_masked_argmax) and episodes end when none is left.
  * --------------------------------------------------------------------------------------------------------- */
 int eco_rollout(const eco_graphs_t* g, eco_env_t* env, const eco_mpnn_t* w, int32_t n_steps, int32_t policy,
                 float norm_max, int32_t* actions_scratch_dev, void* mpnn_scratch_dev, int32_t impl,
