@@ -17,7 +17,7 @@ G = int(os.environ.get("ECO_ENV_G", "1024"))
 n, T = 200, 400
 L = _lib.lib()
 gs = engine.GraphSet(bench.ba_graphs(G, n, 4, seed=0))
-env = engine.BatchedSpinSystem(gs, B, T, 1.0 / n)
+env = engine.BatchedSpinSystem(gs, B, T, None if os.environ.get("ECO_ENV_NOBASIN") else 1.0 / n)
 rng = np.random.default_rng(0)
 env.reset(spins=torch.from_numpy((2 * rng.integers(0, 2, size=(B, n)) - 1).astype(np.int8)).cuda())
 gen = torch.Generator(device="cuda").manual_seed(7)
