@@ -475,30 +475,26 @@ namespace tma {
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 }  // namespace tma
 
-constexpr int TMA_STAGES = 3;
 constexpr int TMA_TSF_MAX = 1024;   // time-since-flip table entries kept in shared memory (T + 1 <= this, else read from global)
 constexpr int TMA_WARPS = 4;
-struct __align__(16) TmaStage {
-    int8_t spins[256];
-    int16_t h[256];
-    uint16_t lf[256];
-    int8_t jrow[256];
-    eco_episode_t ep;
-};
-
 // Two episodes per warp: each half-warp (16 lanes, 16 vertices per lane in two 8-vertex chunks) runs its own episode
 // stream with its own ring, so the scalar bookkeeping of two episodes -- done by lanes 0 and 16 -- issues ONCE.
-constexpr int TMA_STREAMS = TMA_WARPS * 2;
+// TPE lanes per episode stream (16 or 8): 32 / TPE streams per warp.  The ring lives in dynamic shared memory, one stage =
+// [spins NP | h 2NP | last_flip 2NP | J row NP | scalar block 96] bytes.
+template <int TPE, int STAGES>
 __global__ void __launch_bounds__(TMA_WARPS * 32, 4)
 env_step_ring_kernel(const eco_graphs_t g, const eco_env_t env, const int32_t* __restrict__ actions,
                     double* __restrict__ reward_out, uint8_t* __restrict__ done_out, int32_t* __restrict__ hist_a,
                     double* __restrict__ hist_r, double* __restrict__ hist_s) {
-    __shared__ TmaStage ring[TMA_STREAMS][TMA_STAGES];
+    extern __shared__ __align__(16) unsigned char ring_raw[];
+    constexpr int SPW = 32 / TPE, NSTREAMS = TMA_WARPS * SPW;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int l16 = lane & 15, stream = warp * 2 + (lane >> 4);
-    const long long sglobal = (long long)blockIdx.x * TMA_STREAMS + stream;
-    const long long stotal = (long long)gridDim.x * TMA_STREAMS;
+    const int l16 = lane % TPE, stream = warp * SPW + lane / TPE;
+    const long long sglobal = (long long)blockIdx.x * NSTREAMS + stream;
+    const long long stotal = (long long)gridDim.x * NSTREAMS;
     const int N = env.N, NP = env.NP, NCH = NP >> 3;
+    const int stage_bytes = 6 * NP + (int)sizeof(eco_episode_t);
+    unsigned char* my_ring = ring_raw + (size_t)stream * STAGES * stage_bytes;
     const bool use_tab = (g.reserved & 1) != 0;
     // the two tables every episode indexes with data-dependent addresses live in shared memory (L2 latency otherwise
     // sits between the loads and the first feature store / the visited-set probe)
@@ -516,17 +512,16 @@ env_step_ring_kernel(const eco_graphs_t g, const eco_env_t env, const int32_t* _
     //  issue slots, bounded the first version of this kernel.)
     const int p1 = NP >> 4, p2 = 3 * p1, p3 = 5 * p1, p4 = 6 * p1, p5 = p4 + (int)(sizeof(eco_episode_t) >> 4);
     auto issue = [&](long long b, int a, int gi, int st, bool go) {
-        TmaStage& S = ring[stream][st];
+        char* S = (char*)my_ring + (size_t)st * stage_bytes;      // the stage is laid out in copy order
         if (go) {
-            for (int p = l16; p < p5; p += 16) {
+            for (int p = l16; p < p5; p += TPE) {
                 const char* src;
-                char* dst;
-                if (p < p1) { src = (const char*)(env.spins + (size_t)b * NP) + 16 * p; dst = (char*)S.spins + 16 * p; }
-                else if (p < p2) { src = (const char*)(env.hfield + (size_t)b * NP) + 16 * (p - p1); dst = (char*)S.h + 16 * (p - p1); }
-                else if (p < p3) { src = (const char*)(env.last_flip + (size_t)b * NP) + 16 * (p - p2); dst = (char*)S.lf + 16 * (p - p2); }
-                else if (p < p4) { src = (const char*)(g.J + ((size_t)gi * NP + a) * NP) + 16 * (p - p3); dst = (char*)S.jrow + 16 * (p - p3); }
-                else { src = (const char*)(env.ep + b) + 16 * (p - p4); dst = (char*)&S.ep + 16 * (p - p4); }
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tma::smem_addr(dst)), "l"(src) : "memory");
+                if (p < p1) src = (const char*)(env.spins + (size_t)b * NP) + 16 * p;
+                else if (p < p2) src = (const char*)(env.hfield + (size_t)b * NP) + 16 * (p - p1);
+                else if (p < p3) src = (const char*)(env.last_flip + (size_t)b * NP) + 16 * (p - p2);
+                else if (p < p4) src = (const char*)(g.J + ((size_t)gi * NP + a) * NP) + 16 * (p - p3);
+                else src = (const char*)(env.ep + b) + 16 * (p - p4);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tma::smem_addr(S + 16 * p)), "l"(src) : "memory");
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");     // (an empty group keeps the group count uniform)
@@ -534,7 +529,7 @@ env_step_ring_kernel(const eco_graphs_t g, const eco_env_t env, const int32_t* _
     auto clamp_action = [&](int a) { return (a < 0 || a >= N) ? 0 : a; };
 
     // prologue: the first D = TMA_STAGES - 1 episodes of this stream in flight; action / graph of the next one in registers
-    constexpr int D = TMA_STAGES - 1;
+    constexpr int D = STAGES - 1;
     const long long b0 = sglobal;
     int an[D + 1], gn[D + 1];       // action / graph index of episodes b, b + stotal, ..., b + D * stotal
 #pragma unroll
@@ -548,12 +543,17 @@ env_step_ring_kernel(const eco_graphs_t g, const eco_env_t env, const int32_t* _
 
     for (long long b = b0; __any_sync(0xffffffffu, b < env.B); b += stotal) {
         const bool valid = b < env.B;                 // (the two streams of a warp may differ by one episode at the end)
-        TmaStage& S = ring[stream][st];
+        const unsigned char* Sb = my_ring + (size_t)st * stage_bytes;
+        const int8_t* S_spins = reinterpret_cast<const int8_t*>(Sb);
+        const int16_t* S_h = reinterpret_cast<const int16_t*>(Sb + NP);
+        const uint16_t* S_lf = reinterpret_cast<const uint16_t*>(Sb + 3 * NP);
+        const int8_t* S_jrow = reinterpret_cast<const int8_t*>(Sb + 5 * NP);
+        const eco_episode_t* S_ep = reinterpret_cast<const eco_episode_t*>(Sb + 6 * NP);
         // ---- keep the pipeline full: bulk copies of episode b + D*stotal, action / graph of b + (D+1)*stotal ----
         const long long bD = b + D * stotal, bN = b + (D + 1) * stotal;
         int a_new = 0, gi_new = 0;
         if (bN < env.B) { a_new = actions[bN]; gi_new = env.graph_idx[bN]; }
-        issue(bD, clamp_action(an[D]), gn[D], (st + D) % TMA_STAGES, bD < env.B);
+        issue(bD, clamp_action(an[D]), gn[D], (st + D) % STAGES, bD < env.B);
         const int a_cur = an[0], gi_cur = gn[0];
 
         asm volatile("cp.async.wait_group %0;" ::"n"(D) : "memory");   // this episode's group (D newer ones may be in flight)
@@ -564,15 +564,15 @@ env_step_ring_kernel(const eco_graphs_t g, const eco_env_t env, const int32_t* _
         int a = a_cur;
         int4 e0 = make_int4(0, 0, 0, 0), e1 = make_int4(0, FLAG_DONE, 0, 0);
         if (valid) {
-            e0 = *reinterpret_cast<const int4*>(&S.ep);
-            e1 = *(reinterpret_cast<const int4*>(&S.ep) + 1);
+            e0 = *reinterpret_cast<const int4*>(S_ep);
+            e1 = *(reinterpret_cast<const int4*>(S_ep) + 1);
         }
         const int flags = e1.y;
         const int step_new = e0.x + 1;
         bool active = valid && !(flags & (FLAG_DONE | FLAG_STOPPED)) && step_new <= env.T;
         if (a < 0 || a >= N) { a = 0; active = false; }
-        const int s_a_old = valid ? S.spins[a] : 1;
-        const int h_a_old = valid ? S.h[a] : 0;
+        const int s_a_old = valid ? S_spins[a] : 1;
+        const int h_a_old = valid ? S_h[a] : 0;
         const int s_a_new = -s_a_old;
         const int delta = s_a_old * h_a_old;                            // spinsystem.py:393
         const double mlr = g.gscal[(size_t)gi * 4 + 0];
@@ -583,9 +583,9 @@ env_step_ring_kernel(const eco_graphs_t g, const eco_env_t env, const int32_t* _
         ulonglong2 key = make_ulonglong2(0, 0), zob = make_ulonglong2(0, 0);
         uint32_t old_word = 0;
         if (l16 == 0 && valid) {
-            sc0 = S.ep.score; sc1 = S.ep.nscore; sc2 = S.ep.best_score; sc3 = S.ep.best_nscore;
-            key = make_ulonglong2(S.ep.key[0], S.ep.key[1]);
-            total_reward = S.ep.total_reward;
+            sc0 = S_ep->score; sc1 = S_ep->nscore; sc2 = S_ep->best_score; sc3 = S_ep->best_nscore;
+            key = make_ulonglong2(S_ep->key[0], S_ep->key[1]);
+            total_reward = S_ep->total_reward;
             zob = *reinterpret_cast<const ulonglong2*>(s_zob + 2 * a);
             old_word = env.diff_bits[(size_t)b * env.NW + (a >> 5)];
             if (use_tab) delta_n = __ldg(g.dn_tab + (size_t)gi * tab_stride(NP) + NP + delta);
@@ -600,14 +600,14 @@ env_step_ring_kernel(const eco_graphs_t g, const eco_env_t env, const int32_t* _
         int nimp = 0;
         if (active) {
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-                const int ch = l16 + 16 * cc;             // this lane's 8-vertex chunk
+            for (int cc = 0; cc < 32 / TPE; ++cc) {       // NP <= 256: at most 32 chunks
+                const int ch = l16 + TPE * cc;            // this lane's 8-vertex chunk
                 if (ch >= NCH) continue;
                 V8s s, j; V8h h; V8u l;
-                s.v = *reinterpret_cast<const uint2*>(S.spins + ch * 8);
-                j.v = *reinterpret_cast<const uint2*>(S.jrow + ch * 8);
-                h.v = *reinterpret_cast<const uint4*>(S.h + ch * 8);
-                l.v = *reinterpret_cast<const uint4*>(S.lf + ch * 8);
+                s.v = *reinterpret_cast<const uint2*>(S_spins + ch * 8);
+                j.v = *reinterpret_cast<const uint2*>(S_jrow + ch * 8);
+                h.v = *reinterpret_cast<const uint4*>(S_h + ch * 8);
+                l.v = *reinterpret_cast<const uint4*>(S_lf + ch * 8);
                 float* x0 = env.xn + (size_t)b * 3 * NP + ch * 8;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
@@ -637,7 +637,7 @@ env_step_ring_kernel(const eco_graphs_t g, const eco_env_t env, const int32_t* _
                 }
             }
         }
-        nimp = group_sum<16>(nimp);
+        nimp = group_sum<TPE>(nimp);
 
         int new_best = 0;
         eco_episode_t* ep = env.ep + (valid ? b : 0);
@@ -694,11 +694,11 @@ env_step_ring_kernel(const eco_graphs_t g, const eco_env_t env, const int32_t* _
             if (reward_out) reward_out[b] = 0.0;
             if (done_out) done_out[b] = 1;
         }
-        new_best = __shfl_sync(0xffffffffu, new_best, 0, 16);
+        new_best = __shfl_sync(0xffffffffu, new_best, 0, TPE);
         if (new_best && active && l16 < env.NW) env.diff_bits[(size_t)b * env.NW + l16] = 0u;
 
         __syncwarp();                 // every lane is done with this stage before it is refilled two iterations on
-        st = (st + 1) % TMA_STAGES;
+        st = (st + 1) % STAGES;
 #pragma unroll
         for (int k = 0; k < D; ++k) { an[k] = an[k + 1]; gn[k] = gn[k + 1]; }
         an[D] = a_new; gn[D] = gi_new;
@@ -841,9 +841,18 @@ int launch_env_step(const eco_graphs_t* g, eco_env_t* env, int policy, const int
             if (policy == ECO_POLICY_ACTIONS && B_ >= 4096) {      // bulk-copy staged, persistent warps
                 static int n_sm = 0;
                 if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
-                long long blocks = (B_ + TMA_STREAMS - 1) / TMA_STREAMS;
+                // 16 lanes per stream (two streams per warp), 3-deep ring.  (8 lanes per stream with a 2-deep ring -- 64
+                // streams per SM -- was measured slower: 377 us vs 327 us.)
+                constexpr int TPE = 16, STAGES = 3, NSTREAMS = TMA_WARPS * (32 / TPE);
+                const size_t ring_bytes = (size_t)NSTREAMS * STAGES * (6 * NP_ + sizeof(eco_episode_t));
+                static bool attr = false;
+                if (!attr) {
+                    ECO_CUDA(cudaFuncSetAttribute(env_step_ring_kernel<TPE, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+                    attr = true;
+                }
+                long long blocks = (B_ + NSTREAMS - 1) / NSTREAMS;
                 if (blocks > (long long)n_sm * 4) blocks = (long long)n_sm * 4;
-                env_step_ring_kernel<<<(unsigned)blocks, TMA_WARPS * 32, 0, st>>>(*g, *env, actions, reward, done, ha, hr, hs);
+                env_step_ring_kernel<TPE, STAGES><<<(unsigned)blocks, TMA_WARPS * 32, ring_bytes, st>>>(*g, *env, actions, reward, done, ha, hr, hs);
             } else ECO_SW(32);
         }
         else if (NP_ <= 1024) env_step_kernel<128, true><<<(unsigned)B_, 128, 0, st>>>(*g, *env, policy, actions, reward, done, ha, hr, hs);
