@@ -59,9 +59,9 @@ def ba_graphs(count, n, m, seed):
 
 
 def load_weights():
-    from oracle.mpnn import weights_from_npz   # only a dict-of-arrays loader; no oracle compute on this arm
+    """The reference's pretrained eco/network_best_BA_200spin checkpoint, as recorded in the golden fixture (`w::<key>`)."""
     z = np.load(os.path.join(ROOT, "tests", "golden", "ba200_g0.npz"))
-    return weights_from_npz(z)
+    return {k[3:]: np.asarray(z[k], dtype=np.float32) for k in z.files if k.startswith("w::")}
 
 
 def peaks():
