@@ -74,7 +74,7 @@ static void carve_graphs(eco_graphs_t* g, Carver& c, int G, int N) {
     g->dmax = c.take<float>(64);
     g->gain_tab = c.take<float>((size_t)G * tab_stride(NP));
     g->dn_tab = c.take<double>((size_t)G * tab_stride(NP));
-    g->tc_ops = N <= 208 ? c.take<uint16_t>((size_t)G * 2 * NP * NP) : nullptr;
+    g->tc_ops = c.take<uint16_t>((size_t)G * 2 * NP * NP);   // (N > 208: used panel by panel by the aggregation kernel)
 }
 
 static int hcap_for(int T) {
@@ -340,6 +340,14 @@ int eco_mpnn_forward(const eco_graphs_t* g, const eco_mpnn_t* w, int32_t B, cons
     }
     ECO_CHECK_ARG(use == ECO_MPNN_SIMT, ECO_ERR_INVALID, "eco_mpnn_forward: unknown impl %d", impl);
     return launch_mpnn_simt(g, w, B, gidx, xn, xg, norm_max, q, actions, scratch, (cudaStream_t)stream);
+}
+
+int eco_graph_aggregate(const eco_graphs_t* g, int32_t B, const int32_t* gidx, const float* x, int32_t use_abs,
+                        float scale, float* out, void* stream) {
+    ECO_CHECK_ARG(g && gidx && x && out && B >= 1, ECO_ERR_INVALID, "eco_graph_aggregate: bad argument");
+    ECO_CHECK_ARG(mpnn_tcl_supported(g), ECO_ERR_UNSUPPORTED, "eco_graph_aggregate: needs couplings in {-1,0,1}");
+    return launch_tcl_contract(g, gidx, B, x, use_abs ? 1 : 0, nullptr, 0, (size_t)g->N * 64, out, (size_t)g->N * 64, scale,
+                               0, 0.f, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------ rollout

@@ -204,6 +204,13 @@ int eco_mpnn_forward(const eco_graphs_t* g, const eco_mpnn_t* w, int32_t B, cons
                      const float* xn_dev, const float* xg_dev, float norm_max, float* q_dev,
                      int32_t* actions_dev, void* scratch_dev, int32_t impl, void* stream);
 
+/* The N x N product of a message-passing layer on the tensor cores (reference src/networks/mpnn.py:114-116:
+ * torch.matmul(adj, node_features) / norm), any N <= ECO_MAX_SPINS, couplings in {-1,0,1}:
+ *   out[b][i][f] = scale / max(1, deg_i) * sum_j J'[j][i] * x[b][j][f],   f < 64,   J' = J or |J| (use_abs)
+ * x_dev, out_dev: [B, N, 64] fp32.  fp32-accurate (x is split into two bf16 terms, J is exact). */
+int eco_graph_aggregate(const eco_graphs_t* g, int32_t B, const int32_t* graph_idx_dev, const float* x_dev,
+                        int32_t use_abs, float scale, float* out_dev, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Rollout: n_steps x [Q-eval + argmax -> env step] with no host round trip.  Replaces the hot loop of
  * __test_network_batched (reference experiments/utils.py:169-207) and, with ECO_POLICY_GREEDY, the Greedy

@@ -550,3 +550,31 @@ def test_mincut_env_and_rollout_bit_exact(eng, name):
     gc, gsp, gst = env.results()
     assert np.array_equal(gc.cpu().numpy().astype(np.float64), z["greedy_cuts"])
     assert np.array_equal(gsp.cpu().numpy(), z["greedy_spins"]) and np.array_equal(gst.cpu().numpy(), z["greedy_steps"])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# tensor-core neighbour aggregation for graphs beyond the resident kernel (eco_graph_aggregate, mpnn_tcl.cu)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,p,B", [(20, 0.3, 3), (200, 0.1, 5), (333, 0.1, 4), (500, 0.15, 6), (1100, 0.02, 3), (2000, 0.01, 2)])
+@pytest.mark.parametrize("use_abs", [0, 1])
+def test_graph_aggregate_matches_fp64_product(eng, n, p, B, use_abs):
+    import ctypes as C
+    from eco_dqn_b200 import _lib
+    rng = np.random.default_rng(n + use_abs)
+    G = 2
+    Js = _random_graphs(rng, G, n, p)
+    gs = eng.GraphSet(Js)
+    gidx = torch.from_numpy((np.arange(B) % G).astype(np.int32)).cuda()
+    x = torch.from_numpy(rng.standard_normal((B, n, 64)).astype(np.float32) * 3.0).cuda()
+    out = torch.full((B, n, 64), float("nan"), dtype=torch.float32, device="cuda")
+    eng.check(_lib.lib().eco_graph_aggregate(C.byref(gs.c), B, C.c_void_p(gidx.data_ptr()), C.c_void_p(x.data_ptr()),
+                                             use_abs, 0.5, C.c_void_p(out.data_ptr()),
+                                             C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    Jd = torch.from_numpy(Js.astype(np.float64)).cuda()[gidx.long()]
+    if use_abs:
+        Jd = Jd.abs()
+    deg = (Jd != 0).sum(1).clamp(min=1).double()                       # [B, n] (symmetric)
+    ref = 0.5 * torch.einsum("bji,bjf->bif", Jd, x.double()) / deg.unsqueeze(-1)
+    err = (out.double() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert np.isfinite(err) and err <= 2e-5 * scale, (err, scale)      # bf16 hi+lo: 16 mantissa bits per term, fp32 accumulate
