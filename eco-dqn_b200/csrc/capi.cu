@@ -127,7 +127,12 @@ static int prepare(const eco_graphs_t* g, cudaStream_t st, int first = 0, int co
 }
 
 static int pick_impl(const eco_graphs_t* g, const eco_mpnn_t* w, int impl) {
-    if (impl == ECO_MPNN_AUTO) return (w->packed && mpnn_tc_supported(g)) ? ECO_MPNN_TCGEN05 : ECO_MPNN_SIMT;
+    // tensor cores: the resident kernel for N <= 208, the panel-streaming aggregation + CUDA-core linears above
+    if (impl == ECO_MPNN_AUTO) {
+        if (w->packed && mpnn_tc_supported(g)) return ECO_MPNN_TCGEN05;
+        if (g->N > 208 && mpnn_tcl_supported(g)) return ECO_MPNN_TCGEN05;
+        return ECO_MPNN_SIMT;
+    }
     return impl;
 }
 
@@ -301,7 +306,7 @@ int eco_env_results(const eco_env_t* env, int32_t* best_cut, int8_t* best_spins,
 // masked: irreversible spins)
 static size_t mpnn_kernel_scratch_bytes(int32_t B, int32_t N, int32_t impl) {
     size_t a = mpnn_simt_scratch_bytes(B, N);
-    size_t b = (impl == ECO_MPNN_SIMT) ? 0 : mpnn_tc_scratch_bytes(B, N);
+    size_t b = (impl == ECO_MPNN_SIMT) ? 0 : (N <= 208 ? mpnn_tc_scratch_bytes(B, N) : mpnn_tcl_scratch_bytes(B, N));
     return align256(a > b ? a : b);
 }
 size_t eco_mpnn_scratch_bytes(int32_t B, int32_t N, int32_t impl) {
@@ -332,10 +337,15 @@ int eco_mpnn_forward(const eco_graphs_t* g, const eco_mpnn_t* w, int32_t B, cons
     int rc = check_weights(w, "eco_mpnn_forward");
     if (rc) return rc;
     const int use = pick_impl(g, w, impl);
+    if (use == ECO_MPNN_TCGEN05 && g->N > 208) {
+        ECO_CHECK_ARG(mpnn_tcl_supported(g), ECO_ERR_UNSUPPORTED,
+                      "eco_mpnn_forward: the tensor-core paths need couplings in {-1,0,1}; use ECO_MPNN_SIMT");
+        return launch_mpnn_tcl(g, w, B, gidx, xn, xg, norm_max, q, actions, scratch, (cudaStream_t)stream);
+    }
     if (use == ECO_MPNN_TCGEN05) {
         ECO_CHECK_ARG(w->packed, ECO_ERR_INVALID, "eco_mpnn_forward: tcgen05 path needs eco_mpnn_pack() output");
         ECO_CHECK_ARG(mpnn_tc_supported(g), ECO_ERR_UNSUPPORTED,
-                      "eco_mpnn_forward: tcgen05 path supports N <= 208 (got N=%d); use ECO_MPNN_SIMT", g->N);
+                      "eco_mpnn_forward: the tensor-core paths need couplings in {-1,0,1}; use ECO_MPNN_SIMT");
         return launch_mpnn_tc(g, w, B, gidx, xn, xg, norm_max, q, actions, scratch, (cudaStream_t)stream);
     }
     ECO_CHECK_ARG(use == ECO_MPNN_SIMT, ECO_ERR_INVALID, "eco_mpnn_forward: unknown impl %d", impl);

@@ -578,3 +578,38 @@ def test_graph_aggregate_matches_fp64_product(eng, n, p, B, use_abs):
     err = (out.double() - ref).abs().max().item()
     scale = ref.abs().max().item()
     assert np.isfinite(err) and err <= 2e-5 * scale, (err, scale)      # bf16 hi+lo: 16 mantissa bits per term, fp32 accumulate
+
+
+@pytest.mark.parametrize("n,p,B", [(209, 0.1, 5), (333, 0.08, 4), (500, 0.15, 6), (1100, 0.02, 3), (2000, 0.01, 2)])
+@pytest.mark.parametrize("norm_max", [None, -1.0])
+def test_mpnn_large_graph_tensor_path_vs_oracle_and_simt(eng, n, p, B, norm_max):
+    """N > 208: aggregation on the tensor cores (mpnn_tcl.cu) + CUDA-core linears, against the oracle (Q tolerance) and
+    against the all-CUDA-core kernel."""
+    from oracle.mpnn import mpnn_forward, KEYS
+    from eco_dqn_b200 import _lib
+    rng = np.random.default_rng(3 * n + B)
+    G = 2
+    Js = _random_graphs(rng, G, n, p)
+    gidx = (np.arange(B) % G).astype(np.int32)
+    wd = {k: (rng.standard_normal(s) * (0.3 if len(s) > 1 else 0.1)).astype(np.float32)
+          for k, s in zip(KEYS, eng.STATE_DICT_SHAPES)}
+    gs = eng.GraphSet(Js)
+    env = eng.BatchedSpinSystem(gs, B, 2 * n, 1.0 / n)
+    env.reset(spins=(2 * rng.integers(0, 2, size=(B, n)) - 1).astype(np.int8), graph_idx=gidx)
+    for t in range(4):
+        env.step(torch.from_numpy(rng.integers(0, n, size=B).astype(np.int32)))
+    w = eng.MPNNWeights(wd)
+    q_tc, a_tc = env.q_values(w, impl=_lib.MPNN_TCGEN05, norm_max=norm_max)
+    q_tc, a_tc = q_tc.cpu().numpy().copy(), a_tc.cpu().numpy().copy()
+    q_si, a_si = env.q_values(w, impl=_lib.MPNN_SIMT, norm_max=norm_max)
+    q_si = q_si.cpu().numpy()
+    assert np.allclose(q_tc, q_si, rtol=Q_RTOL, atol=Q_ATOL_FRAC * np.abs(q_si).max())
+    assert np.array_equal(a_tc, q_tc.argmax(1))
+    if n <= 500:                                                  # the dense oracle needs B * N^2 * 63 floats
+        obs7 = env.observation().cpu().numpy()
+        full = np.concatenate([obs7, Js[gidx].astype(np.float32)], axis=1)
+        if norm_max is None:
+            ref = mpnn_forward(wd, full).numpy()
+        else:
+            ref = np.stack([mpnn_forward(wd, full[b:b + 1]).numpy().reshape(-1) for b in range(B)])
+        assert np.allclose(q_tc, ref, rtol=Q_RTOL, atol=Q_ATOL_FRAC * np.abs(ref).max())

@@ -30,8 +30,6 @@ cases = [("ER-20  (C1) ", 20, 0.15, 100, 5000), ("ER-40  (C5) ", 40, 0.15, 64, 4
 for name, n, p, G, B in cases:
     gs = engine.GraphSet(er_graphs(G, n, p, rng))
     for impl_name, impl in (("simt", _lib.MPNN_SIMT), ("tcgen05", _lib.MPNN_TCGEN05)):
-        if impl == _lib.MPNN_TCGEN05 and n > 208:
-            continue
         env = engine.BatchedSpinSystem(gs, B, 2 * n, 1.0 / n, mpnn_impl=impl)
         w = engine.MPNNWeights(w_all)
         env.reset(spins=(2 * rng.integers(0, 2, size=(B, n)) - 1).astype(np.int8))
