@@ -14,6 +14,7 @@
 // global scratch (L2 resident); neighbour aggregation scans the int8 adjacency row 16 bytes per lane and
 // visits only non-zeros; the 64x64 / 64x128 linears run on 8-vertex tiles per warp (16 accumulators per lane,
 // weights transposed in shared memory, inputs broadcast from shared memory).
+#include <cstdlib>
 #include "eco_common.cuh"
 
 namespace eco {
@@ -607,10 +608,15 @@ int launch_mpnn_tcl(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int
     phase(0);
     // g = (|A| S + A D) / (2 deg), feature 63 = deg / deg_max
     if (!rc) rc = launch_tcl_contract(g, gidx, B, buf + 4 * bs, 1, buf + 5 * bs, 0, es, buf + 3 * bs, es, 0.5f, 1, norm_max, st);
-    phase(1);
+    // per-vertex linears: tensor cores when the packed bf16 hi/lo weights are there (eco_mpnn_pack), else CUDA cores
+    static const bool cuda_linears = getenv("ECO_TCL_CUDA_LINEARS") != nullptr;
+    const bool tl = w->packed != nullptr && !cuda_linears;
+    if (tl) { if (!rc) rc = launch_tcl_linear(g, w, B, buf, -1, st); }
+    else phase(1);
     for (int l = 0; l < 3 && !rc; ++l) {
         rc = launch_tcl_contract(g, gidx, B, buf + ((l & 1) ? bs : 0), 0, nullptr, 0, es, buf + 3 * bs, es, 1.f, 0, norm_max, st);
-        phase(2 + l);
+        if (tl) { if (!rc) rc = launch_tcl_linear(g, w, B, buf, l, st); }
+        else phase(2 + l);
     }
     phase(5);
     prof_end(ECO_PROF_MPNN, st);

@@ -30,6 +30,7 @@
 
 #include "eco_common.cuh"
 #include "tc_prims.cuh"
+#include "mpnn_pack.cuh"
 
 namespace eco {
 namespace {
@@ -71,19 +72,6 @@ constexpr int SM_TOTAL = SM_MISC + 64 + 16 * 4 + 16 * 4;
 static_assert(NPMAX * NPMAX * 2 <= 2 * 128 * NPMAX * 2, "|A| must fit in the H+E region");
 static_assert(7 * NPMAX * 4 <= 128 * CHUNK * 2, "xf must fit in a chunk buffer");
 static_assert(SM_TOTAL + 128 <= 227 * 1024, "shared memory budget (dynamic + static)");
-
-// packed weights (uint32 words): [128 stacked rows][k/2] per matrix
-constexpr int PK_WEF = 0;                    // 128 x 32
-constexpr int PK_WM = PK_WEF + 128 * 32;     // 3 x 128 x 64
-constexpr int PK_WU = PK_WM + 3 * 128 * 64;  // 3 x 128 x 64
-constexpr int PK_WORDS = PK_WU + 3 * 128 * 64;
-
-// Packed layout per matrix (KW words per stacked row): word (r, c) with r = 32q + lane, c = 8cg + 4h + j lives at
-// ((((q * KW/8 + cg) * 2 + h) * 32 + lane) * 4 + j): every LDG.128 of a warp in ldg_weights() is 512 contiguous bytes.
-__host__ __device__ inline int packed_index(int r, int c, int kw) {
-    const int q = r >> 5, lane = r & 31, cg = c >> 3, h = (c >> 2) & 1, j = c & 3;
-    return (((q * (kw / 8) + cg) * 2 + h) * 32 + lane) * 4 + j;
-}
 
 __global__ void mpnn_pack_kernel(const eco_mpnn_t w, uint32_t* __restrict__ out) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
