@@ -127,10 +127,10 @@ static int prepare(const eco_graphs_t* g, cudaStream_t st, int first = 0, int co
 }
 
 static int pick_impl(const eco_graphs_t* g, const eco_mpnn_t* w, int impl) {
-    // tensor cores: the resident kernel for N <= 208, the panel-streaming aggregation + CUDA-core linears above
+    // tensor cores: the resident kernel for N <= 208, the operand-tile pipeline (mpnn_large.cu) above
     if (impl == ECO_MPNN_AUTO) {
         if (w->packed && mpnn_tc_supported(g)) return ECO_MPNN_TCGEN05;
-        if (g->N > 208 && mpnn_tcl_supported(g)) return ECO_MPNN_TCGEN05;
+        if (w->packed && g->N > 208 && mpnn_tcl_supported(g)) return ECO_MPNN_TCGEN05;
         return ECO_MPNN_SIMT;
     }
     return impl;
@@ -338,6 +338,7 @@ int eco_mpnn_forward(const eco_graphs_t* g, const eco_mpnn_t* w, int32_t B, cons
     if (rc) return rc;
     const int use = pick_impl(g, w, impl);
     if (use == ECO_MPNN_TCGEN05 && g->N > 208) {
+        ECO_CHECK_ARG(w->packed, ECO_ERR_INVALID, "eco_mpnn_forward: tcgen05 path needs eco_mpnn_pack() output");
         ECO_CHECK_ARG(mpnn_tcl_supported(g), ECO_ERR_UNSUPPORTED,
                       "eco_mpnn_forward: the tensor-core paths need couplings in {-1,0,1}; use ECO_MPNN_SIMT");
         return launch_mpnn_tcl(g, w, B, gidx, xn, xg, norm_max, q, actions, scratch, (cudaStream_t)stream);

@@ -94,7 +94,6 @@ int launch_mpnn_pack(const eco_mpnn_t* w, void* packed, cudaStream_t st);
 bool mpnn_tc_supported(const eco_graphs_t* g);
 bool mpnn_tcl_supported(const eco_graphs_t* g);
 size_t mpnn_tcl_scratch_bytes(int B, int N);
-int launch_tcl_linear(const eco_graphs_t* g, const eco_mpnn_t* w, int B, float* buf, int layer, cudaStream_t st);
 int launch_mpnn_tcl(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int32_t* gidx, const float* xn,
                     const float* xg, float norm_max, float* q, int32_t* actions, void* scratch, cudaStream_t st);
 int launch_tcl_contract(const eco_graphs_t* g, const int32_t* gidx, int B, const float* X1, int which1, const float* X2,

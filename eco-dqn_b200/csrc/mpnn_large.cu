@@ -1,0 +1,504 @@
+// Kernel family 2d: MPNN forward for graphs that do not fit the resident kernel (208 < N <= 2048, couplings in {-1,0,1}).
+//
+// Replaces (reference, file:line)  src/networks/mpnn.py:38-74 MPNN.forward with its three layer types
+//   :89-104  EdgeAndNodeEmbeddingLayer,  :114-120 UpdateNodeEmbeddingLayer,  :143-159 ReadoutLayer
+// and the argmax of src/agents/dqn/dqn.py:499 (ties -> lowest index), for one observation batch.
+//
+// Everything between the kernels lives in HBM in ONE format ("operand tiles"), which is what the tensor cores eat:
+// a plane holds a [64 features][NP vertices] activation as bf16 hi/lo pairs, 64 vertices per 16 KB tile; inside a tile
+// the 128 stacked rows (r = 32q + 16s + t  <->  feature 16q + t, split s = hi / lo; same order as mpnn_tc.cu) x 64
+// vertices are stored as 8x8 core matrices, core(rb, cb) at (cb*16 + rb)*128 bytes.  A tile is at once
+//   * a K-major A operand  (M = stacked rows, K = vertices)       for the N x N products   X * IMG, and
+//   * an MN-major B operand (K = stacked rows, N = vertices)      for the per-vertex linears W * X,
+// so every kernel moves tiles with bulk copies (no conversion, no staging) and writes tiles from its epilogue.
+// Per episode six planes: 0 H0, 1 H1 (ping / pong), 2 E, 3 AGG, 4 S, 5 D.
+//
+//   tcl_init_kernel      H0 = ReLU(W_init x);  S = R+ + R-, D = R+ - R-,  R+- = ReLU(W_x x +- w0)           CUDA cores
+//   tcl_contract_kernel  AGG = scale / deg * (X1 IMG1 (+ X2 IMG2))   (edge stage: 1/2 (S |A| + D A), feature 63)  tcgen05
+//   tcl_linear_kernel    E = ReLU(W_ef AGG)   |   m = ReLU(W_m [AGG ; E]),  H' = ReLU(W_u [H ; m])                 tcgen05
+//   tcl_readout_kernel   pooled readout, Q, argmax                                                            CUDA cores
+#include <cuda_bf16.h>
+
+#include "eco_common.cuh"
+#include "tc_prims.cuh"
+#include "mpnn_pack.cuh"
+
+namespace eco {
+namespace {
+
+using namespace tc;
+
+constexpr int TILE_V = 64;                        // vertices per operand tile
+constexpr int TILE_BYTES = 128 * TILE_V * 2;      // 16 KB
+constexpr int PLANES = 6;
+constexpr int PL_H0 = 0, PL_H1 = 1, PL_E = 2, PL_AGG = 3, PL_S = 4, PL_D = 5;
+
+__host__ __device__ inline size_t plane_bytes(int NP) { return (size_t)((NP + TILE_V - 1) / TILE_V) * TILE_BYTES; }
+
+// stacked hi row of feature f (the lo row is 16 rows = 2 core rows = 256 bytes further)
+__device__ __forceinline__ int hi_row(int f) { return 32 * (f >> 4) + (f & 15); }
+
+// ------------------------------------------------------------------------------------------------ initial embeddings
+// One thread per (8 vertices, feature): mpnn.py:55 (H0) and the per-vertex half of the factorised edge stage (:89-100).
+__global__ void __launch_bounds__(256)
+tcl_init_kernel(const eco_graphs_t g, const eco_mpnn_t w, const float* __restrict__ xn, const float* __restrict__ xg,
+                unsigned char* __restrict__ buf) {
+    const int N = g.N, NP = g.NP, NB = NP >> 3;
+    const int b = blockIdx.y, f = threadIdx.x & 63;
+    const size_t PB = plane_bytes(NP);
+    unsigned char* eb = buf + (size_t)b * PLANES * PB;
+    float wi[7], we[8];
+#pragma unroll
+    for (int c = 0; c < 7; ++c) wi[c] = w.w_init[f * 7 + c];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) we[c] = f < 63 ? w.w_edge[f * 8 + c] : 0.f;     // feature 63 is deg / deg_max (contraction)
+    const float* x0 = xn + (size_t)b * 3 * NP;
+    const float4 xgl = *reinterpret_cast<const float4*>(xg + (size_t)b * 4);
+    const int r = hi_row(f);
+    for (int cb = blockIdx.x * 4 + (threadIdx.x >> 6); cb < NB; cb += gridDim.x * 4) {
+        float h[8], s[8], d[8];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            const int i = cb * 8 + v;
+            h[v] = s[v] = d[v] = 0.f;                                            // padding vertices stay exactly zero
+            if (i < N) {
+                const float X[7] = {x0[i], x0[NP + i], x0[2 * NP + i], xgl.x, xgl.y, xgl.z, xgl.w};
+                float hh = 0.f, p = 0.f;
+#pragma unroll
+                for (int c = 0; c < 7; ++c) {
+                    hh = fmaf(wi[c], X[c], hh);
+                    p = fmaf(we[1 + c], X[c], p);
+                }
+                const float rp = fmaxf(p + we[0], 0.f), rm = fmaxf(p - we[0], 0.f);
+                h[v] = fmaxf(hh, 0.f);
+                s[v] = rp + rm;
+                d[v] = rp - rm;
+            }
+        }
+        const size_t off = (size_t)(cb >> 3) * TILE_BYTES + (((cb & 7) * 16 + (r >> 3)) * 128) + (r & 7) * 16;
+        auto store8 = [&](int plane, const float (&v)[8]) {
+            uint4 hi, lo;
+            split2(v[0], v[1], hi.x, lo.x);
+            split2(v[2], v[3], hi.y, lo.y);
+            split2(v[4], v[5], hi.z, lo.z);
+            split2(v[6], v[7], hi.w, lo.w);
+            unsigned char* p = eb + (size_t)plane * PB + off;
+            *reinterpret_cast<uint4*>(p) = hi;
+            *reinterpret_cast<uint4*>(p + 256) = lo;
+        };
+        store8(PL_H0, h);
+        store8(PL_S, s);
+        store8(PL_D, d);
+    }
+}
+
+// Epilogue store of the values of two adjacent vertices (even column first) of one feature row into a tile plane:
+// the lane holds feature 16q + lane/4 + 8 fr and vertices nbase + 2 (lane & 3) + {0, 1}, nbase a multiple of 8.
+__device__ __forceinline__ void store_pair(unsigned char* plane, int nbase, int q, int fr, int lane, float va, float vb) {
+    uint32_t hi, lo;
+    split2(va, vb, hi, lo);
+    unsigned char* p = plane + (size_t)(nbase >> 6) * TILE_BYTES + ((((nbase & 63) >> 3) * 16 + 4 * q + fr) * 128) +
+                       16 * (lane >> 2) + 4 * (lane & 3);
+    *reinterpret_cast<uint32_t*>(p) = hi;
+    *reinterpret_cast<uint32_t*>(p + 256) = lo;
+}
+
+// ------------------------------------------------------------------------------------------------ N x N products
+// One CTA per (episode, 256-column slab); K is walked in 64-vertex panels, PAIRS operand pairs one after the other.
+// Warp 0 (one lane) feeds a two-stage ring with bulk copies (activation tile + the matching panel of the graph's bf16
+// operand image, graph_prepare.cu: tc_ops), warp 1 (one lane) issues tcgen05.mma into 256 TMEM columns, all four warps
+// run the epilogue.  Two CTAs per SM.
+constexpr int CW = 256;
+constexpr int CSTAGES = 2;
+constexpr int CB_BYTES = TILE_V * CW * 2;                 // 32 KB: 64 k x 256 columns
+constexpr int CSTAGE_BYTES = TILE_BYTES + CB_BYTES;
+constexpr int CSMEM = CSTAGES * CSTAGE_BYTES;
+
+template <int PAIRS>
+__global__ void __launch_bounds__(128, 2)
+tcl_contract_kernel(const eco_graphs_t g, const int32_t* __restrict__ graph_idx, unsigned char* __restrict__ buf,
+                    const int src1, const int which1, const int src2, const int which2, const int dst,
+                    const float scale, const int edge, const float norm_max) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t full[CSTAGES], empty[CSTAGES], done;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int N = g.N, NP = g.NP, NB = NP >> 3;
+    const int nslabs = (NP + CW - 1) / CW;
+    const int b = blockIdx.x / nslabs, n0 = (blockIdx.x % nslabs) * CW, w = min(CW, NP - n0);   // NP % 16 == 0, so is w
+    const int gi = graph_idx[b];
+    const size_t PB = plane_bytes(NP);
+    unsigned char* eb = buf + (size_t)b * PLANES * PB;
+    const int npanels = (NP + TILE_V - 1) / TILE_V, units = PAIRS * npanels;
+    const int run = (w >> 3) * 128;                        // bytes of one 8-vertex K group of the image panel
+
+    if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+    if (tid == 0) {
+        for (int s = 0; s < CSTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(&done, 1);
+        fence_mbar_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            for (int u = 0; u < units; ++u) {
+                const int s = u % CSTAGES, p = u / npanels, kp = u % npanels;
+                const int k0 = kp * TILE_V, kg = min(TILE_V, NP - k0) >> 3;
+                if (u >= CSTAGES) mbar_wait(&empty[s], (uint32_t)((u / CSTAGES - 1) & 1));
+                unsigned char* sa = smem + s * CSTAGE_BYTES;
+                unsigned char* sb = sa + TILE_BYTES;
+                const uint16_t* img = g.tc_ops + ((size_t)gi * 2 + (p ? which2 : which1)) * NP * NP;
+                mbar_expect_tx(&full[s], (uint32_t)(kg * (2048 + run)));
+                bulk_g2s(sa, eb + (size_t)(p ? src2 : src1) * PB + (size_t)kp * TILE_BYTES, kg * 2048, &full[s]);
+                for (int cb = 0; cb < kg; ++cb)
+                    bulk_g2s(sb + cb * run, img + ((size_t)((k0 >> 3) + cb) * NB + (n0 >> 3)) * 64, run, &full[s]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (elect_one()) {
+            const uint32_t idesc = instr_desc_bf16(128, w, false, false);
+            for (int u = 0; u < units; ++u) {
+                const int s = u % CSTAGES, kp = u % npanels;
+                const int kw = min(TILE_V, NP - kp * TILE_V);
+                mbar_wait(&full[s], (uint32_t)((u / CSTAGES) & 1));
+                tc_fence_after();
+                const uint64_t ad = smem_desc(smem_u32(smem + s * CSTAGE_BYTES), 2048, 128);
+                const uint64_t bd = smem_desc(smem_u32(smem + s * CSTAGE_BYTES + TILE_BYTES), run, 128);
+                for (int ks = 0; ks < (kw >> 4); ++ks)
+                    mma_ss(tmem, ad + (uint64_t)ks * (4096 >> 4), bd + (uint64_t)ks * ((2 * run) >> 4), idesc, u > 0 || ks > 0);
+                mma_commit(&empty[s]);
+            }
+            mma_commit(&done);
+        }
+        __syncwarp();
+    }
+    mbar_wait(&done, 0);
+    tc_fence_after();
+
+    // epilogue: hi + lo rows, scale, 1 / deg; feature 63 of the edge stage = deg / deg_max (mpnn.py:102)
+    const float dmax = norm_max > 0.f ? norm_max : (norm_max < 0.f ? (float)max(g.gstat[(size_t)gi * 4], 1) : *g.dmax);
+    unsigned char* ob = eb + (size_t)dst * PB;
+    const float* deg = g.deg + (size_t)gi * NP;
+    for (int blk = 0; blk < (w >> 4); ++blk) {
+        uint32_t vh[8], vl[8];
+        tmem_ld_16x256b_x2(tmem_addr(tmem, 32 * warp, 16 * blk), vh);
+        tmem_ld_16x256b_x2(tmem_addr(tmem, 32 * warp + 16, 16 * blk), vl);
+        tmem_ld_wait();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int nbase = n0 + 16 * blk + 8 * half, n = nbase + 2 * (lane & 3);
+            const float da = n < N ? deg[n] : 1.f, db = n + 1 < N ? deg[n + 1] : 1.f;
+#pragma unroll
+            for (int fr = 0; fr < 2; ++fr) {
+                const int i = 4 * half + 2 * fr, ff = 16 * warp + (lane >> 2) + 8 * fr;
+                float va = (__uint_as_float(vh[i]) + __uint_as_float(vl[i])) * scale / da;
+                float vb = (__uint_as_float(vh[i + 1]) + __uint_as_float(vl[i + 1])) * scale / db;
+                if (edge && ff == 63) { va = da / dmax; vb = db / dmax; }
+                store_pair(ob, nbase, warp, fr, lane, n < N ? va : 0.f, n + 1 < N ? vb : 0.f);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+// ------------------------------------------------------------------------------------------------ per-vertex linears
+// Persistent CTAs (two per SM) over (episode, 64-vertex tile) items: the weights sit in TMEM as A operands for the whole
+// launch (packed bf16 hi/lo rows, eco_mpnn_pack), the item's tiles arrive by bulk copies one item ahead, the message m
+// goes back to shared memory as the next B operand (over the AGG tile), H' / E leave as tiles.
+constexpr uint32_t TL_WA = 0, TL_WB = 64, TL_ACCM = 128, TL_ACCH = 192;
+constexpr int LSMEM = 2 * 3 * TILE_BYTES;
+
+// 8 MMAs: acc (+)= W[:, 64-feature group at TMEM column tw] * X, X a tile used as MN-major B operand
+__device__ __forceinline__ void issue_linear_half(uint32_t tmem, uint32_t acc_col, uint32_t tw, const unsigned char* x, int width,
+                                                  bool accumulate) {
+    const uint32_t idesc = instr_desc_bf16(128, width, false, true);
+    const uint64_t d = smem_desc(smem_u32(x), /*LBO (k groups)*/ 128, /*SBO (vertex groups)*/ 2048);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)     // i = 2*kq + s: features 16kq..16kq+15, split s
+        mma_ts(tmem + acc_col, tmem + tw + 8 * (i >> 1), d + (uint64_t)(16 * i), idesc, accumulate || i > 0);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128, 2)
+tcl_linear_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, unsigned char* __restrict__ buf, const int layer) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t full[2], bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int NP = g.NP;
+    const size_t PB = plane_bytes(NP);
+    const int ntiles = (NP + TILE_V - 1) / TILE_V, nitems = B * ntiles;
+    const uint32_t* pk = reinterpret_cast<const uint32_t*>(w.packed);
+    constexpr int NIN = MODE == 0 ? 1 : 3;
+    const int in_plane[3] = {PL_AGG, PL_E, (layer & 1) ? PL_H1 : PL_H0};
+    const int out_plane = MODE == 0 ? PL_E : ((layer & 1) ? PL_H0 : PL_H1);
+
+    if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+    if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_init(&bar, 1); fence_mbar_init(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+
+    auto fetch = [&](int item, int s) {                   // one thread: the item's tiles -> stage s
+        const int b = item / ntiles, t = item % ntiles;
+        const uint32_t bytes = (uint32_t)(min(TILE_V, NP - t * TILE_V) >> 3) * 2048;
+        mbar_expect_tx(&full[s], NIN * bytes);
+        for (int p = 0; p < NIN; ++p)
+            bulk_g2s(smem + (s * 3 + p) * TILE_BYTES, buf + ((size_t)b * PLANES + in_plane[p]) * PB + (size_t)t * TILE_BYTES,
+                     bytes, &full[s]);
+    };
+    if (tid == 0 && (int)blockIdx.x < nitems) fetch(blockIdx.x, 0);
+    {   // this layer's weights: packed global -> registers -> TMEM (warp q owns lane quadrant q)
+        auto load = [&](const uint32_t* m, int kw, uint32_t tcol) {
+            const uint4* src = reinterpret_cast<const uint4*>(m) + (size_t)(warp * (kw / 8) * 2) * 32 + lane;
+            for (int cg = 0; cg < kw / 8; ++cg) {
+                const uint4 x = __ldg(src + (2 * cg) * 32), y = __ldg(src + (2 * cg + 1) * 32);
+                const uint32_t v[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+                tmem_st_32x32b_x8(tmem_addr(tmem, 32 * warp, tcol + cg * 8), v);
+            }
+        };
+        if (MODE == 0) load(pk + PK_WEF, 32, TL_WA);
+        else { load(pk + PK_WM + layer * 128 * 64, 64, TL_WA); load(pk + PK_WU + layer * 128 * 64, 64, TL_WB); }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncthreads();
+    }
+    uint32_t phase = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+        const int s = it & 1;
+        const int b = item / ntiles, n0 = (item % ntiles) * TILE_V, wdt = min(TILE_V, NP - n0);
+        unsigned char* sAgg = smem + (s * 3 + 0) * TILE_BYTES;
+        unsigned char* sE = smem + (s * 3 + 1) * TILE_BYTES;
+        unsigned char* sH = smem + (s * 3 + 2) * TILE_BYTES;
+        if (warp == 0) {
+            if (elect_one()) {
+                if (item + (int)gridDim.x < nitems) fetch(item + gridDim.x, s ^ 1);   // the other stage is idle since the last item
+                mbar_wait(&full[s], (uint32_t)((it >> 1) & 1));
+                tc_fence_after();
+                if (MODE == 0) {
+                    issue_linear_half(tmem, TL_ACCM, TL_WA, sAgg, wdt, false);
+                } else {
+                    issue_linear_half(tmem, TL_ACCM, TL_WA + 32, sE, wdt, false);       // W_m[:, 64:] e
+                    issue_linear_half(tmem, TL_ACCM, TL_WA, sAgg, wdt, true);           // += W_m[:, :64] agg
+                }
+                mma_commit(&bar);
+                if (MODE == 1) issue_linear_half(tmem, TL_ACCH, TL_WB, sH, wdt, false);  // W_u[:, :64] h, ahead
+            }
+            __syncwarp();
+        }
+        mbar_wait(&bar, phase); phase ^= 1u;
+        tc_fence_after();
+        unsigned char* ob = buf + ((size_t)b * PLANES + out_plane) * PB;
+        // epilogue 1: ReLU; MODE 0 -> E tile (global); MODE 1 -> m as the next B operand (over the AGG tile)
+        for (int blk = 0; blk < (wdt >> 4); ++blk) {
+            uint32_t vh[8], vl[8];
+            tmem_ld_16x256b_x2(tmem_addr(tmem, 32 * warp, TL_ACCM + 16 * blk), vh);
+            tmem_ld_16x256b_x2(tmem_addr(tmem, 32 * warp + 16, TL_ACCM + 16 * blk), vl);
+            tmem_ld_wait();
+#pragma unroll
+            for (int half = 0; half < 2; ++half)
+#pragma unroll
+                for (int fr = 0; fr < 2; ++fr) {
+                    const int i = 4 * half + 2 * fr;
+                    const float va = fmaxf(__uint_as_float(vh[i]) + __uint_as_float(vl[i]), 0.f);
+                    const float vb = fmaxf(__uint_as_float(vh[i + 1]) + __uint_as_float(vl[i + 1]), 0.f);
+                    if (MODE == 0) store_pair(ob, n0 + 16 * blk + 8 * half, warp, fr, lane, va, vb);
+                    else store_pair(sAgg, 16 * blk + 8 * half, warp, fr, lane, va, vb);
+                }
+        }
+        if (MODE == 1) {
+            fence_proxy_async();
+            tc_fence_before();
+            __syncthreads();
+            if (warp == 0) {
+                tc_fence_after();
+                if (elect_one()) {
+                    issue_linear_half(tmem, TL_ACCH, TL_WB + 32, sAgg, wdt, true);       // += W_u[:, 64:] m
+                    mma_commit(&bar);
+                }
+                __syncwarp();
+            }
+            mbar_wait(&bar, phase); phase ^= 1u;
+            tc_fence_after();
+            for (int blk = 0; blk < (wdt >> 4); ++blk) {           // epilogue 2: H' = ReLU(.) tile
+                uint32_t vh[8], vl[8];
+                tmem_ld_16x256b_x2(tmem_addr(tmem, 32 * warp, TL_ACCH + 16 * blk), vh);
+                tmem_ld_16x256b_x2(tmem_addr(tmem, 32 * warp + 16, TL_ACCH + 16 * blk), vl);
+                tmem_ld_wait();
+#pragma unroll
+                for (int half = 0; half < 2; ++half)
+#pragma unroll
+                    for (int fr = 0; fr < 2; ++fr) {
+                        const int i = 4 * half + 2 * fr;
+                        const float va = fmaxf(__uint_as_float(vh[i]) + __uint_as_float(vl[i]), 0.f);
+                        const float vb = fmaxf(__uint_as_float(vh[i + 1]) + __uint_as_float(vl[i + 1]), 0.f);
+                        store_pair(ob, n0 + 16 * blk + 8 * half, warp, fr, lane, va, vb);
+                    }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();              // this stage and the accumulators are reused
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+// ------------------------------------------------------------------------------------------------ readout
+// One CTA per episode: mpnn.py:143-159 on the H plane, then argmax (ties -> lowest index).  Warps walk 8-vertex groups,
+// lanes own features lane and lane + 32.
+constexpr int RD_WARPS = 8;
+constexpr int RD_NMAX = 2048;
+
+__device__ __forceinline__ float bf16lo(uint32_t x) { return __uint_as_float(x << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t x) { return __uint_as_float(x & 0xffff0000u); }
+
+__global__ void __launch_bounds__(RD_WARPS * 32)
+tcl_readout_kernel(const eco_graphs_t g, const eco_mpnn_t w, const unsigned char* __restrict__ buf, const int plane,
+                   float* __restrict__ q_out, int32_t* __restrict__ act_out) {
+    __shared__ float qpart[RD_NMAX];
+    __shared__ float part[RD_WARPS][64];
+    __shared__ float pooled[64];
+    __shared__ float c0_s;
+    __shared__ float red_val[RD_WARPS];
+    __shared__ int red_idx[RD_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = g.N, NP = g.NP, NB = NP >> 3, b = blockIdx.x;
+    const size_t PB = plane_bytes(NP);
+    const unsigned char* Hp = buf + ((size_t)b * PLANES + plane) * PB;
+    const int r0 = hi_row(lane);                           // feature lane; feature lane + 32 is 64 rows = 8 core rows further
+    const float wr0 = w.w_read[64 + lane], wr1 = w.w_read[96 + lane];
+    float sum0 = 0.f, sum1 = 0.f;
+    for (int cb = warp; cb < NB; cb += RD_WARPS) {
+        const unsigned char* p = Hp + (size_t)(cb >> 3) * TILE_BYTES + (((cb & 7) * 16 + (r0 >> 3)) * 128) + (r0 & 7) * 16;
+        const uint4 h0 = *reinterpret_cast<const uint4*>(p), l0 = *reinterpret_cast<const uint4*>(p + 256);
+        const uint4 h1 = *reinterpret_cast<const uint4*>(p + 1024), l1 = *reinterpret_cast<const uint4*>(p + 1280);
+        const uint32_t H0[4] = {h0.x, h0.y, h0.z, h0.w}, L0[4] = {l0.x, l0.y, l0.z, l0.w};
+        const uint32_t H1[4] = {h1.x, h1.y, h1.z, h1.w}, L1[4] = {l1.x, l1.y, l1.z, l1.w};
+        float qv[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float a0 = bf16lo(H0[k]) + bf16lo(L0[k]), a1 = bf16hi(H0[k]) + bf16hi(L0[k]);
+            const float c0 = bf16lo(H1[k]) + bf16lo(L1[k]), c1 = bf16hi(H1[k]) + bf16hi(L1[k]);
+            sum0 += a0 + a1;
+            sum1 += c0 + c1;
+            qv[2 * k] = fmaf(wr0, fmaxf(a0, 0.f), wr1 * fmaxf(c0, 0.f));
+            qv[2 * k + 1] = fmaf(wr0, fmaxf(a1, 0.f), wr1 * fmaxf(c1, 0.f));
+        }
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) qv[v] += __shfl_xor_sync(0xffffffffu, qv[v], o);
+        }
+        if (lane < 8) {
+            float x = qv[0];
+#pragma unroll
+            for (int v = 1; v < 8; ++v) x = lane == v ? qv[v] : x;
+            qpart[cb * 8 + lane] = x;
+        }
+    }
+    part[warp][lane] = sum0;
+    part[warp][lane + 32] = sum1;
+    __syncthreads();
+    if (tid < 64) {
+        float s = 0.f;
+        for (int ww = 0; ww < RD_WARPS; ++ww) s += part[ww][tid];
+        pooled[tid] = s / (float)N;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        float c = 0.f;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int f = lane + 32 * half;
+            float p = 0.f;
+            for (int k = 0; k < 64; ++k) p = fmaf(w.w_pool[f * 64 + k], pooled[k], p);
+            c = fmaf(w.w_read[f], fmaxf(p, 0.f), c);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0) c0_s = c + w.b_read[0];
+    }
+    __syncthreads();
+    const float c0 = c0_s;
+    float best_v = -INFINITY;
+    int best_i = 0x7fffffff;
+    for (int i = tid; i < N; i += RD_WARPS * 32) {
+        const float v = qpart[i] + c0;
+        if (q_out) q_out[(size_t)b * NP + i] = v;
+        if (v > best_v) { best_v = v; best_i = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best_v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+        if (ov > best_v || (ov == best_v && oi < best_i)) { best_v = ov; best_i = oi; }
+    }
+    if (lane == 0) { red_val[warp] = best_v; red_idx[warp] = best_i; }
+    __syncthreads();
+    if (tid == 0 && act_out) {
+        float bv = red_val[0];
+        int bi = red_idx[0];
+        for (int ww = 1; ww < RD_WARPS; ++ww)
+            if (red_val[ww] > bv || (red_val[ww] == bv && red_idx[ww] < bi)) { bv = red_val[ww]; bi = red_idx[ww]; }
+        act_out[b] = bi;
+    }
+}
+
+}  // namespace
+
+// scratch: B episodes x 6 planes of operand tiles
+size_t mpnn_tcl_scratch_bytes(int B, int N) { return align256((size_t)B * PLANES * plane_bytes(padded_n(N))); }
+
+int launch_mpnn_tcl(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int32_t* gidx, const float* xn,
+                    const float* xg, float norm_max, float* q, int32_t* actions, void* scratch, cudaStream_t st) {
+    static bool attr = false;
+    static int n_sm = 148;
+    if (!attr) {
+        ECO_CUDA(cudaFuncSetAttribute(tcl_contract_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CSMEM));
+        ECO_CUDA(cudaFuncSetAttribute(tcl_contract_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CSMEM));
+        ECO_CUDA(cudaFuncSetAttribute(tcl_linear_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, LSMEM));
+        ECO_CUDA(cudaFuncSetAttribute(tcl_linear_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, LSMEM));
+        int dev = 0;
+        ECO_CUDA(cudaGetDevice(&dev));
+        ECO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        attr = true;
+    }
+    unsigned char* buf = (unsigned char*)scratch;
+    const int NP = g->NP, NB = NP >> 3;
+    const int ntiles = (NP + TILE_V - 1) / TILE_V, nslabs = (NP + CW - 1) / CW;
+    const long long items = (long long)B * ntiles;
+    const int lgrid = (int)(items < 2LL * n_sm ? items : 2LL * n_sm);
+    const unsigned cgrid = (unsigned)((size_t)B * nslabs);
+    prof_begin(ECO_PROF_MPNN, st);
+    tcl_init_kernel<<<dim3((NB + 3) / 4, B), 256, 0, st>>>(*g, *w, xn, xg, buf);
+    ECO_LAUNCH_CHECK();
+    // g = (S |A| + D A) / (2 deg), feature 63 = deg / deg_max
+    tcl_contract_kernel<2><<<cgrid, 128, CSMEM, st>>>(*g, gidx, buf, PL_S, 1, PL_D, 0, PL_AGG, 0.5f, 1, norm_max);
+    ECO_LAUNCH_CHECK();
+    tcl_linear_kernel<0><<<lgrid, 128, LSMEM, st>>>(*g, *w, B, buf, 0);
+    ECO_LAUNCH_CHECK();
+    for (int l = 0; l < 3; ++l) {
+        tcl_contract_kernel<1><<<cgrid, 128, CSMEM, st>>>(*g, gidx, buf, (l & 1) ? PL_H1 : PL_H0, 0, 0, 0, PL_AGG, 1.f, 0, norm_max);
+        ECO_LAUNCH_CHECK();
+        tcl_linear_kernel<1><<<lgrid, 128, LSMEM, st>>>(*g, *w, B, buf, l);
+        ECO_LAUNCH_CHECK();
+    }
+    tcl_readout_kernel<<<B, RD_WARPS * 32, 0, st>>>(*g, *w, buf, PL_H1, q, actions);
+    ECO_LAUNCH_CHECK();
+    prof_end(ECO_PROF_MPNN, st);
+    return ECO_OK;
+}
+
+}  // namespace eco

@@ -14,7 +14,6 @@
 // global scratch (L2 resident); neighbour aggregation scans the int8 adjacency row 16 bytes per lane and
 // visits only non-zeros; the 64x64 / 64x128 linears run on 8-vertex tiles per warp (16 accumulators per lane,
 // weights transposed in shared memory, inputs broadcast from shared memory).
-#include <cstdlib>
 #include "eco_common.cuh"
 
 namespace eco {
@@ -373,182 +372,6 @@ mpnn_simt_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const in
     }
 }
 
-// ------------------------------------------------------------------------------------------------ phase mode
-// The per-vertex parts of the forward, one launch per phase, for the large-graph path (mpnn_tcl.cu) whose N x N products
-// run on the tensor cores between the phases.  Per episode six [NP][64] fp32 buffers (stride 6 NP 64 floats):
-//   0 H0, 1 H1 (ping / pong), 2 E, 3 AGG (written by the contraction: g, then agg of each layer), 4 S, 5 D.
-//   phase 0: H0 = ReLU(W_init x);  S = R+ + R-, D = R+ - R-,  R+- = ReLU(P +- w0), P = W_x x   (mpnn.py:55, 89-100)
-//   phase 1: E = ReLU(W_ef AGG)                                                                (mpnn.py:100-104)
-//   phase 2 + l: m = ReLU(W_m [AGG ; E]); H' = ReLU(W_u [H ; m])                               (mpnn.py:114-120)
-//   phase 5: readout + argmax from H1                                                          (mpnn.py:143-159)
-__global__ void __launch_bounds__(WARPS * 32, 2)
-mpnn_phase_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const float* __restrict__ xn,
-                  const float* __restrict__ xg, float* __restrict__ q_out, int32_t* __restrict__ act_out,
-                  const float* __restrict__ wt, float* __restrict__ buf, const int phase) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem& S = *reinterpret_cast<Smem*>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int N = g.N, NP = g.NP;
-    float* xs = S.xs[warp];
-    const int ntiles = (N + TILE - 1) / TILE;
-    const size_t estride = (size_t)6 * NP * F;
-
-    if (phase == 0) {
-        for (int i = tid; i < 64 * 7; i += blockDim.x) S.w_init[i] = w.w_init[i];
-        for (int i = tid; i < 64 * 8; i += blockDim.x) S.w_edge[i] = i < 63 * 8 ? w.w_edge[i] : 0.f;
-    } else if (phase == 1) {
-        for (int i = tid; i < 64 * F; i += blockDim.x) S.wa[i] = wt[OFF_WEF + i];
-    } else if (phase < 5) {
-        const int l = phase - 2;
-        for (int i = tid; i < 128 * F; i += blockDim.x) {
-            S.wa[i] = wt[OFF_WMSG + l * 128 * F + i];
-            S.wb[i] = wt[OFF_WUPD + l * 128 * F + i];
-        }
-    } else {
-        for (int i = tid; i < 128; i += blockDim.x) S.w_read[i] = w.w_read[i];
-    }
-    __syncthreads();
-
-    for (int b = blockIdx.x; b < B; b += gridDim.x) {
-        float* H0 = buf + (size_t)b * estride;
-        float* H1 = H0 + (size_t)NP * F;
-        float* E = H0 + (size_t)2 * NP * F;
-        float* AGG = H0 + (size_t)3 * NP * F;
-        float* Sx = H0 + (size_t)4 * NP * F;
-        float* Dx = H0 + (size_t)5 * NP * F;
-        if (phase == 0) {
-            const float* x0 = xn + (size_t)b * 3 * NP;
-            const float4 xgl = *reinterpret_cast<const float4*>(xg + (size_t)b * 4);
-            for (int i = warp; i < N; i += WARPS) {
-                const float X[7] = {x0[i], x0[NP + i], x0[2 * NP + i], xgl.x, xgl.y, xgl.z, xgl.w};
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const int f = lane + 32 * half;
-                    float h = 0.f, p = 0.f;
-#pragma unroll
-                    for (int c = 0; c < 7; ++c) {
-                        h = fmaf(S.w_init[f * 7 + c], X[c], h);
-                        p = fmaf(S.w_edge[f * 8 + 1 + c], X[c], p);
-                    }
-                    const float w0 = S.w_edge[f * 8];
-                    const float rp = fmaxf(p + w0, 0.f), rm = fmaxf(p - w0, 0.f);
-                    H0[(size_t)i * F + f] = fmaxf(h, 0.f);
-                    Sx[(size_t)i * F + f] = rp + rm;
-                    Dx[(size_t)i * F + f] = rp - rm;
-                }
-            }
-        } else if (phase == 1) {
-            for (int t = warp; t < ntiles; t += WARPS) {
-                for (int n = 0; n < TILE; ++n) {
-                    const int i = t * TILE + n;
-                    xs[lane * TILE + n] = i < N ? AGG[(size_t)i * F + lane] : 0.f;
-                    xs[(lane + 32) * TILE + n] = i < N ? AGG[(size_t)i * F + lane + 32] : 0.f;
-                }
-                __syncwarp();
-                float acc[16];
-                tile_linear(S.wa, xs, 64, lane, acc);
-                __syncwarp();
-                for (int n = 0; n < TILE; ++n) {
-                    const int i = t * TILE + n;
-                    if (i < N) {
-                        E[(size_t)i * F + lane] = fmaxf(acc[n], 0.f);
-                        E[(size_t)i * F + lane + 32] = fmaxf(acc[8 + n], 0.f);
-                    }
-                }
-            }
-        } else if (phase < 5) {
-            const int l = phase - 2;
-            const float* Hc = (l & 1) ? H1 : H0;
-            float* Hn = (l & 1) ? H0 : H1;
-            for (int t = warp; t < ntiles; t += WARPS) {
-                for (int n = 0; n < TILE; ++n) {
-                    const int i = t * TILE + n;
-                    const bool ok = i < N;
-                    xs[lane * TILE + n] = ok ? AGG[(size_t)i * F + lane] : 0.f;
-                    xs[(lane + 32) * TILE + n] = ok ? AGG[(size_t)i * F + lane + 32] : 0.f;
-                    xs[(64 + lane) * TILE + n] = ok ? E[(size_t)i * F + lane] : 0.f;
-                    xs[(96 + lane) * TILE + n] = ok ? E[(size_t)i * F + lane + 32] : 0.f;
-                }
-                __syncwarp();
-                float acc[16];
-                tile_linear(S.wa, xs, 128, lane, acc);          // message = ReLU(W_m [agg ; e])
-                __syncwarp();
-                for (int n = 0; n < TILE; ++n) {
-                    const int i = t * TILE + n;
-                    const bool ok = i < N;
-                    xs[lane * TILE + n] = ok ? Hc[(size_t)i * F + lane] : 0.f;
-                    xs[(lane + 32) * TILE + n] = ok ? Hc[(size_t)i * F + lane + 32] : 0.f;
-                    xs[(64 + lane) * TILE + n] = fmaxf(acc[n], 0.f);
-                    xs[(96 + lane) * TILE + n] = fmaxf(acc[8 + n], 0.f);
-                }
-                __syncwarp();
-                tile_linear(S.wb, xs, 128, lane, acc);          // h' = ReLU(W_u [h ; message])
-                __syncwarp();
-                for (int n = 0; n < TILE; ++n) {
-                    const int i = t * TILE + n;
-                    if (i < N) {
-                        Hn[(size_t)i * F + lane] = fmaxf(acc[n], 0.f);
-                        Hn[(size_t)i * F + lane + 32] = fmaxf(acc[8 + n], 0.f);
-                    }
-                }
-            }
-        } else {
-            const float* Hc = H1;                                 // after three layers
-            {
-                float sa = 0.f, sb = 0.f;
-                for (int i = warp; i < N; i += WARPS) {
-                    sa += Hc[(size_t)i * F + lane];
-                    sb += Hc[(size_t)i * F + lane + 32];
-                }
-                S.part[warp][lane] = sa;
-                S.part[warp][lane + 32] = sb;
-            }
-            __syncthreads();
-            if (tid < F) {
-                float s = 0.f;
-                for (int ww = 0; ww < WARPS; ++ww) s += S.part[ww][tid];
-                S.pooled[tid] = s / (float)N;
-            }
-            __syncthreads();
-            if (warp == 0) {
-                float c = 0.f;
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const int f = lane + 32 * half;
-                    float p = 0.f;
-                    for (int k = 0; k < F; ++k) p = fmaf(w.w_pool[f * F + k], S.pooled[k], p);
-                    c = fmaf(S.w_read[f], fmaxf(p, 0.f), c);
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-                if (lane == 0) S.c0 = c + w.b_read[0];
-            }
-            __syncthreads();
-            float best_v = -INFINITY;
-            int best_i = 0x7fffffff;
-            for (int i = warp; i < N; i += WARPS) {
-                float v = fmaf(S.w_read[64 + lane], fmaxf(Hc[(size_t)i * F + lane], 0.f),
-                               S.w_read[96 + lane] * fmaxf(Hc[(size_t)i * F + lane + 32], 0.f));
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                v += S.c0;
-                if (lane == 0 && q_out) q_out[(size_t)b * NP + i] = v;
-                if (v > best_v) { best_v = v; best_i = i; }
-            }
-            if (lane == 0) { S.red_val[warp] = best_v; S.red_idx[warp] = best_i; }
-            __syncthreads();
-            if (tid == 0 && act_out) {
-                float bv = S.red_val[0];
-                int bi = S.red_idx[0];
-                for (int ww = 1; ww < WARPS; ++ww)
-                    if (S.red_val[ww] > bv || (S.red_val[ww] == bv && S.red_idx[ww] < bi)) { bv = S.red_val[ww]; bi = S.red_idx[ww]; }
-                act_out[b] = bi;
-            }
-            __syncthreads();
-        }
-    }
-}
-
 int simt_grid(int B) {
     const int max_ctas = 148 * 2;
     return B < max_ctas ? B : max_ctas;
@@ -577,52 +400,6 @@ int launch_mpnn_simt(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const in
                                                                     actions, (float*)scratch);
     prof_end(ECO_PROF_MPNN, st);
     ECO_LAUNCH_CHECK();
-    return ECO_OK;
-}
-
-// Large graphs (N > 208, couplings in {-1,0,1}): per-vertex phases on the CUDA cores, the five N x N products on the
-// tensor cores (mpnn_tcl.cu).  scratch: [transposed weights][B x 6 x NP x 64 floats].
-size_t mpnn_tcl_scratch_bytes(int B, int N) {
-    const int NP = padded_n(N);
-    return align256(sizeof(float) * ((size_t)WT_FLOATS + (size_t)B * 6 * NP * F));
-}
-
-int launch_mpnn_tcl(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int32_t* gidx, const float* xn,
-                    const float* xg, float norm_max, float* q, int32_t* actions, void* scratch, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        ECO_CUDA(cudaFuncSetAttribute(mpnn_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-        attr_set = true;
-    }
-    float* wt = (float*)scratch;
-    float* buf = wt + WT_FLOATS;
-    const int NP = g->NP;
-    const size_t es = (size_t)6 * NP * F, bs = (size_t)NP * F;
-    transpose_weights_kernel<<<(128 * 64 + 255) / 256, 256, 0, st>>>(*w, wt);
-    ECO_LAUNCH_CHECK();
-    prof_begin(ECO_PROF_MPNN, st);
-    auto phase = [&](int ph) {
-        mpnn_phase_kernel<<<simt_grid(B), WARPS * 32, sizeof(Smem), st>>>(*g, *w, B, xn, xg, q, actions, wt, buf, ph);
-    };
-    int rc = ECO_OK;
-    phase(0);
-    // g = (|A| S + A D) / (2 deg), feature 63 = deg / deg_max
-    if (!rc) rc = launch_tcl_contract(g, gidx, B, buf + 4 * bs, 1, buf + 5 * bs, 0, es, buf + 3 * bs, es, 0.5f, 1, norm_max, st);
-    // per-vertex linears: tensor cores when the packed bf16 hi/lo weights are there (eco_mpnn_pack), else CUDA cores
-    static const bool cuda_linears = getenv("ECO_TCL_CUDA_LINEARS") != nullptr;
-    const bool tl = w->packed != nullptr && !cuda_linears;
-    if (tl) { if (!rc) rc = launch_tcl_linear(g, w, B, buf, -1, st); }
-    else phase(1);
-    for (int l = 0; l < 3 && !rc; ++l) {
-        rc = launch_tcl_contract(g, gidx, B, buf + ((l & 1) ? bs : 0), 0, nullptr, 0, es, buf + 3 * bs, es, 1.f, 0, norm_max, st);
-        if (tl) { if (!rc) rc = launch_tcl_linear(g, w, B, buf, l, st); }
-        else phase(2 + l);
-    }
-    phase(5);
-    prof_end(ECO_PROF_MPNN, st);
-    if (rc) return rc;
-    ECO_LAUNCH_CHECK();
-    count_launch(5);      // (the six phase launches share one check)
     return ECO_OK;
 }
 
