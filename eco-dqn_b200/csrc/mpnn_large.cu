@@ -122,6 +122,7 @@ tcl_contract_kernel(const eco_graphs_t g, const int32_t* __restrict__ graph_idx,
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t full[CSTAGES], empty[CSTAGES], done;
     __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(8) float s_rdeg[CW], s_dn[CW];
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int N = g.N, NP = g.NP, NB = NP >> 3;
@@ -177,14 +178,24 @@ tcl_contract_kernel(const eco_graphs_t g, const int32_t* __restrict__ graph_idx,
             mma_commit(&done);
         }
         __syncwarp();
+    } else {
+        // warps 2, 3 (idle during the main loop): 1 / deg and deg / deg_max of the slab's vertices; 0 for padding vertices
+        const float dmax = norm_max > 0.f ? norm_max : (norm_max < 0.f ? (float)max(g.gstat[(size_t)gi * 4], 1) : *g.dmax);
+        for (int i = tid - 64; i < w; i += 64) {
+            const bool ok = n0 + i < N;
+            const float d = ok ? g.deg[(size_t)gi * NP + n0 + i] : 1.f;
+            s_rdeg[i] = ok ? scale / d : 0.f;
+            s_dn[i] = ok ? d / dmax : 0.f;
+        }
     }
+    __syncthreads();
     mbar_wait(&done, 0);
     tc_fence_after();
 
-    // epilogue: hi + lo rows, scale, 1 / deg; feature 63 of the edge stage = deg / deg_max (mpnn.py:102)
-    const float dmax = norm_max > 0.f ? norm_max : (norm_max < 0.f ? (float)max(g.gstat[(size_t)gi * 4], 1) : *g.dmax);
+    // epilogue: (hi + lo rows) * scale / deg; feature 63 of the edge stage = deg / deg_max (mpnn.py:102)
     unsigned char* ob = eb + (size_t)dst * PB;
-    const float* deg = g.deg + (size_t)gi * NP;
+    const bool f63 = edge && warp == 3 && (lane >> 2) == 7;      // this lane's fr = 1 row is feature 63
+#pragma unroll 2
     for (int blk = 0; blk < (w >> 4); ++blk) {
         uint32_t vh[8], vl[8];
         tmem_ld_16x256b_x2(tmem_addr(tmem, 32 * warp, 16 * blk), vh);
@@ -192,15 +203,16 @@ tcl_contract_kernel(const eco_graphs_t g, const int32_t* __restrict__ graph_idx,
         tmem_ld_wait();
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-            const int nbase = n0 + 16 * blk + 8 * half, n = nbase + 2 * (lane & 3);
-            const float da = n < N ? deg[n] : 1.f, db = n + 1 < N ? deg[n + 1] : 1.f;
+            const int c = 16 * blk + 8 * half + 2 * (lane & 3);
+            const float2 rd = *reinterpret_cast<const float2*>(&s_rdeg[c]);
+            const float2 dn = *reinterpret_cast<const float2*>(&s_dn[c]);
 #pragma unroll
             for (int fr = 0; fr < 2; ++fr) {
-                const int i = 4 * half + 2 * fr, ff = 16 * warp + (lane >> 2) + 8 * fr;
-                float va = (__uint_as_float(vh[i]) + __uint_as_float(vl[i])) * scale / da;
-                float vb = (__uint_as_float(vh[i + 1]) + __uint_as_float(vl[i + 1])) * scale / db;
-                if (edge && ff == 63) { va = da / dmax; vb = db / dmax; }
-                store_pair(ob, nbase, warp, fr, lane, n < N ? va : 0.f, n + 1 < N ? vb : 0.f);
+                const int i = 4 * half + 2 * fr;
+                float va = (__uint_as_float(vh[i]) + __uint_as_float(vl[i])) * rd.x;
+                float vb = (__uint_as_float(vh[i + 1]) + __uint_as_float(vl[i + 1])) * rd.y;
+                if (fr == 1 && f63) { va = dn.x; vb = dn.y; }
+                store_pair(ob, n0 + 16 * blk + 8 * half, warp, fr, lane, va, vb);
             }
         }
     }
