@@ -58,7 +58,7 @@ extern "C" {
 /* MPNN implementations */
 #define ECO_MPNN_AUTO          0
 #define ECO_MPNN_SIMT          1   /* fp32 CUDA-core kernel: any int8 weights, any N <= ECO_MAX_SPINS      */
-#define ECO_MPNN_TCGEN05       2   /* tcgen05/TMEM tensor-core kernel: weights in {-1,0,1}, N <= 208       */
+#define ECO_MPNN_TCGEN05       2   /* tcgen05/TMEM tensor-core kernels: weights in {-1,0,1}                  */
 
 const char* eco_last_error(void);
 int         eco_abi_version(void);
@@ -193,8 +193,9 @@ size_t eco_mpnn_packed_bytes(void);
 /* pre-split the weights into the bf16 hi/lo operand layout the tcgen05 kernel consumes (device -> device) */
 int    eco_mpnn_pack(const eco_mpnn_t* w, void* packed_dev, void* stream);
 
-/* ECO_MPNN_TCGEN05 / AUTO with couplings in {-1,0,1}: N <= 208 on the tensor cores (graphs with NP <= 96 are processed
- * 192/NP at a time as one block-diagonal graph); larger graphs and other weights run on the CUDA-core kernel.
+/* ECO_MPNN_TCGEN05 / AUTO with couplings in {-1,0,1} run on the tensor cores: N <= 208 in one resident kernel (graphs
+ * with NP <= 96 are processed 192/NP at a time as one block-diagonal graph), larger graphs as a pipeline of kernels
+ * that exchange bf16 operand tiles through scratch_dev; other weights run on the CUDA-core kernel.
  * Q[b, i] for b < B from features xn [B,3,NP] / xg [B,4] and graph_idx [B] (use env->xn etc. for live
  * episodes, or replayed features for training).  norm_max: the batch-wide max degree the reference divides
  * by (mpnn.py:102); 0 means "max degree over the whole graph set", < 0 means "each episode's own graph" (what the

@@ -583,8 +583,8 @@ def test_graph_aggregate_matches_fp64_product(eng, n, p, B, use_abs):
 @pytest.mark.parametrize("n,p,B", [(209, 0.1, 5), (333, 0.08, 4), (500, 0.15, 6), (1100, 0.02, 3), (2000, 0.01, 2)])
 @pytest.mark.parametrize("norm_max", [None, -1.0])
 def test_mpnn_large_graph_tensor_path_vs_oracle_and_simt(eng, n, p, B, norm_max):
-    """N > 208: aggregation on the tensor cores (mpnn_tcl.cu) + CUDA-core linears, against the oracle (Q tolerance) and
-    against the all-CUDA-core kernel."""
+    """N > 208: the operand-tile pipeline (mpnn_large.cu: N x N products and per-vertex linears on the tensor cores),
+    against the oracle (Q tolerance) and against the all-CUDA-core kernel."""
     from oracle.mpnn import mpnn_forward, KEYS
     from eco_dqn_b200 import _lib
     rng = np.random.default_rng(3 * n + B)
