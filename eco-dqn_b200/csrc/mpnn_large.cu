@@ -104,40 +104,38 @@ __device__ __forceinline__ void store_pair(unsigned char* plane, int nbase, int 
 }
 
 // ------------------------------------------------------------------------------------------------ N x N products
-// One CTA per (episode, 256-column slab); K is walked in 64-vertex panels, PAIRS operand pairs one after the other.
-// Warp 0 (one lane) feeds a two-stage ring with bulk copies (activation tile + the matching panel of the graph's bf16
-// operand image, graph_prepare.cu: tc_ops), warp 1 (one lane) issues tcgen05.mma into 256 TMEM columns, all four warps
-// run the epilogue.  Two CTAs per SM.
+// Persistent CTAs (one per SM) over (episode, 256-column slab) items; K is walked in 64-vertex panels, PAIRS operand
+// pairs one after the other.  Warp 0 (one lane) feeds a four-stage ring with bulk copies (activation tile + the matching
+// panel of the graph's bf16 operand image, graph_prepare.cu: tc_ops), warp 1 (one lane) issues tcgen05.mma into one of
+// two 256-column TMEM accumulators, warps 2-5 (one per TMEM lane quadrant) drain the other one: the epilogue of a slab
+// overlaps the main loop of the next.
 constexpr int CW = 256;
-constexpr int CSTAGES = 2;
+constexpr int CSTAGES = 4;
 constexpr int CB_BYTES = TILE_V * CW * 2;                 // 32 KB: 64 k x 256 columns
 constexpr int CSTAGE_BYTES = TILE_BYTES + CB_BYTES;
 constexpr int CSMEM = CSTAGES * CSTAGE_BYTES;
+constexpr int CTHREADS = 192;
 
 template <int PAIRS>
-__global__ void __launch_bounds__(128, 2)
-tcl_contract_kernel(const eco_graphs_t g, const int32_t* __restrict__ graph_idx, unsigned char* __restrict__ buf,
+__global__ void __launch_bounds__(CTHREADS, 1)
+tcl_contract_kernel(const eco_graphs_t g, const int32_t* __restrict__ graph_idx, const int B, unsigned char* __restrict__ buf,
                     const int src1, const int which1, const int src2, const int which2, const int dst,
                     const float scale, const int edge, const float norm_max) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t full[CSTAGES], empty[CSTAGES], done;
+    __shared__ uint64_t full[CSTAGES], empty[CSTAGES], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_s;
-    __shared__ __align__(8) float s_rdeg[CW], s_dn[CW];
+    __shared__ __align__(8) float s_rdeg[2][CW], s_dn[2][CW];
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int N = g.N, NP = g.NP, NB = NP >> 3;
-    const int nslabs = (NP + CW - 1) / CW;
-    const int b = blockIdx.x / nslabs, n0 = (blockIdx.x % nslabs) * CW, w = min(CW, NP - n0);   // NP % 16 == 0, so is w
-    const int gi = graph_idx[b];
+    const int nslabs = (NP + CW - 1) / CW, nitems = B * nslabs;
     const size_t PB = plane_bytes(NP);
-    unsigned char* eb = buf + (size_t)b * PLANES * PB;
     const int npanels = (NP + TILE_V - 1) / TILE_V, units = PAIRS * npanels;
-    const int run = (w >> 3) * 128;                        // bytes of one 8-vertex K group of the image panel
 
-    if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+    if (warp == 0) tmem_alloc(&tmem_base_s, 512);
     if (tid == 0) {
         for (int s = 0; s < CSTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(&done, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
         fence_mbar_init();
     }
     tc_fence_before();
@@ -147,78 +145,96 @@ tcl_contract_kernel(const eco_graphs_t g, const int32_t* __restrict__ graph_idx,
 
     if (warp == 0) {
         if (elect_one()) {
-            for (int u = 0; u < units; ++u) {
-                const int s = u % CSTAGES, p = u / npanels, kp = u % npanels;
-                const int k0 = kp * TILE_V, kg = min(TILE_V, NP - k0) >> 3;
-                if (u >= CSTAGES) mbar_wait(&empty[s], (uint32_t)((u / CSTAGES - 1) & 1));
-                unsigned char* sa = smem + s * CSTAGE_BYTES;
-                unsigned char* sb = sa + TILE_BYTES;
-                const uint16_t* img = g.tc_ops + ((size_t)gi * 2 + (p ? which2 : which1)) * NP * NP;
-                mbar_expect_tx(&full[s], (uint32_t)(kg * (2048 + run)));
-                bulk_g2s(sa, eb + (size_t)(p ? src2 : src1) * PB + (size_t)kp * TILE_BYTES, kg * 2048, &full[s]);
-                for (int cb = 0; cb < kg; ++cb)
-                    bulk_g2s(sb + cb * run, img + ((size_t)((k0 >> 3) + cb) * NB + (n0 >> 3)) * 64, run, &full[s]);
+            int uc = 0;                                    // units fed so far (ring position)
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const int b = item / nslabs, n0 = (item % nslabs) * CW, w = min(CW, NP - n0);   // NP % 16 == 0, so is w
+                const int gi = graph_idx[b], run = (w >> 3) * 128;    // run: bytes of one 8-vertex K group of the panel
+                const unsigned char* eb = buf + (size_t)b * PLANES * PB;
+                for (int u = 0; u < units; ++u, ++uc) {
+                    const int s = uc % CSTAGES, p = u / npanels, kp = u % npanels;
+                    const int k0 = kp * TILE_V, kg = min(TILE_V, NP - k0) >> 3;
+                    if (uc >= CSTAGES) mbar_wait(&empty[s], (uint32_t)((uc / CSTAGES - 1) & 1));
+                    unsigned char* sa = smem + s * CSTAGE_BYTES;
+                    unsigned char* sb = sa + TILE_BYTES;
+                    const uint16_t* img = g.tc_ops + ((size_t)gi * 2 + (p ? which2 : which1)) * NP * NP;
+                    mbar_expect_tx(&full[s], (uint32_t)(kg * (2048 + run)));
+                    bulk_g2s(sa, eb + (size_t)(p ? src2 : src1) * PB + (size_t)kp * TILE_BYTES, kg * 2048, &full[s]);
+                    for (int cb = 0; cb < kg; ++cb)
+                        bulk_g2s(sb + cb * run, img + ((size_t)((k0 >> 3) + cb) * NB + (n0 >> 3)) * 64, run, &full[s]);
+                }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         if (elect_one()) {
-            const uint32_t idesc = instr_desc_bf16(128, w, false, false);
-            for (int u = 0; u < units; ++u) {
-                const int s = u % CSTAGES, kp = u % npanels;
-                const int kw = min(TILE_V, NP - kp * TILE_V);
-                mbar_wait(&full[s], (uint32_t)((u / CSTAGES) & 1));
-                tc_fence_after();
-                const uint64_t ad = smem_desc(smem_u32(smem + s * CSTAGE_BYTES), 2048, 128);
-                const uint64_t bd = smem_desc(smem_u32(smem + s * CSTAGE_BYTES + TILE_BYTES), run, 128);
-                for (int ks = 0; ks < (kw >> 4); ++ks)
-                    mma_ss(tmem, ad + (uint64_t)ks * (4096 >> 4), bd + (uint64_t)ks * ((2 * run) >> 4), idesc, u > 0 || ks > 0);
-                mma_commit(&empty[s]);
+            int uc = 0, k = 0;
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++k) {
+                const int w = min(CW, NP - (item % nslabs) * CW), run = (w >> 3) * 128;
+                const uint32_t idesc = instr_desc_bf16(128, w, false, false);
+                const uint32_t acc = tmem + (uint32_t)(k & 1) * CW;
+                if (k >= 2) { mbar_wait(&acc_empty[k & 1], (uint32_t)(((k >> 1) - 1) & 1)); tc_fence_after(); }
+                for (int u = 0; u < units; ++u, ++uc) {
+                    const int s = uc % CSTAGES, kp = u % npanels;
+                    const int kw = min(TILE_V, NP - kp * TILE_V);
+                    mbar_wait(&full[s], (uint32_t)((uc / CSTAGES) & 1));
+                    tc_fence_after();
+                    const uint64_t ad = smem_desc(smem_u32(smem + s * CSTAGE_BYTES), 2048, 128);
+                    const uint64_t bd = smem_desc(smem_u32(smem + s * CSTAGE_BYTES + TILE_BYTES), run, 128);
+                    for (int ks = 0; ks < (kw >> 4); ++ks)
+                        mma_ss(acc, ad + (uint64_t)ks * (4096 >> 4), bd + (uint64_t)ks * ((2 * run) >> 4), idesc, u > 0 || ks > 0);
+                    mma_commit(&empty[s]);
+                }
+                mma_commit(&acc_full[k & 1]);
             }
-            mma_commit(&done);
         }
         __syncwarp();
     } else {
-        // warps 2, 3 (idle during the main loop): 1 / deg and deg / deg_max of the slab's vertices; 0 for padding vertices
-        const float dmax = norm_max > 0.f ? norm_max : (norm_max < 0.f ? (float)max(g.gstat[(size_t)gi * 4], 1) : *g.dmax);
-        for (int i = tid - 64; i < w; i += 64) {
-            const bool ok = n0 + i < N;
-            const float d = ok ? g.deg[(size_t)gi * NP + n0 + i] : 1.f;
-            s_rdeg[i] = ok ? scale / d : 0.f;
-            s_dn[i] = ok ? d / dmax : 0.f;
-        }
-    }
-    __syncthreads();
-    mbar_wait(&done, 0);
-    tc_fence_after();
-
-    // epilogue: (hi + lo rows) * scale / deg; feature 63 of the edge stage = deg / deg_max (mpnn.py:102)
-    unsigned char* ob = eb + (size_t)dst * PB;
-    const bool f63 = edge && warp == 3 && (lane >> 2) == 7;      // this lane's fr = 1 row is feature 63
-#pragma unroll 2
-    for (int blk = 0; blk < (w >> 4); ++blk) {
-        uint32_t vh[8], vl[8];
-        tmem_ld_16x256b_x2(tmem_addr(tmem, 32 * warp, 16 * blk), vh);
-        tmem_ld_16x256b_x2(tmem_addr(tmem, 32 * warp + 16, 16 * blk), vl);
-        tmem_ld_wait();
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int c = 16 * blk + 8 * half + 2 * (lane & 3);
-            const float2 rd = *reinterpret_cast<const float2*>(&s_rdeg[c]);
-            const float2 dn = *reinterpret_cast<const float2*>(&s_dn[c]);
-#pragma unroll
-            for (int fr = 0; fr < 2; ++fr) {
-                const int i = 4 * half + 2 * fr;
-                float va = (__uint_as_float(vh[i]) + __uint_as_float(vl[i])) * rd.x;
-                float vb = (__uint_as_float(vh[i + 1]) + __uint_as_float(vl[i + 1])) * rd.y;
-                if (fr == 1 && f63) { va = dn.x; vb = dn.y; }
-                store_pair(ob, n0 + 16 * blk + 8 * half, warp, fr, lane, va, vb);
+        // epilogue warps: (hi + lo rows) * scale / deg; feature 63 of the edge stage = deg / deg_max (mpnn.py:102)
+        const int q = warp & 3, et = tid - 64;             // TMEM lane quadrant of this warp; index among the 128 threads
+        const bool f63 = edge && q == 3 && (lane >> 2) == 7;        // this lane's fr = 1 row is feature 63
+        int k = 0;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++k) {
+            const int b = item / nslabs, n0 = (item % nslabs) * CW, w = min(CW, NP - n0);
+            const int gi = graph_idx[b], a = k & 1;
+            const float dmax = norm_max > 0.f ? norm_max : (norm_max < 0.f ? (float)max(g.gstat[(size_t)gi * 4], 1) : *g.dmax);
+            for (int i = et; i < w; i += 128) {            // 0 for padding vertices
+                const bool ok = n0 + i < N;
+                const float d = ok ? g.deg[(size_t)gi * NP + n0 + i] : 1.f;
+                s_rdeg[a][i] = ok ? scale / d : 0.f;
+                s_dn[a][i] = ok ? d / dmax : 0.f;
             }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(&acc_full[a], (uint32_t)((k >> 1) & 1));
+            tc_fence_after();
+            unsigned char* ob = buf + ((size_t)b * PLANES + dst) * PB;
+#pragma unroll 2
+            for (int blk = 0; blk < (w >> 4); ++blk) {
+                uint32_t vh[8], vl[8];
+                tmem_ld_16x256b_x2(tmem_addr(tmem, 32 * q, a * CW + 16 * blk), vh);
+                tmem_ld_16x256b_x2(tmem_addr(tmem, 32 * q + 16, a * CW + 16 * blk), vl);
+                tmem_ld_wait();
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int c = 16 * blk + 8 * half + 2 * (lane & 3);
+                    const float2 rd = *reinterpret_cast<const float2*>(&s_rdeg[a][c]);
+                    const float2 dn = *reinterpret_cast<const float2*>(&s_dn[a][c]);
+#pragma unroll
+                    for (int fr = 0; fr < 2; ++fr) {
+                        const int i = 4 * half + 2 * fr;
+                        float va = (__uint_as_float(vh[i]) + __uint_as_float(vl[i])) * rd.x;
+                        float vb = (__uint_as_float(vh[i + 1]) + __uint_as_float(vl[i + 1])) * rd.y;
+                        if (fr == 1 && f63) { va = dn.x; vb = dn.y; }
+                        store_pair(ob, n0 + 16 * blk + 8 * half, q, fr, lane, va, vb);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[a]);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 256);
+    if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------------------ per-vertex linears
@@ -492,17 +508,18 @@ int launch_mpnn_tcl(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int
     const int ntiles = (NP + TILE_V - 1) / TILE_V, nslabs = (NP + CW - 1) / CW;
     const long long items = (long long)B * ntiles;
     const int lgrid = (int)(items < 2LL * n_sm ? items : 2LL * n_sm);
-    const unsigned cgrid = (unsigned)((size_t)B * nslabs);
+    const long long citems = (long long)B * nslabs;
+    const int cgrid = (int)(citems < n_sm ? citems : n_sm);
     prof_begin(ECO_PROF_MPNN, st);
     tcl_init_kernel<<<dim3((NB + 3) / 4, B), 256, 0, st>>>(*g, *w, xn, xg, buf);
     ECO_LAUNCH_CHECK();
     // g = (S |A| + D A) / (2 deg), feature 63 = deg / deg_max
-    tcl_contract_kernel<2><<<cgrid, 128, CSMEM, st>>>(*g, gidx, buf, PL_S, 1, PL_D, 0, PL_AGG, 0.5f, 1, norm_max);
+    tcl_contract_kernel<2><<<cgrid, CTHREADS, CSMEM, st>>>(*g, gidx, B, buf, PL_S, 1, PL_D, 0, PL_AGG, 0.5f, 1, norm_max);
     ECO_LAUNCH_CHECK();
     tcl_linear_kernel<0><<<lgrid, 128, LSMEM, st>>>(*g, *w, B, buf, 0);
     ECO_LAUNCH_CHECK();
     for (int l = 0; l < 3; ++l) {
-        tcl_contract_kernel<1><<<cgrid, 128, CSMEM, st>>>(*g, gidx, buf, (l & 1) ? PL_H1 : PL_H0, 0, 0, 0, PL_AGG, 1.f, 0, norm_max);
+        tcl_contract_kernel<1><<<cgrid, CTHREADS, CSMEM, st>>>(*g, gidx, B, buf, (l & 1) ? PL_H1 : PL_H0, 0, 0, 0, PL_AGG, 1.f, 0, norm_max);
         ECO_LAUNCH_CHECK();
         tcl_linear_kernel<1><<<lgrid, 128, LSMEM, st>>>(*g, *w, B, buf, l);
         ECO_LAUNCH_CHECK();
