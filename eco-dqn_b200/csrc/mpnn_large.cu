@@ -16,6 +16,7 @@
 //   tcl_init_kernel      H0 = ReLU(W_init x);  S = R+ + R-, D = R+ - R-,  R+- = ReLU(W_x x +- w0)           CUDA cores
 //   tcl_contract_kernel  AGG = scale / deg * (X1 IMG1 (+ X2 IMG2))   (edge stage: 1/2 (S |A| + D A), feature 63)  tcgen05
 //   tcl_linear_kernel    E = ReLU(W_ef AGG)   |   m = ReLU(W_m [AGG ; E]),  H' = ReLU(W_u [H ; m])                 tcgen05
+//   (last layer)         H' is not stored: the epilogue leaves w_r . H'_i per vertex and pooled sums per tile
 //   tcl_readout_kernel   pooled readout, Q, argmax                                                            CUDA cores
 #include <cuda_bf16.h>
 
@@ -256,10 +257,12 @@ __device__ __forceinline__ void issue_linear_half(uint32_t tmem, uint32_t acc_co
 
 template <int MODE>
 __global__ void __launch_bounds__(128, 2)
-tcl_linear_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, unsigned char* __restrict__ buf, const int layer) {
+tcl_linear_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, unsigned char* __restrict__ buf, const int layer,
+                  float* __restrict__ qpart, float* __restrict__ ppart) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t full[2], bar;
     __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(8) float sq[4][TILE_V], sp[64];              // MODE 2: per-warp Q partial sums, per-feature pooled sums of the tile
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int NP = g.NP;
@@ -301,6 +304,9 @@ tcl_linear_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, unsigne
         tc_fence_before();
         __syncthreads();
     }
+    // MODE 2: readout weights of this lane's two feature rows (16 warp + lane/4, + 8)
+    const float wr0 = MODE == 2 ? w.w_read[64 + 16 * warp + (lane >> 2)] : 0.f;
+    const float wr1 = MODE == 2 ? w.w_read[64 + 16 * warp + (lane >> 2) + 8] : 0.f;
     uint32_t phase = 0;
     int it = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
@@ -321,7 +327,7 @@ tcl_linear_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, unsigne
                     issue_linear_half(tmem, TL_ACCM, TL_WA, sAgg, wdt, true);           // += W_m[:, :64] agg
                 }
                 mma_commit(&bar);
-                if (MODE == 1) issue_linear_half(tmem, TL_ACCH, TL_WB, sH, wdt, false);  // W_u[:, :64] h, ahead
+                if (MODE >= 1) issue_linear_half(tmem, TL_ACCH, TL_WB, sH, wdt, false);  // W_u[:, :64] h, ahead
             }
             __syncwarp();
         }
@@ -345,7 +351,7 @@ tcl_linear_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, unsigne
                     else store_pair(sAgg, 16 * blk + 8 * half, warp, fr, lane, va, vb);
                 }
         }
-        if (MODE == 1) {
+        if (MODE >= 1) {
             fence_proxy_async();
             tc_fence_before();
             __syncthreads();
@@ -359,20 +365,46 @@ tcl_linear_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, unsigne
             }
             mbar_wait(&bar, phase); phase ^= 1u;
             tc_fence_after();
+            float ps0 = 0.f, ps1 = 0.f;
             for (int blk = 0; blk < (wdt >> 4); ++blk) {           // epilogue 2: H' = ReLU(.) tile
                 uint32_t vh[8], vl[8];
                 tmem_ld_16x256b_x2(tmem_addr(tmem, 32 * warp, TL_ACCH + 16 * blk), vh);
                 tmem_ld_16x256b_x2(tmem_addr(tmem, 32 * warp + 16, TL_ACCH + 16 * blk), vl);
                 tmem_ld_wait();
+                float v[8];
 #pragma unroll
-                for (int half = 0; half < 2; ++half)
+                for (int i = 0; i < 8; ++i) v[i] = fmaxf(__uint_as_float(vh[i]) + __uint_as_float(vl[i]), 0.f);
 #pragma unroll
-                    for (int fr = 0; fr < 2; ++fr) {
-                        const int i = 4 * half + 2 * fr;
-                        const float va = fmaxf(__uint_as_float(vh[i]) + __uint_as_float(vl[i]), 0.f);
-                        const float vb = fmaxf(__uint_as_float(vh[i + 1]) + __uint_as_float(vl[i + 1]), 0.f);
-                        store_pair(ob, n0 + 16 * blk + 8 * half, warp, fr, lane, va, vb);
+                for (int half = 0; half < 2; ++half) {
+                    if (MODE == 1) {
+                        store_pair(ob, n0 + 16 * blk + 8 * half, warp, 0, lane, v[4 * half], v[4 * half + 1]);
+                        store_pair(ob, n0 + 16 * blk + 8 * half, warp, 1, lane, v[4 * half + 2], v[4 * half + 3]);
+                    } else {
+                        // last layer: H' only feeds the readout (mpnn.py:143-159); keep its per-vertex and pooled sums
+                        ps0 += v[4 * half] + v[4 * half + 1];
+                        ps1 += v[4 * half + 2] + v[4 * half + 3];
+                        float qa = fmaf(wr0, v[4 * half], wr1 * v[4 * half + 2]);
+                        float qb = fmaf(wr0, v[4 * half + 1], wr1 * v[4 * half + 3]);
+#pragma unroll
+                        for (int o = 4; o < 32; o <<= 1) {
+                            qa += __shfl_xor_sync(0xffffffffu, qa, o);
+                            qb += __shfl_xor_sync(0xffffffffu, qb, o);
+                        }
+                        if ((lane >> 2) == 0)
+                            *reinterpret_cast<float2*>(&sq[warp][16 * blk + 8 * half + 2 * (lane & 3)]) = make_float2(qa, qb);
                     }
+                }
+            }
+            if (MODE == 2) {
+#pragma unroll
+                for (int o = 1; o < 4; o <<= 1) {
+                    ps0 += __shfl_xor_sync(0xffffffffu, ps0, o);
+                    ps1 += __shfl_xor_sync(0xffffffffu, ps1, o);
+                }
+                if ((lane & 3) == 0) { sp[16 * warp + (lane >> 2)] = ps0; sp[16 * warp + (lane >> 2) + 8] = ps1; }
+                __syncthreads();
+                if (tid < wdt) qpart[(size_t)b * NP + n0 + tid] = (sq[0][tid] + sq[1][tid]) + (sq[2][tid] + sq[3][tid]);
+                if (tid < 64) ppart[((size_t)b * ntiles + n0 / TILE_V) * 64 + tid] = sp[tid];
             }
         }
         tc_fence_before();
@@ -384,64 +416,23 @@ tcl_linear_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, unsigne
 }
 
 // ------------------------------------------------------------------------------------------------ readout
-// One CTA per episode: mpnn.py:143-159 on the H plane, then argmax (ties -> lowest index).  Warps walk 8-vertex groups,
-// lanes own features lane and lane + 32.
-constexpr int RD_WARPS = 8;
-constexpr int RD_NMAX = 2048;
+// One CTA per episode: mpnn.py:143-159 from the sums the last layer left (per-vertex w_r[64:] . H'_i, per-tile pooled
+// sums), then argmax (ties -> lowest index).
+constexpr int RD_THREADS = 256;
 
-__device__ __forceinline__ float bf16lo(uint32_t x) { return __uint_as_float(x << 16); }
-__device__ __forceinline__ float bf16hi(uint32_t x) { return __uint_as_float(x & 0xffff0000u); }
-
-__global__ void __launch_bounds__(RD_WARPS * 32)
-tcl_readout_kernel(const eco_graphs_t g, const eco_mpnn_t w, const unsigned char* __restrict__ buf, const int plane,
+__global__ void __launch_bounds__(RD_THREADS)
+tcl_readout_kernel(const eco_graphs_t g, const eco_mpnn_t w, const float* __restrict__ qpart, const float* __restrict__ ppart,
                    float* __restrict__ q_out, int32_t* __restrict__ act_out) {
-    __shared__ float qpart[RD_NMAX];
-    __shared__ float part[RD_WARPS][64];
     __shared__ float pooled[64];
     __shared__ float c0_s;
-    __shared__ float red_val[RD_WARPS];
-    __shared__ int red_idx[RD_WARPS];
+    __shared__ float red_val[RD_THREADS / 32];
+    __shared__ int red_idx[RD_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int N = g.N, NP = g.NP, NB = NP >> 3, b = blockIdx.x;
-    const size_t PB = plane_bytes(NP);
-    const unsigned char* Hp = buf + ((size_t)b * PLANES + plane) * PB;
-    const int r0 = hi_row(lane);                           // feature lane; feature lane + 32 is 64 rows = 8 core rows further
-    const float wr0 = w.w_read[64 + lane], wr1 = w.w_read[96 + lane];
-    float sum0 = 0.f, sum1 = 0.f;
-    for (int cb = warp; cb < NB; cb += RD_WARPS) {
-        const unsigned char* p = Hp + (size_t)(cb >> 3) * TILE_BYTES + (((cb & 7) * 16 + (r0 >> 3)) * 128) + (r0 & 7) * 16;
-        const uint4 h0 = *reinterpret_cast<const uint4*>(p), l0 = *reinterpret_cast<const uint4*>(p + 256);
-        const uint4 h1 = *reinterpret_cast<const uint4*>(p + 1024), l1 = *reinterpret_cast<const uint4*>(p + 1280);
-        const uint32_t H0[4] = {h0.x, h0.y, h0.z, h0.w}, L0[4] = {l0.x, l0.y, l0.z, l0.w};
-        const uint32_t H1[4] = {h1.x, h1.y, h1.z, h1.w}, L1[4] = {l1.x, l1.y, l1.z, l1.w};
-        float qv[8];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float a0 = bf16lo(H0[k]) + bf16lo(L0[k]), a1 = bf16hi(H0[k]) + bf16hi(L0[k]);
-            const float c0 = bf16lo(H1[k]) + bf16lo(L1[k]), c1 = bf16hi(H1[k]) + bf16hi(L1[k]);
-            sum0 += a0 + a1;
-            sum1 += c0 + c1;
-            qv[2 * k] = fmaf(wr0, fmaxf(a0, 0.f), wr1 * fmaxf(c0, 0.f));
-            qv[2 * k + 1] = fmaf(wr0, fmaxf(a1, 0.f), wr1 * fmaxf(c1, 0.f));
-        }
-#pragma unroll
-        for (int v = 0; v < 8; ++v) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) qv[v] += __shfl_xor_sync(0xffffffffu, qv[v], o);
-        }
-        if (lane < 8) {
-            float x = qv[0];
-#pragma unroll
-            for (int v = 1; v < 8; ++v) x = lane == v ? qv[v] : x;
-            qpart[cb * 8 + lane] = x;
-        }
-    }
-    part[warp][lane] = sum0;
-    part[warp][lane + 32] = sum1;
-    __syncthreads();
+    const int N = g.N, NP = g.NP, b = blockIdx.x;
+    const int ntiles = (NP + TILE_V - 1) / TILE_V;
     if (tid < 64) {
         float s = 0.f;
-        for (int ww = 0; ww < RD_WARPS; ++ww) s += part[ww][tid];
+        for (int t = 0; t < ntiles; ++t) s += ppart[((size_t)b * ntiles + t) * 64 + tid];
         pooled[tid] = s / (float)N;
     }
     __syncthreads();
@@ -462,8 +453,8 @@ tcl_readout_kernel(const eco_graphs_t g, const eco_mpnn_t w, const unsigned char
     const float c0 = c0_s;
     float best_v = -INFINITY;
     int best_i = 0x7fffffff;
-    for (int i = tid; i < N; i += RD_WARPS * 32) {
-        const float v = qpart[i] + c0;
+    for (int i = tid; i < N; i += RD_THREADS) {
+        const float v = qpart[(size_t)b * NP + i] + c0;
         if (q_out) q_out[(size_t)b * NP + i] = v;
         if (v > best_v) { best_v = v; best_i = i; }
     }
@@ -478,7 +469,7 @@ tcl_readout_kernel(const eco_graphs_t g, const eco_mpnn_t w, const unsigned char
     if (tid == 0 && act_out) {
         float bv = red_val[0];
         int bi = red_idx[0];
-        for (int ww = 1; ww < RD_WARPS; ++ww)
+        for (int ww = 1; ww < RD_THREADS / 32; ++ww)
             if (red_val[ww] > bv || (red_val[ww] == bv && red_idx[ww] < bi)) { bv = red_val[ww]; bi = red_idx[ww]; }
         act_out[b] = bi;
     }
@@ -486,8 +477,11 @@ tcl_readout_kernel(const eco_graphs_t g, const eco_mpnn_t w, const unsigned char
 
 }  // namespace
 
-// scratch: B episodes x 6 planes of operand tiles
-size_t mpnn_tcl_scratch_bytes(int B, int N) { return align256((size_t)B * PLANES * plane_bytes(padded_n(N))); }
+// scratch: B episodes x 6 planes of operand tiles, then the last layer's readout sums [B][NP] + [B][tiles][64] floats
+size_t mpnn_tcl_scratch_bytes(int B, int N) {
+    const int NP = padded_n(N);
+    return align256((size_t)B * PLANES * plane_bytes(NP) + sizeof(float) * ((size_t)B * NP + (size_t)B * ((NP + TILE_V - 1) / TILE_V) * 64));
+}
 
 int launch_mpnn_tcl(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int32_t* gidx, const float* xn,
                     const float* xg, float norm_max, float* q, int32_t* actions, void* scratch, cudaStream_t st) {
@@ -498,12 +492,15 @@ int launch_mpnn_tcl(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int
         ECO_CUDA(cudaFuncSetAttribute(tcl_contract_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CSMEM));
         ECO_CUDA(cudaFuncSetAttribute(tcl_linear_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, LSMEM));
         ECO_CUDA(cudaFuncSetAttribute(tcl_linear_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, LSMEM));
+        ECO_CUDA(cudaFuncSetAttribute(tcl_linear_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, LSMEM));
         int dev = 0;
         ECO_CUDA(cudaGetDevice(&dev));
         ECO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         attr = true;
     }
     unsigned char* buf = (unsigned char*)scratch;
+    float* qpart = reinterpret_cast<float*>(buf + (size_t)B * PLANES * plane_bytes(g->NP));
+    float* ppart = qpart + (size_t)B * g->NP;
     const int NP = g->NP, NB = NP >> 3;
     const int ntiles = (NP + TILE_V - 1) / TILE_V, nslabs = (NP + CW - 1) / CW;
     const long long items = (long long)B * ntiles;
@@ -516,15 +513,16 @@ int launch_mpnn_tcl(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int
     // g = (S |A| + D A) / (2 deg), feature 63 = deg / deg_max
     tcl_contract_kernel<2><<<cgrid, CTHREADS, CSMEM, st>>>(*g, gidx, B, buf, PL_S, 1, PL_D, 0, PL_AGG, 0.5f, 1, norm_max);
     ECO_LAUNCH_CHECK();
-    tcl_linear_kernel<0><<<lgrid, 128, LSMEM, st>>>(*g, *w, B, buf, 0);
+    tcl_linear_kernel<0><<<lgrid, 128, LSMEM, st>>>(*g, *w, B, buf, 0, nullptr, nullptr);
     ECO_LAUNCH_CHECK();
     for (int l = 0; l < 3; ++l) {
         tcl_contract_kernel<1><<<cgrid, CTHREADS, CSMEM, st>>>(*g, gidx, B, buf, (l & 1) ? PL_H1 : PL_H0, 0, 0, 0, PL_AGG, 1.f, 0, norm_max);
         ECO_LAUNCH_CHECK();
-        tcl_linear_kernel<1><<<lgrid, 128, LSMEM, st>>>(*g, *w, B, buf, l);
+        if (l < 2) tcl_linear_kernel<1><<<lgrid, 128, LSMEM, st>>>(*g, *w, B, buf, l, nullptr, nullptr);
+        else tcl_linear_kernel<2><<<lgrid, 128, LSMEM, st>>>(*g, *w, B, buf, l, qpart, ppart);   // H' only as readout sums
         ECO_LAUNCH_CHECK();
     }
-    tcl_readout_kernel<<<B, RD_WARPS * 32, 0, st>>>(*g, *w, buf, PL_H1, q, actions);
+    tcl_readout_kernel<<<B, RD_THREADS, 0, st>>>(*g, *w, qpart, ppart, q, actions);
     ECO_LAUNCH_CHECK();
     prof_end(ECO_PROF_MPNN, st);
     return ECO_OK;
