@@ -339,6 +339,8 @@ int eco_mpnn_forward(const eco_graphs_t* g, const eco_mpnn_t* w, int32_t B, cons
     const int use = pick_impl(g, w, impl);
     if (use == ECO_MPNN_TCGEN05 && g->N > 208) {
         ECO_CHECK_ARG(w->packed, ECO_ERR_INVALID, "eco_mpnn_forward: tcgen05 path needs eco_mpnn_pack() output");
+        ECO_CHECK_ARG((((uintptr_t)xn | (uintptr_t)xg | (uintptr_t)scratch) & 15) == 0, ECO_ERR_INVALID,
+                      "eco_mpnn_forward: xn, xg and scratch must be 16-byte aligned");
         ECO_CHECK_ARG(mpnn_tcl_supported(g), ECO_ERR_UNSUPPORTED,
                       "eco_mpnn_forward: the tensor-core paths need couplings in {-1,0,1}; use ECO_MPNN_SIMT");
         return launch_mpnn_tcl(g, w, B, gidx, xn, xg, norm_max, q, actions, scratch, (cudaStream_t)stream);

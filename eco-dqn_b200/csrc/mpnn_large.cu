@@ -57,13 +57,20 @@ tcl_init_kernel(const eco_graphs_t g, const eco_mpnn_t w, const float* __restric
     const float4 xgl = *reinterpret_cast<const float4*>(xg + (size_t)b * 4);
     const int r = hi_row(f);
     for (int cb = blockIdx.x * 4 + (threadIdx.x >> 6); cb < NB; cb += gridDim.x * 4) {
-        float h[8], s[8], d[8];
+        float h[8], s[8], d[8], xr[3][8];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {                                            // NP % 16 == 0: 32-byte aligned rows
+            const float4 lo = *reinterpret_cast<const float4*>(x0 + (size_t)c * NP + cb * 8);
+            const float4 hi = *reinterpret_cast<const float4*>(x0 + (size_t)c * NP + cb * 8 + 4);
+            xr[c][0] = lo.x; xr[c][1] = lo.y; xr[c][2] = lo.z; xr[c][3] = lo.w;
+            xr[c][4] = hi.x; xr[c][5] = hi.y; xr[c][6] = hi.z; xr[c][7] = hi.w;
+        }
 #pragma unroll
         for (int v = 0; v < 8; ++v) {
             const int i = cb * 8 + v;
             h[v] = s[v] = d[v] = 0.f;                                            // padding vertices stay exactly zero
             if (i < N) {
-                const float X[7] = {x0[i], x0[NP + i], x0[2 * NP + i], xgl.x, xgl.y, xgl.z, xgl.w};
+                const float X[7] = {xr[0][v], xr[1][v], xr[2][v], xgl.x, xgl.y, xgl.z, xgl.w};
                 float hh = 0.f, p = 0.f;
 #pragma unroll
                 for (int c = 0; c < 7; ++c) {
