@@ -153,6 +153,39 @@ def test_free_running_rollout_against_oracle(eng, name):
     assert bc.cpu().numpy().max() <= z["best_cut"].max() + 1e9  # (upper bound checked in known-answer test)
 
 
+@pytest.mark.parametrize("n,p,B,T", [(230, 0.1, 3, 24), (300, 0.08, 2, 16)])
+def test_free_running_rollout_large_graph_against_oracle(eng, n, p, B, T):
+    """N > 208 (operand-tile pipeline, mpnn_large.cu) inside eco_rollout: the GPU's own action sequence replayed through
+    the CPU oracle -- rewards / scores / best cuts bit-exact, every action an argmax of the oracle's Q."""
+    from oracle.rollout import rollout as cpu_rollout
+    from oracle.mpnn import KEYS
+    from eco_dqn_b200 import _lib
+    rng = np.random.default_rng(n)
+    J = _random_graphs(rng, 1, n, p)
+    wd = {k: (rng.standard_normal(s) * (0.3 if len(s) > 1 else 0.1)).astype(np.float32)
+          for k, s in zip(KEYS, eng.STATE_DICT_SHAPES)}
+    init = (2 * rng.integers(0, 2, size=(B, n)) - 1).astype(np.int8)
+    gs = eng.GraphSet(J)
+    env = eng.BatchedSpinSystem(gs, B, T, 1.0 / n, mpnn_impl=_lib.MPNN_TCGEN05)
+    env.reset(spins=init)
+    ha, hr, hs = env.rollout(eng.MPNNWeights(wd), record_history=True)
+    ha, hr, hs = ha.cpu().numpy(), hr.cpu().numpy(), hs.cpu().numpy()
+    slack = []
+
+    def hook(t, qs):
+        qs = qs.numpy()
+        picked = qs[np.arange(qs.shape[0]), ha[:, t]]
+        slack.append(float(((qs.max(1) - picked) / (np.abs(qs.max(1)) + 1e-6)).max()))
+
+    ref = cpu_rollout(J[0].astype(np.float64), wd, init, T, 1.0 / n, forced_actions=ha, q_hook=hook)
+    assert np.array_equal(hr.view(np.uint64), ref["rewards"].view(np.uint64))
+    assert np.array_equal(hs, ref["scores"][:, 1:])
+    bc, bs, _ = env.results()
+    assert np.array_equal(bc.cpu().numpy().astype(np.float64), ref["best_cut"])
+    assert np.array_equal(bs.cpu().numpy(), ref["best_spins"])
+    assert max(slack) <= Q_RTOL, "GPU picked an action that is not an argmax of the oracle's Q"
+
+
 @pytest.mark.parametrize("name", golden_cases())
 def test_greedy_baseline_bit_exact(eng, name):
     z = load(name)
