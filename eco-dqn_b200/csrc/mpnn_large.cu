@@ -19,6 +19,7 @@
 //   (last layer)         H' is not stored: the epilogue leaves w_r . H'_i per vertex and pooled sums per tile
 //   tcl_readout_kernel   pooled readout, Q, argmax                                                            CUDA cores
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 #include "eco_common.cuh"
 #include "tc_prims.cuh"
@@ -32,6 +33,7 @@ using namespace tc;
 constexpr int TILE_V = 64;                        // vertices per operand tile
 constexpr int TILE_BYTES = 128 * TILE_V * 2;      // 16 KB
 constexpr int PLANES = 6;
+constexpr long long TCL_PLANE_BUDGET = 4LL << 30;  // bytes of planes per pass: bounds the scratch
 constexpr int PL_H0 = 0, PL_H1 = 1, PL_E = 2, PL_AGG = 3, PL_S = 4, PL_D = 5;
 
 __host__ __device__ inline size_t plane_bytes(int NP) { return (size_t)((NP + TILE_V - 1) / TILE_V) * TILE_BYTES; }
@@ -484,10 +486,21 @@ tcl_readout_kernel(const eco_graphs_t g, const eco_mpnn_t w, const float* __rest
 
 }  // namespace
 
-// scratch: B episodes x 6 planes of operand tiles, then the last layer's readout sums [B][NP] + [B][tiles][64] floats
+// Episodes per pass of the ten launches.  One pass unless the planes would exceed TCL_PLANE_BUDGET: keeping the planes
+// L2-resident with small passes was measured and loses (ER-500, B = 1024: one pass 0.81 ms, 512 episodes per pass 0.90,
+// 128 per pass 1.34 -- ten launch tails per pass cost more than the L2 hits save).  ECO_TCL_CHUNK overrides.
+static int tcl_chunk(int B, int NP) {
+    static const int forced = getenv("ECO_TCL_CHUNK") ? atoi(getenv("ECO_TCL_CHUNK")) : 0;
+    long long c = forced > 0 ? forced : (long long)TCL_PLANE_BUDGET / (long long)(PLANES * plane_bytes(NP));
+    if (c < 1) c = 1;
+    return c < B ? (int)c : B;
+}
+
+// scratch: `chunk` episodes x 6 planes of operand tiles, then the last layer's readout sums [chunk][NP] + [chunk][tiles][64]
 size_t mpnn_tcl_scratch_bytes(int B, int N) {
     const int NP = padded_n(N);
-    return align256((size_t)B * PLANES * plane_bytes(NP) + sizeof(float) * ((size_t)B * NP + (size_t)B * ((NP + TILE_V - 1) / TILE_V) * 64));
+    const size_t c = (size_t)tcl_chunk(B, NP);
+    return align256(c * PLANES * plane_bytes(NP) + sizeof(float) * (c * NP + c * ((NP + TILE_V - 1) / TILE_V) * 64));
 }
 
 int launch_mpnn_tcl(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int32_t* gidx, const float* xn,
@@ -506,31 +519,38 @@ int launch_mpnn_tcl(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int
         attr = true;
     }
     unsigned char* buf = (unsigned char*)scratch;
-    float* qpart = reinterpret_cast<float*>(buf + (size_t)B * PLANES * plane_bytes(g->NP));
-    float* ppart = qpart + (size_t)B * g->NP;
     const int NP = g->NP, NB = NP >> 3;
     const int ntiles = (NP + TILE_V - 1) / TILE_V, nslabs = (NP + CW - 1) / CW;
-    const long long items = (long long)B * ntiles;
-    const int lgrid = (int)(items < 2LL * n_sm ? items : 2LL * n_sm);
-    const long long citems = (long long)B * nslabs;
-    const int cgrid = (int)(citems < n_sm ? citems : n_sm);
+    const int chunk = tcl_chunk(B, NP);
+    float* qpart = reinterpret_cast<float*>(buf + (size_t)chunk * PLANES * plane_bytes(NP));
+    float* ppart = qpart + (size_t)chunk * NP;
     prof_begin(ECO_PROF_MPNN, st);
-    tcl_init_kernel<<<dim3((NB + 3) / 4, B), 256, 0, st>>>(*g, *w, xn, xg, buf);
-    ECO_LAUNCH_CHECK();
-    // g = (S |A| + D A) / (2 deg), feature 63 = deg / deg_max
-    tcl_contract_kernel<2><<<cgrid, CTHREADS, CSMEM, st>>>(*g, gidx, B, buf, PL_S, 1, PL_D, 0, PL_AGG, 0.5f, 1, norm_max);
-    ECO_LAUNCH_CHECK();
-    tcl_linear_kernel<0><<<lgrid, 128, LSMEM, st>>>(*g, *w, B, buf, 0, nullptr, nullptr);
-    ECO_LAUNCH_CHECK();
-    for (int l = 0; l < 3; ++l) {
-        tcl_contract_kernel<1><<<cgrid, CTHREADS, CSMEM, st>>>(*g, gidx, B, buf, (l & 1) ? PL_H1 : PL_H0, 0, 0, 0, PL_AGG, 1.f, 0, norm_max);
+    // Episodes go through the ten launches `chunk` at a time (normally all at once); the planes are reused by every pass.
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int nb = B - b0 < chunk ? B - b0 : chunk;
+        const int32_t* gi = gidx + b0;
+        const long long items = (long long)nb * ntiles;
+        const int lgrid = (int)(items < 2LL * n_sm ? items : 2LL * n_sm);
+        const long long citems = (long long)nb * nslabs;
+        const int cgrid = (int)(citems < n_sm ? citems : n_sm);
+        tcl_init_kernel<<<dim3((NB + 3) / 4, nb), 256, 0, st>>>(*g, *w, xn + (size_t)b0 * 3 * NP, xg + (size_t)b0 * 4, buf);
         ECO_LAUNCH_CHECK();
-        if (l < 2) tcl_linear_kernel<1><<<lgrid, 128, LSMEM, st>>>(*g, *w, B, buf, l, nullptr, nullptr);
-        else tcl_linear_kernel<2><<<lgrid, 128, LSMEM, st>>>(*g, *w, B, buf, l, qpart, ppart);   // H' only as readout sums
+        // g = (S |A| + D A) / (2 deg), feature 63 = deg / deg_max
+        tcl_contract_kernel<2><<<cgrid, CTHREADS, CSMEM, st>>>(*g, gi, nb, buf, PL_S, 1, PL_D, 0, PL_AGG, 0.5f, 1, norm_max);
+        ECO_LAUNCH_CHECK();
+        tcl_linear_kernel<0><<<lgrid, 128, LSMEM, st>>>(*g, *w, nb, buf, 0, nullptr, nullptr);
+        ECO_LAUNCH_CHECK();
+        for (int l = 0; l < 3; ++l) {
+            tcl_contract_kernel<1><<<cgrid, CTHREADS, CSMEM, st>>>(*g, gi, nb, buf, (l & 1) ? PL_H1 : PL_H0, 0, 0, 0, PL_AGG, 1.f, 0, norm_max);
+            ECO_LAUNCH_CHECK();
+            if (l < 2) tcl_linear_kernel<1><<<lgrid, 128, LSMEM, st>>>(*g, *w, nb, buf, l, nullptr, nullptr);
+            else tcl_linear_kernel<2><<<lgrid, 128, LSMEM, st>>>(*g, *w, nb, buf, l, qpart, ppart);   // H' only as readout sums
+            ECO_LAUNCH_CHECK();
+        }
+        tcl_readout_kernel<<<nb, RD_THREADS, 0, st>>>(*g, *w, qpart, ppart, q ? q + (size_t)b0 * NP : nullptr,
+                                                      actions ? actions + b0 : nullptr);
         ECO_LAUNCH_CHECK();
     }
-    tcl_readout_kernel<<<B, RD_THREADS, 0, st>>>(*g, *w, qpart, ppart, q, actions);
-    ECO_LAUNCH_CHECK();
     prof_end(ECO_PROF_MPNN, st);
     return ECO_OK;
 }
