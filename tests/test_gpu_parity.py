@@ -186,6 +186,48 @@ def test_free_running_rollout_large_graph_against_oracle(eng, n, p, B, T):
     assert max(slack) <= Q_RTOL, "GPU picked an action that is not an argmax of the oracle's Q"
 
 
+_CHUNK_SCRIPT = """
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+import eco_dqn_b200.engine as eng
+from eco_dqn_b200 import _lib
+z = np.load(sys.argv[1])
+gs = eng.GraphSet(z["J"])
+B, n = z["spins"].shape
+env = eng.BatchedSpinSystem(gs, B, 2 * n, 1.0 / n)
+env.reset(spins=z["spins"], graph_idx=z["gidx"])
+w = eng.MPNNWeights({k[2:]: z[k] for k in z.files if k.startswith("w_")})
+q, a = env.q_values(w, impl=_lib.MPNN_TCGEN05)
+np.savez(sys.argv[2], q=q.cpu().numpy(), a=a.cpu().numpy())
+"""
+
+
+def test_mpnn_large_graph_passes_match_single_pass(eng, tmp_path):
+    """The large-graph pipeline processes episodes in passes when its planes would exceed the scratch budget
+    (mpnn_large.cu: tcl_chunk); forced here to 3 episodes per pass in a child process: identical Q and actions."""
+    import subprocess
+    import sys
+    from oracle.mpnn import KEYS
+    from eco_dqn_b200 import _lib
+    rng = np.random.default_rng(11)
+    n, B = 300, 7
+    Js = _random_graphs(rng, 2, n, 0.08)
+    gidx = (np.arange(B) % 2).astype(np.int32)
+    spins = (2 * rng.integers(0, 2, size=(B, n)) - 1).astype(np.int8)
+    wd = {k: (rng.standard_normal(s) * (0.3 if len(s) > 1 else 0.1)).astype(np.float32)
+          for k, s in zip(KEYS, eng.STATE_DICT_SHAPES)}
+    env = eng.BatchedSpinSystem(eng.GraphSet(Js), B, 2 * n, 1.0 / n)
+    env.reset(spins=spins, graph_idx=gidx)
+    q, a = env.q_values(eng.MPNNWeights(wd), impl=_lib.MPNN_TCGEN05)
+    inp, out = str(tmp_path / "in.npz"), str(tmp_path / "out.npz")
+    np.savez(inp, J=Js, spins=spins, gidx=gidx, **{"w_" + k: v for k, v in wd.items()})
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env_vars = dict(os.environ, ECO_TCL_CHUNK="3")
+    subprocess.run([sys.executable, "-c", _CHUNK_SCRIPT % root, inp, out], check=True, env=env_vars, timeout=300)
+    z = np.load(out)
+    assert np.array_equal(z["q"], q.cpu().numpy()) and np.array_equal(z["a"], a.cpu().numpy())
+
+
 @pytest.mark.parametrize("name", golden_cases())
 def test_greedy_baseline_bit_exact(eng, name):
     z = load(name)
