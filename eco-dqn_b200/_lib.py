@@ -9,6 +9,8 @@ LIB_PATH = os.path.join(HERE, "lib", "libecodqn_b200.so")
 ECO_OK, ECO_ERR_INVALID, ECO_ERR_UNSUPPORTED, ECO_ERR_CUDA, ECO_ERR_STATE = 0, -1, -2, -3, -4
 POLICY_ACTIONS, POLICY_NETWORK, POLICY_GREEDY = 0, 1, 2
 MPNN_AUTO, MPNN_SIMT, MPNN_TCGEN05 = 0, 1, 2
+MPNN_N_PARAMS = 58425
+LOSS_MSE, LOSS_HUBER = 0, 1
 ENV_IRREVERSIBLE, ENV_DENSE_REWARD = 1, 2      # eco_env_t.reserved mode bits (include/ecodqn_b200.h)
 GRAPHS_MIN_CUT = 2                              # eco_graphs_t.reserved: OptimisationTarget.MIN_CUT
 MAX_SPINS = 2048
@@ -86,6 +88,8 @@ def lib():
         "eco_env_masked_argmax": (C.c_int, [P(Env), vp, vp, vp]),
         "eco_env_results": (C.c_int, [P(Env), vp, vp, vp, vp]),
         "eco_graph_aggregate": (C.c_int, [P(Graphs), i32, vp, vp, i32, C.c_float, vp, vp]),
+        "eco_mpnn_grad_scratch_bytes": (C.c_size_t, [i32, i32]),
+        "eco_mpnn_grad": (C.c_int, [P(Graphs), P(Mpnn), i32, vp, vp, vp, C.c_float, vp, vp, i32, vp, vp, vp, vp]),
         "eco_mpnn_scratch_bytes": (C.c_size_t, [i32, i32, i32]),
         "eco_mpnn_packed_bytes": (C.c_size_t, []),
         "eco_mpnn_pack": (C.c_int, [P(Mpnn), vp, vp]),
@@ -106,7 +110,7 @@ def lib():
 EXPORTED = ["eco_last_error", "eco_abi_version", "eco_launch_count", "eco_profile_enable", "eco_profile_read", "eco_graphs_workspace_bytes",
             "eco_graphs_bind", "eco_graphs_upload", "eco_graphs_load_dev", "eco_graphs_update", "eco_env_workspace_bytes",
             "eco_env_bind", "eco_env_set_tables", "eco_env_reset", "eco_env_step", "eco_env_observation",
-            "eco_env_best_spins", "eco_env_masked_argmax", "eco_env_results", "eco_graph_aggregate", "eco_mpnn_scratch_bytes", "eco_mpnn_packed_bytes",
+            "eco_env_best_spins", "eco_env_masked_argmax", "eco_env_results", "eco_graph_aggregate", "eco_mpnn_grad_scratch_bytes", "eco_mpnn_grad", "eco_mpnn_scratch_bytes", "eco_mpnn_packed_bytes",
             "eco_mpnn_pack", "eco_mpnn_forward", "eco_rollout", "eco_session_create", "eco_session_destroy",
             "eco_session_rollout"]
 

@@ -22,6 +22,7 @@ import torch.nn.functional as F
 import torch.optim as optim
 
 from ... import engine, sharding
+from ... import _lib
 from ..._lib import lib, check
 from .utils import ReplayBuffer, TestMetric, set_global_seed
 
@@ -63,11 +64,14 @@ class DQN:
         self.final_exploration_step = final_exploration_step
         self.adam_epsilon = adam_epsilon
         self.logging = logging
+        self._loss_kind = None                # ECO_LOSS_* when the gradient kernels can take the loss
+        self._grad_scratch = None
         if callable(loss):
             self.loss = loss
         else:
             try:
                 self.loss = {'huber': F.smooth_l1_loss, 'mse': F.mse_loss}[loss]
+                self._loss_kind = {'mse': _lib.LOSS_MSE, 'huber': _lib.LOSS_HUBER}[loss]
             except KeyError:
                 raise ValueError("loss must be 'huber', 'mse' or a callable")
         if test_metric not in (TestMetric.BEST, TestMetric.FINAL):
@@ -281,19 +285,53 @@ class DQN:
                 q_value_target[q_value_target < 0] = 0
             td_target = t["reward"].unsqueeze(1) + (1 - t["done"].unsqueeze(1)) * self.gamma * q_value_target
 
-        q_all = self.network(self._obs_from(t["xn"], t["xg"], graph))
-        if q_all.dim() == 1:
-            q_all = q_all.unsqueeze(0)
-        q_value = q_all.gather(1, t["action"].unsqueeze(1))
-        loss = self.loss(q_value, td_target, reduction='mean')
-        self.optimizer.zero_grad()
-        loss.backward()
+        if self._loss_kind is not None:
+            # forward + backward of the online network in the hand-written kernels (eco_mpnn_grad, csrc/mpnn_grad.cu)
+            loss = self._grad_kernel(t["xn"], t["xg"], graph, norm_max, t["action"], td_target)
+        else:
+            # a user-supplied loss callable: autograd through the PyTorch module
+            q_all = self.network(self._obs_from(t["xn"], t["xg"], graph))
+            if q_all.dim() == 1:
+                q_all = q_all.unsqueeze(0)
+            q_value = q_all.gather(1, t["action"].unsqueeze(1))
+            loss = self.loss(q_value, td_target, reduction='mean')
+            self.optimizer.zero_grad()
+            loss.backward()
         if self.world > 1:
             self._allreduce_grads()
         if self.max_grad_norm is not None:
             torch.nn.utils.clip_grad_norm_(self.network.parameters(), self.max_grad_norm)
         self.optimizer.step()
         return loss.item()
+
+    def _grad_kernel(self, xn, xg, graph, norm_max, action, td_target):
+        """loss and d loss / d weights of the regression step (dqn.py:436-447) through eco_mpnn_grad; the gradient
+        lands in `p.grad` of every parameter (views of one flat buffer, state_dict order)."""
+        B = xn.shape[0]
+        w = self.network.engine_weights(self.device)
+        nb = lib().eco_mpnn_grad_scratch_bytes(B, self.n_spins)
+        if self._grad_scratch is None or self._grad_scratch.numel() < nb:
+            self._grad_scratch = torch.empty(nb, dtype=torch.uint8, device=self.device)
+        flat = torch.empty(_lib.MPNN_N_PARAMS, dtype=torch.float32, device=self.device)
+        loss = torch.empty(1, dtype=torch.float32, device=self.device)
+        xn, xg, graph = xn.contiguous(), xg.contiguous(), graph.to(torch.int32).contiguous()
+        action = action.to(torch.int32).contiguous()
+        target = td_target.reshape(-1).to(torch.float32).contiguous()
+        check(lib().eco_mpnn_grad(C.byref(self._graphs.c), C.byref(w.c), B, engine._ptr(graph), engine._ptr(xn),
+                                  engine._ptr(xg), float(norm_max), engine._ptr(action), engine._ptr(target),
+                                  self._loss_kind, engine._ptr(loss), engine._ptr(flat), engine._ptr(self._grad_scratch),
+                                  engine._stream()))
+        params = dict(self.network.named_parameters())
+        off = 0
+        for key, shp in zip(engine.STATE_DICT_KEYS, engine.STATE_DICT_SHAPES):
+            n = int(np.prod(shp))
+            g = flat[off:off + n].view(shp)
+            p = params[key]
+            if tuple(p.shape) != shp:          # S2V-DQN nets (n_obs_in = 1): the kernels see zero-padded columns
+                g = g[:, :p.shape[1]].contiguous()
+            p.grad = g
+            off += n
+        return loss
 
     def _allreduce_grads(self):
         """One collective per update over a flat buffer of the 12 gradient tensors (sharding.allreduce_mean_grads)."""

@@ -355,6 +355,24 @@ int eco_mpnn_forward(const eco_graphs_t* g, const eco_mpnn_t* w, int32_t B, cons
     return launch_mpnn_simt(g, w, B, gidx, xn, xg, norm_max, q, actions, scratch, (cudaStream_t)stream);
 }
 
+size_t eco_mpnn_grad_scratch_bytes(int32_t B, int32_t N) { return (B >= 1 && N >= 1) ? mpnn_grad_scratch_bytes(B, N) : 0; }
+
+int eco_mpnn_grad(const eco_graphs_t* g, const eco_mpnn_t* w, int32_t B, const int32_t* gidx, const float* xn, const float* xg,
+                  float norm_max, const int32_t* actions, const float* targets, int32_t loss_kind, float* loss, float* grad,
+                  void* scratch, void* stream) {
+    ECO_CHECK_ARG(g && gidx && xn && xg && actions && targets && loss && grad && scratch, ECO_ERR_INVALID,
+                  "eco_mpnn_grad: null argument");
+    ECO_CHECK_ARG(B >= 1, ECO_ERR_INVALID, "eco_mpnn_grad: B must be >= 1");
+    ECO_CHECK_ARG(loss_kind == ECO_LOSS_MSE || loss_kind == ECO_LOSS_HUBER, ECO_ERR_INVALID, "eco_mpnn_grad: unknown loss %d",
+                  loss_kind);
+    ECO_CHECK_ARG(g->reserved & 1, ECO_ERR_UNSUPPORTED, "eco_mpnn_grad: needs couplings in {-1,0,1}");
+    ECO_CHECK_ARG((((uintptr_t)scratch | (uintptr_t)grad) & 15) == 0, ECO_ERR_INVALID, "eco_mpnn_grad: scratch and grad must be 16-byte aligned");
+    int rc = check_weights(w, "eco_mpnn_grad");
+    if (rc) return rc;
+    return launch_mpnn_grad(g, w, B, gidx, xn, xg, norm_max, actions, targets, loss_kind == ECO_LOSS_HUBER, loss, grad, scratch,
+                            (cudaStream_t)stream);
+}
+
 int eco_graph_aggregate(const eco_graphs_t* g, int32_t B, const int32_t* gidx, const float* x, int32_t use_abs,
                         float scale, float* out, void* stream) {
     ECO_CHECK_ARG(g && gidx && x && out && B >= 1, ECO_ERR_INVALID, "eco_graph_aggregate: bad argument");

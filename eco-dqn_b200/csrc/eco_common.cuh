@@ -92,6 +92,10 @@ size_t mpnn_tc_scratch_bytes(int B, int N);
 size_t mpnn_tc_packed_bytes();
 int launch_mpnn_pack(const eco_mpnn_t* w, void* packed, cudaStream_t st);
 bool mpnn_tc_supported(const eco_graphs_t* g);
+size_t mpnn_grad_scratch_bytes(int B, int N);
+int launch_mpnn_grad(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int32_t* gidx, const float* xn, const float* xg,
+                     float norm_max, const int32_t* actions, const float* targets, int huber, float* loss, float* grad,
+                     void* scratch, cudaStream_t st);
 bool mpnn_tcl_supported(const eco_graphs_t* g);
 size_t mpnn_tcl_scratch_bytes(int B, int N);
 int launch_mpnn_tcl(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int32_t* gidx, const float* xn,

@@ -213,6 +213,25 @@ int eco_graph_aggregate(const eco_graphs_t* g, int32_t B, const int32_t* graph_i
                         int32_t use_abs, float scale, float* out_dev, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * DQN regression step: loss and its gradients for a replay minibatch.  Replaces (reference src/agents/dqn/dqn.py:436-447)
+ *   q_value = self.network(states).gather(1, actions); loss = self.loss(q_value, td_target); loss.backward()
+ * i.e. MPNN.forward (src/networks/mpnn.py:38-159) plus its autograd backward.  Couplings in {-1,0,1}.
+ *   loss_dev [1] fp32 = mean_b l(Q[b, actions[b]] - targets[b]),  l = square (ECO_LOSS_MSE, F.mse_loss) or
+ *   smooth-L1 with beta 1 (ECO_LOSS_HUBER, F.smooth_l1_loss)           (dqn.py:113-121)
+ *   grad_dev [ECO_MPNN_N_PARAMS] fp32: d loss / d weights, the 12 tensors of eco_mpnn_t one after the other in
+ *   state_dict order (w_init, w_edge, w_edge_feat, w_msg[0], w_upd[0], ..., w_pool, w_read, b_read).
+ * features as for eco_mpnn_forward; actions_dev [B] int32, targets_dev [B] fp32.  Bit-reproducible (fixed-order sums).
+ * --------------------------------------------------------------------------------------------------------- */
+#define ECO_MPNN_N_PARAMS      58425
+#define ECO_LOSS_MSE           0
+#define ECO_LOSS_HUBER         1
+size_t eco_mpnn_grad_scratch_bytes(int32_t B, int32_t N);
+int    eco_mpnn_grad(const eco_graphs_t* g, const eco_mpnn_t* w, int32_t B, const int32_t* graph_idx_dev,
+                     const float* xn_dev, const float* xg_dev, float norm_max, const int32_t* actions_dev,
+                     const float* targets_dev, int32_t loss_kind, float* loss_dev, float* grad_dev,
+                     void* scratch_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Rollout: n_steps x [Q-eval + argmax -> env step] with no host round trip.  Replaces the hot loop of
  * __test_network_batched (reference experiments/utils.py:169-207) and, with ECO_POLICY_GREEDY, the Greedy
  * baseline (experiments/utils.py:218-227).  actions_scratch_dev [B] int32.  With ECO_ENV_IRREVERSIBLE the network

@@ -89,3 +89,87 @@ def test_learn_runs_and_checkpoints(tmp_path):
     rb = agent.replay_buffer
     assert float(rb.done.sum()) == 960 / 40 and int(rb.graph.max()) < agent._ring_size
     assert torch.isfinite(rb.reward).all() and set(rb.xn[:960, 0, :20].unique().tolist()) <= {-1.0, 1.0}
+
+
+@pytest.mark.parametrize("n,p,B,loss_name,norm_mode", [(17, 0.3, 5, "mse", "batch"), (40, 0.15, 64, "mse", "batch"),
+                                                       (40, 0.15, 16, "huber", "set"), (100, 0.08, 7, "mse", "graph"),
+                                                       (200, 0.04, 9, "huber", "batch")])
+def test_grad_kernels_match_autograd(n, p, B, loss_name, norm_mode):
+    """eco_mpnn_grad (forward + backward in hand-written kernels) against autograd through the PyTorch module of the
+    same network on the same minibatch: loss 1e-5 rel, every gradient tensor 1e-4 of its largest entry; and two calls
+    give identical bits."""
+    import ctypes as C
+    import torch.nn.functional as F
+    import eco_dqn_b200.engine as eng
+    from eco_dqn_b200 import _lib
+    from eco_dqn_b200._lib import lib, check
+    from eco_dqn_b200.networks.mpnn import MPNN
+    rng = np.random.default_rng(7 * n + B)
+    torch.manual_seed(n + B)
+    G = 3
+    Js = np.zeros((G, n, n), dtype=np.int8)
+    for g in range(G):
+        up = np.triu(rng.random((n, n)) < p, 1)
+        a = (up * np.where(rng.random((n, n)) < 0.5, -1, 1)).astype(np.int8)
+        Js[g] = a + a.T
+    Js[:, 0, 1] = Js[:, 1, 0] = 1                                   # no empty graph
+    dev = torch.device("cuda:0")
+    gs = eng.GraphSet(Js, device=dev)
+    NP = gs.NP
+    net = MPNN().to(dev)
+    with torch.no_grad():
+        for q in net.parameters():
+            q.copy_(torch.randn_like(q) * (0.3 if q.dim() > 1 else 0.1))
+    gidx = torch.tensor(rng.integers(0, G, size=B), dtype=torch.int32, device=dev)
+    rows = torch.tensor(rng.standard_normal((B, 7, n)).astype(np.float32), device=dev)
+    rows[:, 0] = torch.sign(rows[:, 0])
+    rows[:, 3:] = rows[:, 3:, :1]                                   # global observables: constant over the vertices
+    xn = torch.zeros(B, 3, NP, device=dev)
+    xn[:, :, :n] = rows[:, :3]
+    xg = rows[:, 3:, 0].contiguous()
+    actions = torch.tensor(rng.integers(0, n, size=B), dtype=torch.int32, device=dev)
+    targets = torch.tensor(rng.standard_normal(B).astype(np.float32) * 3, device=dev)
+    deg = torch.tensor((Js != 0).sum(1).clip(1).astype(np.float32), device=dev)
+    norm_max = {"batch": float(deg[gidx.long()].max()), "set": 0.0, "graph": -1.0}[norm_mode]
+
+    # reference: autograd through the module (one episode at a time for per-graph normalisation)
+    adj = torch.tensor(Js.astype(np.float32), device=dev)[gidx.long()]
+    obs = torch.cat([rows, adj], dim=1)
+    if norm_mode == "graph":
+        q_all = torch.stack([net(obs[b:b + 1]).reshape(-1) for b in range(B)])
+    elif norm_mode == "set":
+        # the whole set's max degree: append one (unused) episode per graph so that norm.max() covers the set
+        extra = torch.cat([torch.zeros(G, 7, n, device=dev), torch.tensor(Js.astype(np.float32), device=dev)], dim=1)
+        q_all = net(torch.cat([obs, extra], dim=0))[:B]
+    else:
+        q_all = net(obs)
+    qv = q_all.gather(1, actions.long().unsqueeze(1)).squeeze(1)
+    loss_ref = {"mse": F.mse_loss, "huber": F.smooth_l1_loss}[loss_name](qv, targets, reduction="mean")
+    net.zero_grad()
+    loss_ref.backward()
+
+    w = net.engine_weights(dev)
+    nb = lib().eco_mpnn_grad_scratch_bytes(B, n)
+    scratch = torch.empty(nb, dtype=torch.uint8, device=dev)
+    outs = []
+    for rep in range(2):
+        flat = torch.full((_lib.MPNN_N_PARAMS,), float("nan"), device=dev)
+        loss = torch.full((1,), float("nan"), device=dev)
+        check(lib().eco_mpnn_grad(C.byref(gs.c), C.byref(w.c), B, eng._ptr(gidx), eng._ptr(xn), eng._ptr(xg), norm_max,
+                                  eng._ptr(actions), eng._ptr(targets), {"mse": _lib.LOSS_MSE, "huber": _lib.LOSS_HUBER}[loss_name],
+                                  eng._ptr(loss), eng._ptr(flat), eng._ptr(scratch), eng._stream()))
+        torch.cuda.synchronize()
+        outs.append((loss.cpu().numpy().copy(), flat.cpu().numpy().copy()))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    loss_k, flat_k = float(outs[0][0][0]), outs[0][1]
+    loss_r = float(loss_ref.detach())
+    assert abs(loss_k - loss_r) <= 1e-5 * abs(loss_r) + 1e-7, (loss_k, loss_r)
+    params = dict(net.named_parameters())
+    off = 0
+    for key, shp in zip(eng.STATE_DICT_KEYS, eng.STATE_DICT_SHAPES):
+        cnt = int(np.prod(shp))
+        gk = flat_k[off:off + cnt].reshape(shp)
+        gr = params[key].grad.cpu().numpy()
+        assert np.isfinite(gk).all(), key
+        assert np.abs(gk - gr).max() <= 1e-4 * np.abs(gr).max() + 1e-8, (key, np.abs(gk - gr).max(), np.abs(gr).max())
+        off += cnt

@@ -53,4 +53,4 @@ agent.learn(timesteps=steps)
 torch.cuda.synchronize()
 tot = time.perf_counter() - t0
 print("n_envs %d: %.1f ms per 1000 timesteps; %d train steps, %.2f ms each = %.0f%% of the time" %
-      (n_envs, tot / steps * 1e6 / 1e3, acc["n"], acc["train_step"] / max(acc["n"], 1) * 1e3, 100 * acc["train_step"] / tot))
+      (n_envs, tot / steps * 1e6, acc["n"], acc["train_step"] / max(acc["n"], 1) * 1e3, 100 * acc["train_step"] / tot))
