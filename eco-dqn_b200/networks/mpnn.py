@@ -2,12 +2,13 @@
 state_dict keys / shapes in SURVEY.md appendix A.3), so the shipped `.pth` files load unchanged.
 
 Two execution paths:
-  * `forward(obs)` -- differentiable PyTorch ops on any device, used for the DQN update (autograd backward) and as
-    the fp32 torch reference of the CUDA kernels.  The edge stage uses the factorised form
+  * `forward(obs)` -- differentiable PyTorch ops on any device: the fp32 torch reference of the CUDA kernels (tests) and
+    the autograd route of the DQN update when the user supplies a loss callable.  The edge stage uses the factorised form
     ReLU(W_e [a_ij ; x_j]) = ReLU(a_ij w0 + W_x x_j), i.e. two N x N contractions for {-1,0,1} couplings instead of
     the reference's [B,N,N,63] intermediate (mpnn.py:89-100); real-valued couplings take the dense route.
   * `engine_weights()` -- the same parameters as device pointers for the hand-written kernels
-    (eco_dqn_b200.engine.BatchedSpinSystem.q_values / rollout): that is the rollout hot path.
+    (eco_dqn_b200.engine.BatchedSpinSystem.q_values / rollout, and eco_mpnn_grad for the DQN update's loss and
+    gradients): that is the hot path.
 """
 import torch
 import torch.nn as nn
