@@ -166,6 +166,58 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def dqn_update_sample(timesteps=3000, n_envs=16):
+    """C5 of BASELINE.json: DQN.learn on ER-40 with the hyper-parameters of experiments/train_eco.py (minibatch 64,
+    update every 32 steps, replay 5000).  Returns ms per train_step (TD target + eco_mpnn_grad + Adam) and ms per 1000
+    environment timesteps of the whole learn loop.  A reported side number, not the bench metric."""
+    import contextlib
+    import tempfile
+    import torch
+    import eco_dqn_b200.envs.core as ising_env
+    from eco_dqn_b200.envs.utils import (DEFAULT_OBSERVABLES, RewardSignal, ExtraAction, OptimisationTarget, SpinBasis,
+                                         Stopping, RandomErdosRenyiGraphGenerator, EdgeType)
+    from eco_dqn_b200.networks.mpnn import MPNN
+    from eco_dqn_b200.agents.dqn.dqn import DQN
+    from eco_dqn_b200.agents.dqn.utils import TestMetric
+    n = 40
+    env_args = {'observables': DEFAULT_OBSERVABLES, 'reward_signal': RewardSignal.BLS, 'extra_action': ExtraAction.NONE,
+                'optimisation_target': OptimisationTarget.CUT, 'spin_basis': SpinBasis.SIGNED, 'norm_rewards': True,
+                'memory_length': None, 'horizon_length': None, 'stag_punishment': None, 'basin_reward': 1. / n,
+                'reversible_spins': True, 'stopping': Stopping.NORMAL}
+    with contextlib.redirect_stdout(sys.stderr):
+        env = ising_env.make("SpinSystem", RandomErdosRenyiGraphGenerator(n, 0.15, EdgeType.DISCRETE), 2 * n, **env_args)
+        tmp = tempfile.mkdtemp()
+        agent = DQN([env], lambda: MPNN(), init_weight_std=0.01, double_dqn=True, gamma=0.95, update_learning_rate=False,
+                    initial_learning_rate=1e-4, minibatch_size=64, update_frequency=32, update_target_frequency=1000,
+                    replay_start_size=500, replay_buffer_size=5000, final_exploration_step=3000,
+                    final_exploration_rate=0.05, test_frequency=10 ** 9, save_network_frequency=10 ** 9, logging=False,
+                    seed=5, test_metric=TestMetric.BEST, test_save_path=os.path.join(tmp, "s"),
+                    network_save_path=os.path.join(tmp, "n"), n_envs=n_envs)
+        acc = {"s": 0.0, "n": 0}
+        orig = agent.train_step
+
+        def timed(tr):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = orig(tr)
+            torch.cuda.synchronize()
+            acc["s"] += time.perf_counter() - t0
+            acc["n"] += 1
+            return out
+
+        agent.train_step = timed
+        agent.learn(timesteps=1000)          # warm-up: fills the replay, first updates
+        acc["s"], acc["n"] = 0.0, 0
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        agent.learn(timesteps=timesteps)
+        torch.cuda.synchronize()
+        tot = time.perf_counter() - t0
+    return {"workload": "DQN.learn, ER-40 p=0.15, minibatch 64, update every 32 timesteps, %d lock-step environments" % n_envs,
+            "train_step_ms": acc["s"] / max(acc["n"], 1) * 1e3, "train_steps": acc["n"],
+            "ms_per_1000_timesteps": tot / timesteps * 1e6, "timing": "host clock around synchronised calls"}
+
+
 def config_dict(world):
     return {"workload": "BA_200spin (m=4, +-1 weights) batched ECO-DQN greedy-Q rollout, %d concurrent episodes per GPU, "
                         "%d distinct graphs per GPU, T=2N=%d env steps per episode" % (B_PER_GPU, B_PER_GPU, 2 * N_SPINS),
@@ -323,6 +375,12 @@ def run_ours(args):
             cpu = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
                    "sample": "32 complete episodes (400 env steps each) of one BA-200 graph, batched like the "
                              "reference's test_network (%.1f s of CPU work)" % secs}
+        dqn = None
+        if not args.skip_dqn:
+            try:
+                dqn = dqn_update_sample()
+            except Exception as e:          # a side number must not cost the bench line
+                dqn = {"error": "%s: %s" % (type(e).__name__, e)}
         line = {"metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16x2-split/f32" if used_impl == "tcgen05" else "f32",
@@ -331,7 +389,8 @@ def run_ours(args):
                         "h2d_bytes_per_step": int(G * n * n + B * 4 + B * n), "d2h_bytes_per_step": int(B * 4 + B * n),
                         "steps": e2e_steps},
                 "gpu_launches": launches, "roofline": roof, "roofline_env_step": roof_env, "env_only": env_only,
-                "cpu_baseline": cpu, "clocks": clocks, "mpnn_impl": used_impl, "mean_best_cut": best_mean}
+                "cpu_baseline": cpu, "clocks": clocks, "mpnn_impl": used_impl, "mean_best_cut": best_mean,
+                "dqn_update": dqn}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -349,6 +408,7 @@ def main():
     ap.add_argument("--mpnn", default="auto", choices=["auto", "simt", "tc"])
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-env-only", action="store_true")
+    ap.add_argument("--skip-dqn", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
