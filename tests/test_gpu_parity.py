@@ -492,6 +492,29 @@ def test_host_session_matches_engine(eng):
     sess.close()
 
 
+def test_host_session_large_graph_matches_engine(eng):
+    """Host-buffer session on a graph with N > 208 (AUTO -> the operand-tile pipeline) against the engine."""
+    from oracle.mpnn import KEYS
+    from eco_dqn_b200 import _lib
+    rng = np.random.default_rng(5)
+    n, B, T = 230, 4, 12
+    J = _random_graphs(rng, 2, n, 0.1)
+    gidx = np.array([0, 1, 1, 0], dtype=np.int32)
+    init = (2 * rng.integers(0, 2, size=(B, n)) - 1).astype(np.int8)
+    wd = {k: (rng.standard_normal(s) * (0.3 if len(s) > 1 else 0.1)).astype(np.float32)
+          for k, s in zip(KEYS, eng.STATE_DICT_SHAPES)}
+    sess = eng.HostSession(2, n, B, T, 1.0 / n, wd, impl=_lib.MPNN_AUTO)
+    best_cut = np.zeros(B, dtype=np.int32)
+    best_spins = np.zeros((B, n), dtype=np.int8)
+    sess.rollout(np.ascontiguousarray(J), gidx, init, best_cut, best_spins)
+    env = eng.BatchedSpinSystem(eng.GraphSet(J), B, T, 1.0 / n)
+    env.reset(spins=init, graph_idx=gidx)
+    env.rollout(eng.MPNNWeights(wd))
+    bc, bs, _ = env.results()
+    assert np.array_equal(best_cut, bc.cpu().numpy()) and np.array_equal(best_spins, bs.cpu().numpy())
+    sess.close()
+
+
 def test_error_behaviour(eng):
     z = load("er20_g0")
     gs, env = make_env(eng, z)
