@@ -54,6 +54,16 @@ static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 static inline int padded_n(int n) { return round_up(n, 16); }
 
+// Byte offset of core matrix (cb = K group, rb = column group; 8 x 8 bf16 = 128 bytes) in a graph's bf16 operand image
+// (eco_graphs_t.tc_ops, built by graph_prepare.cu; NB = NP / 8 groups per side).  Column groups are stored in slabs of
+// 32 (256 columns) and, inside a slab, K group after K group: a (K panel x slab) block is one contiguous run for the
+// bulk copies of the large-graph kernels, and for NP <= 256 this is the plain (cb * NB + rb) order that the resident
+// kernel (mpnn_tc.cu) uses as its shared-memory layout.
+__host__ __device__ inline size_t tc_image_core(int NB, int cb, int rb) {
+    const int s = rb >> 5, left = NB - 32 * s, wg = left < 32 ? left : 32;
+    return ((size_t)s * NB * 32 + (size_t)cb * wg + (rb & 31)) * 128;
+}
+
 // ---- episode flags --------------------------------------------------------------------------------------
 constexpr int FLAG_DONE = 1;
 constexpr int FLAG_STOPPED = 2;

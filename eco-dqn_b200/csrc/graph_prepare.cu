@@ -115,8 +115,9 @@ __global__ void __launch_bounds__(256) graph_prepare_kernel(eco_graphs_t g, int 
         dtab[k] = __ddiv_rn((double)(k - NP), qn_d);                  // delta_score / quality normaliser (spinsystem.py:394)
     }
     // bf16 operand images of J and |J| for the tensor-core MPNN (mpnn_tc.cu): element (r, c) of the K-major operand
-    // lives in core matrix (rb = r / 8, cb = c / 8) at byte ((cb * NP/8 + rb) * 8 + r % 8) * 16 + (c % 8) * 2, i.e.
-    // exactly the shared-memory layout, so an episode fetches each image with one bulk copy.  int8 is exact in bf16.
+    // lives in core matrix (rb = r / 8, cb = c / 8) at byte tc_image_core(NP/8, cb, rb) + (r % 8) * 16 + (c % 8) * 2; for
+    // NP <= 256 that is ((cb * NP/8 + rb) * 8 + r % 8) * 16 + ..., exactly the resident kernel's shared-memory layout, so
+    // an episode fetches each image with one bulk copy.  int8 is exact in bf16.
     if (g.tc_ops != nullptr) {
         const int NB = NP >> 3;
         uint4* img_a = reinterpret_cast<uint4*>(g.tc_ops + (size_t)gi * 2 * NP * NP);
@@ -135,8 +136,9 @@ __global__ void __launch_bounds__(256) graph_prepare_kernel(eco_graphs_t g, int 
                 wb[e] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn((float)abs(v0))) |
                         ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn((float)abs(v1))) << 16);
             }
-            img_a[idx] = make_uint4(wa[0], wa[1], wa[2], wa[3]);
-            img_abs[idx] = make_uint4(wb[0], wb[1], wb[2], wb[3]);
+            const size_t dst = tc_image_core(NB, cb, rb) / 16 + r7;
+            img_a[dst] = make_uint4(wa[0], wa[1], wa[2], wa[3]);
+            img_abs[dst] = make_uint4(wb[0], wb[1], wb[2], wb[3]);
         }
     }
 }

@@ -169,8 +169,8 @@ tcl_contract_kernel(const eco_graphs_t g, const int32_t* __restrict__ graph_idx,
                     const uint16_t* img = g.tc_ops + ((size_t)gi * 2 + (p ? which2 : which1)) * NP * NP;
                     mbar_expect_tx(&full[s], (uint32_t)(kg * (2048 + run)));
                     bulk_g2s(sa, eb + (size_t)(p ? src2 : src1) * PB + (size_t)kp * TILE_BYTES, kg * 2048, &full[s]);
-                    for (int cb = 0; cb < kg; ++cb)
-                        bulk_g2s(sb + cb * run, img + ((size_t)((k0 >> 3) + cb) * NB + (n0 >> 3)) * 64, run, &full[s]);
+                    // the panel's K groups of this slab are contiguous in the image (eco_common.cuh: tc_image_core)
+                    bulk_g2s(sb, reinterpret_cast<const unsigned char*>(img) + tc_image_core(NB, k0 >> 3, n0 >> 3), kg * run, &full[s]);
                 }
             }
         }

@@ -74,7 +74,7 @@ graph_aggregate_kernel(const eco_graphs_t g, const int32_t* __restrict__ graph_i
             mbar_expect_tx(&bar_b, (uint32_t)(PAIRS * (kw >> 3) * run));
             for (int p = 0; p < PAIRS; ++p)
                 for (int cb = 0; cb < (kw >> 3); ++cb)
-                    bulk_g2s(sB[p] + cb * run, img[p] + ((size_t)((k0 >> 3) + cb) * NB + (n0 >> 3)) * 64, run, &bar_b);
+                    bulk_g2s(sB[p] + cb * run, reinterpret_cast<const unsigned char*>(img[p]) + tc_image_core(NB, (k0 >> 3) + cb, n0 >> 3), run, &bar_b);
         }
         for (int p = 0; p < PAIRS; ++p) {
             if (p > 0) __syncthreads();                                     // sXf is reused
