@@ -93,7 +93,7 @@ def test_learn_runs_and_checkpoints(tmp_path):
 
 @pytest.mark.parametrize("n,p,B,loss_name,norm_mode", [(17, 0.3, 5, "mse", "batch"), (40, 0.15, 64, "mse", "batch"),
                                                        (40, 0.15, 16, "huber", "set"), (100, 0.08, 7, "mse", "graph"),
-                                                       (200, 0.04, 9, "huber", "batch")])
+                                                       (200, 0.04, 9, "huber", "batch"), (333, 0.03, 3, "mse", "batch")])
 def test_grad_kernels_match_autograd(n, p, B, loss_name, norm_mode):
     """eco_mpnn_grad (forward + backward in hand-written kernels) against autograd through the PyTorch module of the
     same network on the same minibatch: loss 1e-5 rel, every gradient tensor 1e-4 of its largest entry; and two calls
