@@ -606,6 +606,43 @@ def test_s2v_device_rollout_and_greedy(eng, name):
     assert int(st[1]) == int(z["greedy_steps"])
 
 
+def test_s2v_rollout_large_graph_against_oracle(eng):
+    """S2V-DQN configuration on a graph with N > 208: the operand-tile pipeline feeds the masked argmax inside
+    eco_rollout.  The GPU's action sequence is replayed through the oracle: rewards (with their sign bits), scores and
+    done flags bit-exact, every action a masked argmax of the oracle's Q."""
+    from oracle.rollout import rollout_s2v
+    from oracle.mpnn import KEYS
+    rng = np.random.default_rng(23)
+    n, T = 240, 40
+    J = _random_graphs(rng, 1, n, 0.08)
+    wd = {k: (rng.standard_normal(s) * (0.3 if len(s) > 1 else 0.1)).astype(np.float32)
+          for k, s in zip(KEYS, eng.STATE_DICT_SHAPES)}
+    wd[KEYS[0]] = wd[KEYS[0]][:, :1].copy()                 # n_obs_in = 1 (networks/s2v): W_init [64, 1], W_e [63, 2]
+    wd[KEYS[1]] = wd[KEYS[1]][:, :2].copy()
+    w = eng.MPNNWeights(wd)
+    assert w.n_obs_in == 1
+    env = eng.BatchedSpinSystem(eng.GraphSet(J), 2, T, None, reversible_spins=False, dense_reward=True)
+    env.reset(graph_idx=np.zeros(2, dtype=np.int32))
+    ha, hr, hs = env.rollout(w, record_history=True, norm_max=-1.0)
+    ha, hr, hs = ha.cpu().numpy(), hr.cpu().numpy(), hs.cpu().numpy()
+    assert np.array_equal(ha[0], ha[1]) and len(set(ha[0].tolist())) == T          # irreversible: T distinct vertices
+    slack = []
+
+    def hook(t, qs):
+        q = qs.numpy().reshape(-1).copy()
+        q[np.array(sorted(set(ha[0, :t].tolist())), dtype=np.int64)] = -np.inf
+        slack.append(float((q.max() - q[ha[0, t]]) / (abs(q.max()) + 1e-6)))
+
+    ref = rollout_s2v(J[0].astype(np.float64), wd, T, forced_actions=ha[0], q_hook=hook)
+    k = len(ref["actions"])
+    assert k == T
+    assert np.array_equal(hr[0, :k].view(np.uint64), ref["rewards"].view(np.uint64))
+    assert np.array_equal(hs[0, :k], ref["scores"][1:])
+    bc, bs, st = env.results()
+    assert float(bc[0]) == ref["best_cut"] and np.array_equal(bs[0].cpu().numpy(), ref["best_spins"])
+    assert max(slack) <= Q_RTOL, "GPU picked an action that is not a masked argmax of the oracle's Q"
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # OptimisationTarget.MIN_CUT (SURVEY.md section 8(f)3)
 # ---------------------------------------------------------------------------------------------------------------
