@@ -118,14 +118,16 @@ k_adj(const eco_graphs_t g, const int32_t* __restrict__ graph_idx, const float* 
 constexpr int GT = 64;                 // vertices per tile
 constexpr int AT_LD = 68;
 
-template <bool BWD>
+template <bool BWD, int K>
 __global__ void __launch_bounds__(256)
-k_gemm(const float* __restrict__ A1, const float* __restrict__ A2, const float* __restrict__ maskY, const int V, const int K,
+k_gemm(const float* __restrict__ A1, const float* __restrict__ A2, const float* __restrict__ maskY, const int V,
        const float* __restrict__ W, const int ldw, const int koff, float* __restrict__ C, const int relu, const int accumulate) {
     extern __shared__ __align__(16) unsigned char sm[];
     float* At = reinterpret_cast<float*>(sm);                 // [K][AT_LD]
     float* Bt = At + (size_t)K * AT_LD;                       // [K][64]
     const int tid = threadIdx.x, v0 = blockIdx.x * GT;
+    // (compile-time trip counts: the independent loads of a tile are issued back to back)
+#pragma unroll 8
     for (int idx = tid; idx < GT * K; idx += 256) {
         const int vv = idx / K, k = idx % K, v = v0 + vv;
         float val = 0.f;
@@ -135,6 +137,7 @@ k_gemm(const float* __restrict__ A1, const float* __restrict__ A2, const float* 
         }
         At[k * AT_LD + vv] = val;
     }
+#pragma unroll 8
     for (int idx = tid; idx < 64 * K; idx += 256) {
         if (BWD) { const int k = idx >> 6, n = idx & 63; Bt[k * 64 + n] = W[(size_t)k * ldw + koff + n]; }
         else { const int n = idx / K, k = idx % K; Bt[k * 64 + n] = W[(size_t)n * ldw + k]; }
@@ -142,6 +145,7 @@ k_gemm(const float* __restrict__ A1, const float* __restrict__ A2, const float* 
     __syncthreads();
     const int ty = tid >> 4, tx = tid & 15;
     float acc[4][4] = {};
+#pragma unroll 8
     for (int k = 0; k < K; ++k) {
         const float4 a = *reinterpret_cast<const float4*>(&At[k * AT_LD + ty * 4]);
         const float4 bb = *reinterpret_cast<const float4*>(&Bt[k * 64 + tx * 4]);
@@ -169,9 +173,10 @@ __device__ __forceinline__ void split_range(int s, int S, int ntile, int& t0, in
     t1 = (int)((long long)(s + 1) * ntile / S);
 }
 
+template <int K>
 __global__ void __launch_bounds__(256)
 k_wgrad(const float* __restrict__ dY, const float* __restrict__ maskY, const float* __restrict__ X1,
-        const float* __restrict__ X2, const int V, const int K, float* __restrict__ part) {
+        const float* __restrict__ X2, const int V, float* __restrict__ part) {
     extern __shared__ __align__(16) unsigned char sm[];
     float* dZs = reinterpret_cast<float*>(sm);                // [GT][64]
     float* Xs = dZs + GT * 64;                                // [GT][K]
@@ -182,17 +187,20 @@ k_wgrad(const float* __restrict__ dY, const float* __restrict__ maskY, const flo
     float acc[4][8] = {};
     for (int t = t0; t < t1; ++t) {
         const int v0 = t * GT;
+#pragma unroll 8
         for (int idx = tid; idx < GT * 64; idx += 256) {
             const int v = v0 + (idx >> 6);
             float val = 0.f;
             if (v < V) { val = dY[(size_t)v * F + (idx & 63)]; if (!(maskY[(size_t)v * F + (idx & 63)] > 0.f)) val = 0.f; }
             dZs[idx] = val;
         }
+#pragma unroll 8
         for (int idx = tid; idx < GT * K; idx += 256) {
             const int vv = idx / K, k = idx % K, v = v0 + vv;
             Xs[idx] = v < V ? (k < 64 ? X1[(size_t)v * F + k] : X2[(size_t)v * F + k - 64]) : 0.f;
         }
         __syncthreads();
+#pragma unroll 4
         for (int vv = 0; vv < GT; ++vv) {
             const float4 a = *reinterpret_cast<const float4*>(&dZs[vv * 64 + to * 4]);
             const float4 b0 = *reinterpret_cast<const float4*>(&Xs[vv * K + tk * 4]);
@@ -387,9 +395,8 @@ int launch_mpnn_grad(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const in
     const int wsm128 = (GT * 64 + GT * 128) * 4, wsm64 = (GT * 64 + GT * 64) * 4;
     static bool attr = false;
     if (!attr) {
-        ECO_CUDA(cudaFuncSetAttribute(k_gemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gsm128));
-        ECO_CUDA(cudaFuncSetAttribute(k_gemm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gsm128));
-        ECO_CUDA(cudaFuncSetAttribute(k_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, wsm128));
+        ECO_CUDA(cudaFuncSetAttribute(k_gemm<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, gsm128));
+        ECO_CUDA(cudaFuncSetAttribute(k_wgrad<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsm128));
         attr = true;
     }
     const int vt = (V + GT - 1) / GT;
@@ -404,14 +411,14 @@ int launch_mpnn_grad(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const in
     ECO_LAUNCH_CHECK();
     k_adj<EDGE_FWD><<<agrid, ADJ_ROWS * F, asm_bytes, st>>>(*g, gidx, P(P_RP), P(P_RM), P(P_G), nullptr, norm_max);
     ECO_LAUNCH_CHECK();
-    k_gemm<false><<<vt, 256, gsm64, st>>>(P(P_G), nullptr, nullptr, V, 64, w->w_edge_feat, 64, 0, P(P_E), 1, 0);
+    k_gemm<false, 64><<<vt, 256, gsm64, st>>>(P(P_G), nullptr, nullptr, V, w->w_edge_feat, 64, 0, P(P_E), 1, 0);
     ECO_LAUNCH_CHECK();
     for (int l = 0; l < 3; ++l) {
         k_adj<AGG_FWD><<<agrid, ADJ_ROWS * F, asm_bytes, st>>>(*g, gidx, P(P_H0 + l), nullptr, P(P_AGG0 + l), nullptr, norm_max);
         ECO_LAUNCH_CHECK();
-        k_gemm<false><<<vt, 256, gsm128, st>>>(P(P_AGG0 + l), P(P_E), nullptr, V, 128, w->w_msg[l], 128, 0, P(P_M0 + l), 1, 0);
+        k_gemm<false, 128><<<vt, 256, gsm128, st>>>(P(P_AGG0 + l), P(P_E), nullptr, V, w->w_msg[l], 128, 0, P(P_M0 + l), 1, 0);
         ECO_LAUNCH_CHECK();
-        k_gemm<false><<<vt, 256, gsm128, st>>>(P(P_H0 + l), P(P_M0 + l), nullptr, V, 128, w->w_upd[l], 128, 0, P(P_H1 + l), 1, 0);
+        k_gemm<false, 128><<<vt, 256, gsm128, st>>>(P(P_H0 + l), P(P_M0 + l), nullptr, V, w->w_upd[l], 128, 0, P(P_H1 + l), 1, 0);
         ECO_LAUNCH_CHECK();
     }
     // ---- loss and backward ----
@@ -422,25 +429,25 @@ int launch_mpnn_grad(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const in
     for (int l = 2; l >= 0; --l) {
         float* gl = part + G_LAYER0 + l * G_LAYER_STRIDE;
         const float* Hout = P(P_H1 + l);
-        k_wgrad<<<S, 256, wsm128, st>>>(dcur, Hout, P(P_H0 + l), P(P_M0 + l), V, 128, gl + G_WUPD_OFF);
+        k_wgrad<128><<<S, 256, wsm128, st>>>(dcur, Hout, P(P_H0 + l), P(P_M0 + l), V, gl + G_WUPD_OFF);
         ECO_LAUNCH_CHECK();
-        k_gemm<true><<<vt, 256, gsm64, st>>>(dcur, nullptr, Hout, V, 64, w->w_upd[l], 128, 0, dnext, 0, 0);
+        k_gemm<true, 64><<<vt, 256, gsm64, st>>>(dcur, nullptr, Hout, V, w->w_upd[l], 128, 0, dnext, 0, 0);
         ECO_LAUNCH_CHECK();
-        k_gemm<true><<<vt, 256, gsm64, st>>>(dcur, nullptr, Hout, V, 64, w->w_upd[l], 128, 64, P(P_DM), 0, 0);
+        k_gemm<true, 64><<<vt, 256, gsm64, st>>>(dcur, nullptr, Hout, V, w->w_upd[l], 128, 64, P(P_DM), 0, 0);
         ECO_LAUNCH_CHECK();
-        k_wgrad<<<S, 256, wsm128, st>>>(P(P_DM), P(P_M0 + l), P(P_AGG0 + l), P(P_E), V, 128, gl);
+        k_wgrad<128><<<S, 256, wsm128, st>>>(P(P_DM), P(P_M0 + l), P(P_AGG0 + l), P(P_E), V, gl);
         ECO_LAUNCH_CHECK();
-        k_gemm<true><<<vt, 256, gsm64, st>>>(P(P_DM), nullptr, P(P_M0 + l), V, 64, w->w_msg[l], 128, 0, P(P_DAGG), 0, 0);
+        k_gemm<true, 64><<<vt, 256, gsm64, st>>>(P(P_DM), nullptr, P(P_M0 + l), V, w->w_msg[l], 128, 0, P(P_DAGG), 0, 0);
         ECO_LAUNCH_CHECK();
-        k_gemm<true><<<vt, 256, gsm64, st>>>(P(P_DM), nullptr, P(P_M0 + l), V, 64, w->w_msg[l], 128, 64, P(P_DE), 0, l < 2 ? 1 : 0);
+        k_gemm<true, 64><<<vt, 256, gsm64, st>>>(P(P_DM), nullptr, P(P_M0 + l), V, w->w_msg[l], 128, 64, P(P_DE), 0, l < 2 ? 1 : 0);
         ECO_LAUNCH_CHECK();
         k_adj<AGG_BWD><<<agrid, ADJ_ROWS * F, asm_bytes, st>>>(*g, gidx, P(P_DAGG), nullptr, dnext, nullptr, norm_max);
         ECO_LAUNCH_CHECK();
         float* t = dcur; dcur = dnext; dnext = t;
     }
-    k_wgrad<<<S, 256, wsm64, st>>>(P(P_DE), P(P_E), P(P_G), nullptr, V, 64, part + G_WEF);
+    k_wgrad<64><<<S, 256, wsm64, st>>>(P(P_DE), P(P_E), P(P_G), nullptr, V, part + G_WEF);
     ECO_LAUNCH_CHECK();
-    k_gemm<true><<<vt, 256, gsm64, st>>>(P(P_DE), nullptr, P(P_E), V, 64, w->w_edge_feat, 64, 0, P(P_DG), 0, 0);
+    k_gemm<true, 64><<<vt, 256, gsm64, st>>>(P(P_DE), nullptr, P(P_E), V, w->w_edge_feat, 64, 0, P(P_DG), 0, 0);
     ECO_LAUNCH_CHECK();
     k_adj<EDGE_BWD><<<agrid, ADJ_ROWS * F, asm_bytes, st>>>(*g, gidx, P(P_DG), nullptr, P(P_DRP), P(P_DRM), norm_max);
     ECO_LAUNCH_CHECK();
