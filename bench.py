@@ -327,7 +327,7 @@ def run_ours(args):
 
     # ---- env-step kernel alone at a size that is HBM- rather than launch-bound ---------------------------
     env_only = None
-    if rank == 0 and not args.skip_env_only:
+    if rank == 0 and not args.skip_env_only and world == 1:
         Bbig = 262144
         envb = engine.BatchedSpinSystem(gs, Bbig, T, 1.0 / n)
         envb.reset(spins=torch.from_numpy((2 * rng.integers(0, 2, size=(Bbig, n)) - 1).astype(np.int8)).cuda())
@@ -370,13 +370,13 @@ def run_ours(args):
                     "note": "B=4096 moves only %.1f MB per launch: launch-latency bound; see env_only" %
                             (bytes_env(n) * B / 1e6)}
         cpu = None
-        if not args.skip_cpu:
+        if not args.skip_cpu and world == 1:          # side numbers: rank 0 at N = 1 only (the other ranks would wait)
             v, cores, secs = cpu_reference_sample(J[0], wd, 32, 2 * n)
             cpu = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
                    "sample": "32 complete episodes (400 env steps each) of one BA-200 graph, batched like the "
                              "reference's test_network (%.1f s of CPU work)" % secs}
         dqn = None
-        if not args.skip_dqn:
+        if not args.skip_dqn and world == 1:
             try:
                 dqn = dqn_update_sample()
             except Exception as e:          # a side number must not cost the bench line
