@@ -165,6 +165,7 @@ class MPNNWeights:
         self.device = _require_cuda(device)
         self.tensors = []
         self.n_obs_in = 7
+        self.aliases = True        # every tensor IS the caller's storage (fp32, contiguous, on the device): see repack()
         for i, (k, shp) in enumerate(zip(STATE_DICT_KEYS, STATE_DICT_SHAPES)):
             if k not in state_dict:
                 raise KeyError("state_dict is missing %r (expected the reference MPNN layout, n_obs_in=7 or 1, 3 layers, "
@@ -178,6 +179,8 @@ class MPNNWeights:
                 t = torch.cat([t, torch.zeros(shp[0], 6, dtype=torch.float32, device=self.device)], dim=1).contiguous()
             if tuple(t.shape) != shp:
                 raise ValueError("%s has shape %s, expected %s" % (k, tuple(t.shape), shp))
+            src = state_dict[k]
+            self.aliases = self.aliases and torch.is_tensor(src) and src.data_ptr() == t.data_ptr()
             self.tensors.append(t)
         t = self.tensors
         self.c = Mpnn()
@@ -195,6 +198,13 @@ class MPNNWeights:
                 self._packed = torch.empty(nb, dtype=torch.uint8, device=self.device)
                 check(L.eco_mpnn_pack(C.byref(self.c), _ptr(self._packed), _stream()))
             self.c.packed = self._packed.data_ptr()
+
+    def repack(self):
+        """The caller changed the weights in place (an optimizer step on aliased storage): rebuild the bf16 hi/lo
+        operand copy the tensor-core kernels read; the fp32 pointers are the live parameters already."""
+        if self._packed is not None:
+            with torch.cuda.device(self.device):
+                check(lib().eco_mpnn_pack(C.byref(self.c), _ptr(self._packed), _stream()))
 
     def state_dict(self):
         return {k: t.clone() for k, t in zip(STATE_DICT_KEYS, self.tensors)}

@@ -115,7 +115,13 @@ class MPNN(nn.Module):
                 len(self.readout_layer.layers_readout) != 1:
             raise NotImplementedError("the CUDA kernels implement the reference configurations: n_obs_in=7 (ECO-DQN) or "
                                       "1 (S2V-DQN), 3 untied layers, 64 features, no hidden readout layer")
-        version = tuple(p._version for p in self.parameters()) + tuple(p.data_ptr() for p in self.parameters())
-        if self._engine_cache is None or self._engine_cache[0] != version:
-            self._engine_cache = (version, engine.MPNNWeights(self.state_dict(), device=device))
-        return self._engine_cache[1]
+        version = tuple(p._version for p in self.parameters())
+        ptrs = tuple(p.data_ptr() for p in self.parameters())
+        cache = self._engine_cache
+        if cache is not None and cache[1] == ptrs and cache[2].aliases:
+            if cache[0] != version:            # same storage, new values (optimizer step): only the packed copy is stale
+                cache[2].repack()
+                self._engine_cache = (version, ptrs, cache[2])
+        elif cache is None or cache[0] != version or cache[1] != ptrs:
+            self._engine_cache = (version, ptrs, engine.MPNNWeights(self.state_dict(), device=device))
+        return self._engine_cache[2]
