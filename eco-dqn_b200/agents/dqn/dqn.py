@@ -24,7 +24,7 @@ import torch.optim as optim
 from ... import engine, sharding
 from ... import _lib
 from ..._lib import lib, check
-from .utils import ReplayBuffer, TestMetric, set_global_seed
+from .utils import KernelAdam, ReplayBuffer, TestMetric, set_global_seed
 
 import ctypes as C
 
@@ -111,8 +111,13 @@ class DQN:
         self.target_network.load_state_dict(self.network.state_dict())
         for p in self.target_network.parameters():
             p.requires_grad = False
-        self.optimizer = optim.Adam(self.network.parameters(), lr=self.initial_learning_rate, eps=self.adam_epsilon,
-                                    weight_decay=self.weight_decay)
+        if self.network.engine_weights(self.device).aliases:
+            # Adam in one hand-written kernel over the live parameters (eco_mpnn_adam)
+            self.optimizer = KernelAdam(self.network, lr=self.initial_learning_rate, eps=self.adam_epsilon,
+                                        weight_decay=self.weight_decay)
+        else:
+            self.optimizer = optim.Adam(self.network.parameters(), lr=self.initial_learning_rate, eps=self.adam_epsilon,
+                                        weight_decay=self.weight_decay)
 
         self.evaluate = evaluate
         if test_envs in [None, [None]]:

@@ -64,3 +64,55 @@ class ReplayBuffer:
 
     def __len__(self):
         return self._size
+
+
+class KernelAdam:
+    """torch.optim.Adam for the MPNN's 12 tensors in one kernel launch (eco_mpnn_adam, csrc/mpnn_grad.cu): the update of
+    reference dqn.py:449.  Keeps the small part of the torch optimizer interface the trainer uses (`param_groups[i]['lr']`,
+    `zero_grad`, `step`).  The moments live in two flat fp32 buffers in state_dict order."""
+
+    def __init__(self, network, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        from ... import engine, _lib
+        self._engine, self._lib = engine, _lib
+        self.network = network
+        self.params = list(network.parameters())
+        self.param_groups = [{'lr': float(lr), 'betas': tuple(betas), 'eps': float(eps),
+                              'weight_decay': float(weight_decay), 'params': self.params}]
+        dev = self.params[0].device
+        self.exp_avg = torch.zeros(_lib.MPNN_N_PARAMS, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(_lib.MPNN_N_PARAMS, dtype=torch.float32, device=dev)
+        self.steps = 0
+
+    def zero_grad(self):
+        for p in self.params:
+            p.grad = None
+
+    def _flat_grad(self):
+        """The gradients as one flat buffer in state_dict order (no copy when they are views of eco_mpnn_grad's output)."""
+        named = dict(self.network.named_parameters())
+        grads = [named[k].grad for k in self._engine.STATE_DICT_KEYS]
+        base, off, flat_ok = grads[0], 0, True
+        for g in grads:
+            flat_ok = flat_ok and g.is_contiguous() and g.untyped_storage().data_ptr() == base.untyped_storage().data_ptr() \
+                and g.storage_offset() == base.storage_offset() + off
+            off += g.numel()
+        if flat_ok:
+            return torch.as_strided(base, (off,), (1,), base.storage_offset())
+        return torch.cat([g.reshape(-1) for g in grads])
+
+    @torch.no_grad()
+    def step(self):
+        import ctypes as C
+        eng, L = self._engine, self._lib.lib()
+        w = self.network.engine_weights(self.params[0].device)
+        if not w.aliases:
+            raise NotImplementedError("KernelAdam updates the live fp32 parameters in place; this network's engine weights "
+                                      "are copies (n_obs_in = 1)")
+        g = self.param_groups[0]
+        flat = self._flat_grad()
+        self.steps += 1
+        with torch.cuda.device(flat.device):
+            self._lib.check(L.eco_mpnn_adam(C.byref(w.c), eng._ptr(flat), eng._ptr(self.exp_avg), eng._ptr(self.exp_avg_sq),
+                                            self.steps, g['lr'], g['betas'][0], g['betas'][1], g['eps'], g['weight_decay'],
+                                            eng._stream()))
+        w.repack()                # the parameters changed behind autograd's version counters

@@ -373,6 +373,15 @@ int eco_mpnn_grad(const eco_graphs_t* g, const eco_mpnn_t* w, int32_t B, const i
                             (cudaStream_t)stream);
 }
 
+int eco_mpnn_adam(const eco_mpnn_t* w, const float* grad, float* exp_avg, float* exp_avg_sq, int32_t step, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, void* stream) {
+    ECO_CHECK_ARG(grad && exp_avg && exp_avg_sq, ECO_ERR_INVALID, "eco_mpnn_adam: null argument");
+    ECO_CHECK_ARG(step >= 1, ECO_ERR_INVALID, "eco_mpnn_adam: step counts from 1");
+    int rc = check_weights(w, "eco_mpnn_adam");
+    if (rc) return rc;
+    return launch_mpnn_adam(w, grad, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, weight_decay, (cudaStream_t)stream);
+}
+
 int eco_graph_aggregate(const eco_graphs_t* g, int32_t B, const int32_t* gidx, const float* x, int32_t use_abs,
                         float scale, float* out, void* stream) {
     ECO_CHECK_ARG(g && gidx && x && out && B >= 1, ECO_ERR_INVALID, "eco_graph_aggregate: bad argument");

@@ -12,6 +12,8 @@
 //   dE (summed over the layers), dM, dAGG, dG, dRP, dRM.
 // Weight gradients are reduced in two fixed-order stages (per-split partial sums, then one sum over the splits), so a
 // step is bit-reproducible.  The flat gradient has the 12 tensors in state_dict order.
+#include <cmath>
+
 #include "eco_common.cuh"
 
 namespace eco {
@@ -368,6 +370,28 @@ k_reduce(const float* __restrict__ part, const int S, float* __restrict__ grad, 
     else *loss = t;
 }
 
+// ---- Adam (torch.optim.Adam semantics: L2 weight decay added to the gradient, bias correction; dqn.py:212, 449) -----
+struct AdamTable { float* p[12]; int off[13]; };
+
+__global__ void __launch_bounds__(256)
+k_adam(const AdamTable t, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v, const float step_size,
+       const float bc2_sqrt, const float beta1, const float beta2, const float eps, const float weight_decay) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= N_PARAMS) return;
+    int k = 0;
+#pragma unroll
+    for (int j = 1; j < 12; ++j) k += i >= t.off[j];
+    float* p = t.p[k] + (i - t.off[k]);
+    const float w = *p;
+    const float g = fmaf(weight_decay, w, grad[i]);
+    const float mi = fmaf(beta1, m[i], (1.f - beta1) * g);            // exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = fmaf(beta2, v[i], (1.f - beta2) * g * g);        // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    *p = w - step_size * (mi / denom);
+}
+
 int n_splits(int B, int NP) {
     const int ntile = (B * NP + GT - 1) / GT;
     int S = ntile < NSPLIT_MAX ? ntile : NSPLIT_MAX;
@@ -454,6 +478,23 @@ int launch_mpnn_grad(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const in
     k_init_bwd<<<S, 256, 0, st>>>(*g, *w, B, xn, xg, P(P_H0), P(P_P), dcur, P(P_DRP), P(P_DRM), part);
     ECO_LAUNCH_CHECK();
     k_reduce<<<(N_PARAMS + 1 + 255) / 256, 256, 0, st>>>(part, S, grad, loss);
+    ECO_LAUNCH_CHECK();
+    return ECO_OK;
+}
+
+int launch_mpnn_adam(const eco_mpnn_t* w, const float* grad, float* m, float* v, int step, float lr, float beta1, float beta2,
+                     float eps, float weight_decay, cudaStream_t st) {
+    static const int counts[12] = {64 * 7, 63 * 8, 64 * 64, 64 * 128, 64 * 128, 64 * 128, 64 * 128, 64 * 128, 64 * 128, 64 * 64, 128, 1};
+    AdamTable t;
+    float* ptrs[12] = {(float*)w->w_init, (float*)w->w_edge, (float*)w->w_edge_feat, (float*)w->w_msg[0], (float*)w->w_upd[0],
+                       (float*)w->w_msg[1], (float*)w->w_upd[1], (float*)w->w_msg[2], (float*)w->w_upd[2], (float*)w->w_pool,
+                       (float*)w->w_read, (float*)w->b_read};
+    int off = 0;
+    for (int k = 0; k < 12; ++k) { t.p[k] = ptrs[k]; t.off[k] = off; off += counts[k]; }
+    t.off[12] = off;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    k_adam<<<(N_PARAMS + 255) / 256, 256, 0, st>>>(t, grad, m, v, (float)((double)lr / bc1), (float)sqrt(bc2), beta1, beta2, eps,
+                                                   weight_decay);
     ECO_LAUNCH_CHECK();
     return ECO_OK;
 }

@@ -231,6 +231,13 @@ int    eco_mpnn_grad(const eco_graphs_t* g, const eco_mpnn_t* w, int32_t B, cons
                      const float* targets_dev, int32_t loss_kind, float* loss_dev, float* grad_dev,
                      void* scratch_dev, void* stream);
 
+/* The optimizer step that follows (reference src/agents/dqn/dqn.py:212 `optim.Adam(...)`, :449 `self.optimizer.step()`):
+ * torch.optim.Adam semantics (weight_decay is added to the gradient, bias-corrected moments, no amsgrad) applied IN
+ * PLACE to the 12 fp32 tensors `w` points at.  grad_dev as written by eco_mpnn_grad; exp_avg_dev / exp_avg_sq_dev
+ * [ECO_MPNN_N_PARAMS] fp32 state (zero before the first step); step = 1, 2, ...  Re-run eco_mpnn_pack afterwards. */
+int    eco_mpnn_adam(const eco_mpnn_t* w, const float* grad_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int32_t step,
+                     float lr, float beta1, float beta2, float eps, float weight_decay, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Rollout: n_steps x [Q-eval + argmax -> env step] with no host round trip.  Replaces the hot loop of
  * __test_network_batched (reference experiments/utils.py:169-207) and, with ECO_POLICY_GREEDY, the Greedy
