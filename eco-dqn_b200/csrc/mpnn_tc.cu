@@ -206,7 +206,7 @@ __device__ __forceinline__ void issue_part(const Ctx& c, uint32_t acc_col, uint3
 // PACKED: K = packK >= 2 small graphs (NP <= 96) are processed side by side as ONE block-diagonal graph of K * NP <= 192
 // vertices ("pack"): the tensor part below does not know about it; only the inputs (per-vertex episode), the operand
 // images (diagonal blocks), feature 63 and the readout (pooling / argmax per episode) are per episode.
-template <bool PACKED>
+template <bool PACKED, bool TLINE>
 __global__ void __launch_bounds__(LAUNCH_THREADS, 1)
 mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int32_t* __restrict__ graph_idx,
                const float* __restrict__ xn, const float* __restrict__ xg, const float norm_max,
@@ -217,7 +217,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     int dbg_n = 0;
 #define TL(id)                                                                                           \
     do {                                                                                                 \
-        if (dbg != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && dbg_n < 1024)                \
+        if (TLINE && dbg != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && dbg_n < 1024)       \
             dbg[(threadIdx.x >> 5) * 1024 + dbg_n++] = ((unsigned long long)(id) << 48) | (clock64() & 0xFFFFFFFFFFFFull); \
     } while (0)
     __shared__ uint64_t bars[5];      // 0: edge contraction; 1, 2: linear MMAs of group 0 / 1; 3, 4: aggregation columns of group 0 / 1
@@ -833,8 +833,9 @@ int launch_mpnn_tc(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int3
     static bool attr_set = false;
     static int n_sm = 148;
     if (!attr_set) {
-        ECO_CUDA(cudaFuncSetAttribute(mpnn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-        ECO_CUDA(cudaFuncSetAttribute(mpnn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+        ECO_CUDA((cudaFuncSetAttribute(mpnn_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)));
+        ECO_CUDA((cudaFuncSetAttribute(mpnn_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)));
+        ECO_CUDA((cudaFuncSetAttribute(mpnn_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)));
         int dev = 0;
         ECO_CUDA(cudaGetDevice(&dev));
         ECO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
@@ -848,8 +849,10 @@ int launch_mpnn_tc(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int3
     static const bool timeline = getenv("ECO_TC_TIMELINE") != nullptr;
     if (timeline) ECO_CUDA(cudaMemsetAsync(scratch, 0, (NWARPS + 1) * 1024 * 8, st));
     unsigned long long* dbg = timeline ? (unsigned long long*)scratch : nullptr;
-    if (packed) mpnn_tc_kernel<true><<<grid, LAUNCH_THREADS, SM_TOTAL, st>>>(*g, *w, B, gidx, xn, xg, norm_max, q, actions, dbg, packK);
-    else mpnn_tc_kernel<false><<<grid, LAUNCH_THREADS, SM_TOTAL, st>>>(*g, *w, B, gidx, xn, xg, norm_max, q, actions, dbg, 1);
+    // (the clock trace of tools/tc_timeline.py is its own instantiation: the production kernels carry no trace code)
+    if (packed) mpnn_tc_kernel<true, false><<<grid, LAUNCH_THREADS, SM_TOTAL, st>>>(*g, *w, B, gidx, xn, xg, norm_max, q, actions, nullptr, packK);
+    else if (dbg) mpnn_tc_kernel<false, true><<<grid, LAUNCH_THREADS, SM_TOTAL, st>>>(*g, *w, B, gidx, xn, xg, norm_max, q, actions, dbg, 1);
+    else mpnn_tc_kernel<false, false><<<grid, LAUNCH_THREADS, SM_TOTAL, st>>>(*g, *w, B, gidx, xn, xg, norm_max, q, actions, nullptr, 1);
     prof_end(ECO_PROF_MPNN, st);
     ECO_LAUNCH_CHECK();
     return ECO_OK;
