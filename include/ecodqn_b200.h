@@ -82,9 +82,9 @@ typedef struct {
     float*   gain_tab;   /* [G, 2*NP+4]  entry [NP + k] = (float)((double)k / mlr) for k = -NP..NP: observable row 1 of a vertex whose
                                          flip changes the cut by k (valid for couplings in {-1,0,1}; spinsystem.py:490) */
     double*  dn_tab;     /* [G, 2*NP+4]  entry [NP + k] = (double)k / qn: the normalised score change of such a flip (spinsystem.py:394) */
-    uint16_t* tc_ops;    /* [G, 2, NP*NP] bf16 images of J and |J| in the tensor-core kernel's shared-memory operand
-                                         layout (8x8 core matrices), fetched per episode with one bulk copy each;
-                                         NULL when N > 208 (no tcgen05 path)                                  */
+    uint16_t* tc_ops;    /* [G, 2, NP*NP] bf16 images of J and |J| in the tensor-core kernels' shared-memory operand
+                                         layout (8x8 core matrices; slabs of 256 columns for NP > 256), fetched with one
+                                         bulk copy per episode (N <= 208) or per 64-row panel (larger graphs)     */
 } eco_graphs_t;
 
 size_t eco_graphs_workspace_bytes(int32_t G, int32_t N);
