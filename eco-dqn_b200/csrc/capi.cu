@@ -362,7 +362,7 @@ int eco_mpnn_grad(const eco_graphs_t* g, const eco_mpnn_t* w, int32_t B, const i
                   void* scratch, void* stream) {
     ECO_CHECK_ARG(g && gidx && xn && xg && actions && targets && loss && grad && scratch, ECO_ERR_INVALID,
                   "eco_mpnn_grad: null argument");
-    ECO_CHECK_ARG(B >= 1, ECO_ERR_INVALID, "eco_mpnn_grad: B must be >= 1");
+    ECO_CHECK_ARG(B >= 1 && B <= 65535, ECO_ERR_INVALID, "eco_mpnn_grad: B must be in 1..65535 (minibatch), got %d", B);
     ECO_CHECK_ARG(loss_kind == ECO_LOSS_MSE || loss_kind == ECO_LOSS_HUBER, ECO_ERR_INVALID, "eco_mpnn_grad: unknown loss %d",
                   loss_kind);
     ECO_CHECK_ARG(g->reserved & 1, ECO_ERR_UNSUPPORTED, "eco_mpnn_grad: needs couplings in {-1,0,1}");
