@@ -58,6 +58,15 @@ def allreduce_mean_grads(params):
     """Average the gradients of `params` over ranks with ONE collective: flatten (58 425 floats for the MPNN), all-reduce,
     scatter back in place.  Returns the flat averaged buffer."""
     params = [p for p in params if p.grad is not None]
+    # the gradient kernels (eco_mpnn_grad) leave the gradients as consecutive views of one buffer: reduce it in place
+    base, off, aliased = params[0].grad, 0, True
+    for p in params:
+        g = p.grad
+        aliased = aliased and g.is_contiguous() and g.untyped_storage().data_ptr() == base.untyped_storage().data_ptr() \
+            and g.storage_offset() == base.storage_offset() + off
+        off += g.numel()
+    if aliased:
+        return allreduce_mean_(torch.as_strided(base, (off,), (1,), base.storage_offset()))
     flat = torch.cat([p.grad.reshape(-1) for p in params])
     allreduce_mean_(flat)
     off = 0

@@ -40,6 +40,15 @@ def _worker(rank, world, port, n_total, q):
     dist.all_gather(others, torch.cat([g.reshape(-1) for g in local]))
     assert torch.allclose(flat, sum(others) / world)
     assert torch.allclose(torch.cat([p.grad.reshape(-1) for p in lin.parameters()]), flat)
+    # gradients that are consecutive views of one buffer (what eco_mpnn_grad leaves): reduced in place, no copies
+    buf = torch.arange(20, dtype=torch.float32) * (rank + 1)
+    lin[0].weight.grad = buf[0:12].view(4, 3)
+    lin[0].bias.grad = buf[12:16]
+    flat2 = sharding.allreduce_mean_grads(list(lin.parameters())[:2])
+    assert flat2.data_ptr() == buf.data_ptr() and flat2.numel() == 16
+    assert torch.allclose(buf[:16], torch.arange(16, dtype=torch.float32) * 1.5)
+    assert torch.allclose(buf[16:], torch.arange(16, 20, dtype=torch.float32) * (rank + 1))
+    assert torch.allclose(lin[0].bias.grad, torch.arange(12, 16, dtype=torch.float32) * 1.5)
     per_graph = sharding.best_per_graph(allc, torch.arange(n_total) % 3, 3)
     q.put((rank, lo, hi, allc.tolist(), alls[:, 0].tolist(), grad.tolist(), per_graph.tolist()))
     dist.destroy_process_group()
