@@ -7,9 +7,15 @@ gradient clipping), same schedules (dqn.py:467-487), same evaluation metric and 
   * acting: `n_envs` episodes step in lock-step on the device (n_envs = 1 is the reference's schedule); the greedy
     branch is the fused MPNN + argmax kernel, evaluated per environment like the reference's B = 1 forward;
   * replay: compact device-resident transitions (agents/dqn/utils.py) pointing into a device ring of graphs;
-  * update: target Q-values come from the CUDA forward kernels; the online forward/backward runs through PyTorch
-    autograd on the reference-compatible MPNN module; with several ranks the gradients are averaged with ONE
-    all-reduce over a flat buffer (NCCL over NVLink), then every rank applies the same Adam step.
+  * update: target Q-values come from the CUDA forward kernels; loss and all 12 gradient tensors come from the
+    hand-written forward/backward kernels (eco_mpnn_grad) and Adam is one kernel (eco_mpnn_adam).  Only a
+    user-supplied loss callable takes the autograd route through the PyTorch module.  With several ranks the
+    gradients are averaged with ONE all-reduce over the flat gradient buffer (NCCL over NVLink), then every rank
+    applies the same Adam step.
+
+Differences from the reference that a caller can see: `test_metric` defaults to TestMetric.BEST (the reference's
+default ENERGY_ERROR has no branch left in its evaluate_agent and always scores 0); BEST and FINAL are supported.
+`logging` is accepted and ignored (the reference's pickle Logger is out of scope; every script passes False).
 """
 import os
 import pickle
@@ -25,6 +31,7 @@ from ... import engine, sharding
 from ... import _lib
 from ..._lib import lib, check
 from .utils import KernelAdam, ReplayBuffer, TestMetric, set_global_seed
+from ...envs.utils import OptimisationTarget
 
 import ctypes as C
 
@@ -38,7 +45,7 @@ class DQN:
                  update_exploration=True, initial_exploration_rate=1, final_exploration_rate=0.1,
                  final_exploration_step=1000000, adam_epsilon=1e-8, loss="mse", save_network_frequency=10000,
                  network_save_path='network', evaluate=True, test_envs=None, test_episodes=20, test_frequency=10000,
-                 test_save_path='test_scores', test_metric=TestMetric.ENERGY_ERROR, logging=True, seed=None, n_envs=1):
+                 test_save_path='test_scores', test_metric=TestMetric.BEST, logging=True, seed=None, n_envs=1):
         self.device = engine._require_cuda()
         self.rank, self.world = sharding.world_info()
         self.double_dqn = double_dqn
@@ -75,18 +82,19 @@ class DQN:
             except KeyError:
                 raise ValueError("loss must be 'huber', 'mse' or a callable")
         if test_metric not in (TestMetric.BEST, TestMetric.FINAL):
-            raise NotImplementedError("test_metric must be TestMetric.BEST or TestMetric.FINAL on this path")
+            raise NotImplementedError("test_metric=%s: only TestMetric.BEST (default here) and TestMetric.FINAL are "
+                                      "evaluated on this path" % (test_metric,))
 
         if type(envs) != list:
             envs = [envs]
         self.envs = envs
-        if len(set(e.n_spins for e in envs)) != 1 or len(set(e.max_steps for e in envs)) != 1:
-            raise NotImplementedError("all training environments must share n_spins and max_steps")
+        self._check_uniform(envs, "training")
         if any(not e.reversible_spins for e in envs):
             raise NotImplementedError("irreversible (S2V-DQN) environments are outside the accelerated path")
         self.acting_in_reversible_spin_env = True
         self.n_spins, self.max_steps = envs[0].n_spins, envs[0].max_steps
         self.basin_reward = envs[0].basin_reward
+        self.min_cut = envs[0].optimisation_target == OptimisationTarget.MIN_CUT
         self.n_envs = int(n_envs)
 
         self.seed = random.randint(0, int(1e6)) if seed is None else seed      # dqn.py:187 (int() for Python 3.12)
@@ -124,6 +132,9 @@ class DQN:
             self.test_envs = self.envs
         else:
             self.test_envs = test_envs if type(test_envs) == list else [test_envs]
+        self._check_uniform(self.test_envs, "test")
+        if any(not e.reversible_spins for e in self.test_envs):
+            raise NotImplementedError("irreversible (S2V-DQN) environments are outside the accelerated path")
         self.test_episodes = int(test_episodes)
         self.test_frequency = test_frequency
         self.test_save_path = test_save_path
@@ -140,7 +151,7 @@ class DQN:
         first = [self._new_graph() for _ in range(E)]
         ring = np.zeros((self._ring_size, n, n), dtype=np.int8)
         ring[:] = engine.graphs_to_int8(first[0])[0]          # placeholder so that every slot holds a valid graph
-        self._graphs = engine.GraphSet(ring, device=self.device)
+        self._graphs = engine.GraphSet(ring, device=self.device, min_cut=self.min_cut)
         self._ring_pos = 0
         self._env = engine.BatchedSpinSystem(self._graphs, E, T, self.basin_reward)
         self.replay_buffer = ReplayBuffer(replay_buffer_size, self._env.NP, self.device)
@@ -148,6 +159,14 @@ class DQN:
         self._start_episodes(first)
 
     # ------------------------------------------------------------------ environment plumbing
+    @staticmethod
+    def _check_uniform(envs, what):
+        """One device batch steps every environment of a list: they must agree on what the kernels are configured with."""
+        for attr in ("n_spins", "max_steps", "optimisation_target", "basin_reward", "reversible_spins"):
+            if len(set(getattr(e, attr) for e in envs)) != 1:
+                raise NotImplementedError("all %s environments must share %s (got %s)" %
+                                          (what, attr, sorted(set(str(getattr(e, attr)) for e in envs))))
+
     def _new_graph(self):
         env = random.sample(self.envs, k=1)[0]                # get_random_env, dqn.py:242-248
         return np.asarray(env.gg.get())
@@ -343,9 +362,15 @@ class DQN:
         sharding.allreduce_mean_grads(self.network.parameters())
 
     def act(self, state, is_training_ready=True):
-        """epsilon-greedy for all lock-step environments (reference dqn.py:453-465, one environment there)."""
+        """epsilon-greedy (reference dqn.py:453-465).  One environment: the reference's own draws, in its order
+        (`random.uniform(0, 1) >= epsilon` -> greedy, else `np.random.randint(0, n)`), so a seeded run picks the
+        reference's actions.  Several lock-step environments: one device draw per environment."""
         xn, xg, graph = state
         E = xn.shape[0]
+        if E == 1:
+            if is_training_ready and random.uniform(0, 1) >= self.epsilon:
+                return self.predict(state)
+            return torch.tensor([np.random.randint(0, self.n_spins)], dtype=torch.int32, device=self.device)
         rand_actions = torch.randint(0, self.n_spins, (E,), device=self.device, generator=self._gen, dtype=torch.int32)
         if not is_training_ready:
             return rand_actions
@@ -380,23 +405,37 @@ class DQN:
 
     @torch.no_grad()
     def evaluate_agent(self, batch_size=None):
-        """Greedy-Q rollouts of `test_episodes` episodes on random test environments, all in one device batch
-        (reference dqn.py:514-602).  Returns (mean score, mean solution) for TestMetric.BEST / FINAL."""
+        """Greedy-Q rollouts of `test_episodes` episodes on random test environments (reference dqn.py:514-602).
+        Returns (mean score, mean solution) for TestMetric.BEST / FINAL.
+
+        The reference fills `batch_size` (default: the minibatch size) slots, steps them together -- so `norm.max()`
+        (mpnn.py:102) is the largest degree among the graphs of that group -- and refills when the group is done; per
+        episode it draws, in order, the environment (`random.sample`), the graph (`gg.get()`) and the spins
+        (`np.random.randint`).  Same draws, same groups here; every group is one device rollout."""
         k = self.test_episodes
-        envs = [random.sample(self.test_envs, k=1)[0] for _ in range(k)]
-        graphs = np.stack([np.asarray(e.gg.get()) for e in envs])
-        spins = np.stack([2 * np.random.randint(2, size=self.n_spins) - 1 for _ in range(k)])
-        gs = engine.GraphSet(graphs, device=self.device)
-        env = engine.BatchedSpinSystem(gs, k, envs[0].max_steps, envs[0].basin_reward)
-        env.reset(spins=spins, graph_idx=np.arange(k, dtype=np.int32))
-        env.rollout(self.network.engine_weights(self.device))
-        ep = env.episodes()
-        lb = gs.lb.cpu().numpy()
-        if self.test_metric == TestMetric.BEST:
-            scores, sols = ep["best_score"], ep["best_cut"].astype(np.float64)
-        else:
-            scores, sols = ep["score"], ep["cut"].astype(np.float64)
-        assert np.allclose(scores - np.abs(np.minimum(0, lb)), sols)
+        bsz = self.minibatch_size if batch_size is None else int(batch_size)
+        graphs, spins = [], []
+        for _ in range(k):
+            e = random.sample(self.test_envs, k=1)[0]                        # get_random_env, dqn.py:242-248
+            graphs.append(np.asarray(e.gg.get()))                            # env.reset(): spinsystem.py:188-198
+            spins.append(2 * np.random.randint(2, size=self.n_spins) - 1)    # spinsystem.py:294
+        t_env = self.test_envs[0]
+        gs = engine.GraphSet(np.stack(graphs), device=self.device,
+                             min_cut=t_env.optimisation_target == OptimisationTarget.MIN_CUT)
+        deg = gs.gstat[:, 0].cpu().numpy()
+        w = self.network.engine_weights(self.device)
+        scores, sols = np.zeros(k), np.zeros(k)
+        for g0 in range(0, k, bsz):
+            g1 = min(k, g0 + bsz)
+            env = engine.BatchedSpinSystem(gs, g1 - g0, t_env.max_steps, t_env.basin_reward)
+            env.reset(spins=np.stack(spins[g0:g1]), graph_idx=np.arange(g0, g1, dtype=np.int32))
+            env.rollout(w, norm_max=float(max(1, deg[g0:g1].max())))
+            ep = env.episodes()
+            if self.test_metric == TestMetric.BEST:
+                scores[g0:g1], sols[g0:g1] = ep["best_score"], ep["best_cut"]
+            else:
+                scores[g0:g1], sols[g0:g1] = ep["score"], ep["cut"]
+        self.last_test_scores, self.last_test_solutions = scores, sols
         return (np.mean(scores), np.mean(sols))
 
     def save(self, path='network.pth'):

@@ -59,7 +59,11 @@ class ReplayBuffer:
         self._size = min(self._size + e, self._capacity)
 
     def sample(self, batch_size, generator=None):
-        idx = torch.randint(0, self._size, (batch_size,), device=self.device, generator=generator)
+        """`batch_size` distinct transitions, like the reference's `random.sample(memory, batch_size)`
+        (dqn/utils.py:45-48: without replacement)."""
+        if batch_size > self._size:
+            raise ValueError("Sample larger than population or is negative")     # what random.sample raises
+        idx = torch.randperm(self._size, device=self.device, generator=generator)[:batch_size]
         return {k: getattr(self, k)[idx] for k in self.FIELDS}
 
     def __len__(self):

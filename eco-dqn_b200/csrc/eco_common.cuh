@@ -50,6 +50,26 @@ void prof_end(int kind, cudaStream_t st);
         eco::count_launch();                                                                      \
     } while (0)
 
+// Function attributes (opt-in dynamic shared memory) and the SM count belong to a DEVICE, not to the process: a
+// `static bool` guard would leave the second GPU of a process unconfigured.  `mask` is the caller's static bit set of
+// devices already configured; true on the first call per device.  (Entry points are not re-entrant: no locking.)
+static inline bool first_use_on_device(unsigned long long* mask) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (*mask & bit) return false;
+    *mask |= bit;
+    return true;
+}
+static inline int device_sm_count() {
+    static int n_sm[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& n = n_sm[dev & 63];
+    if (!n && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+    return n;
+}
+
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 static inline int padded_n(int n) { return round_up(n, 16); }

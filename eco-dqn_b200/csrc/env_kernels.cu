@@ -839,17 +839,14 @@ int launch_env_step(const eco_graphs_t* g, eco_env_t* env, int policy, const int
         else if (NP_ <= 128) ECO_SW(16);
         else if (NP_ <= 256) {
             if (policy == ECO_POLICY_ACTIONS && B_ >= 4096) {      // bulk-copy staged, persistent warps
-                static int n_sm = 0;
-                if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+                const int n_sm = device_sm_count();
                 // 16 lanes per stream (two streams per warp), 3-deep ring.  (8 lanes per stream with a 2-deep ring -- 64
                 // streams per SM -- was measured slower: 377 us vs 327 us.)
                 constexpr int TPE = 16, STAGES = 3, NSTREAMS = TMA_WARPS * (32 / TPE);
                 const size_t ring_bytes = (size_t)NSTREAMS * STAGES * (6 * NP_ + sizeof(eco_episode_t));
-                static bool attr = false;
-                if (!attr) {
+                static unsigned long long attr = 0;
+                if (first_use_on_device(&attr))
                     ECO_CUDA(cudaFuncSetAttribute(env_step_ring_kernel<TPE, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-                    attr = true;
-                }
                 long long blocks = (B_ + NSTREAMS - 1) / NSTREAMS;
                 if (blocks > (long long)n_sm * 4) blocks = (long long)n_sm * 4;
                 env_step_ring_kernel<TPE, STAGES><<<(unsigned)blocks, TMA_WARPS * 32, ring_bytes, st>>>(*g, *env, actions, reward, done, ha, hr, hs);

@@ -417,11 +417,10 @@ int launch_mpnn_grad(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const in
     const int S = n_splits(B, NP);
     const int gsm128 = (128 * AT_LD + 128 * 64) * 4, gsm64 = (64 * AT_LD + 64 * 64) * 4;
     const int wsm128 = (GT * 64 + GT * 128) * 4, wsm64 = (GT * 64 + GT * 64) * 4;
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr = 0;
+    if (first_use_on_device(&attr)) {
         ECO_CUDA(cudaFuncSetAttribute(k_gemm<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, gsm128));
         ECO_CUDA(cudaFuncSetAttribute(k_wgrad<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsm128));
-        attr = true;
     }
     const int vt = (V + GT - 1) / GT;
     const dim3 agrid((NP + ADJ_ROWS - 1) / ADJ_ROWS, B);

@@ -505,18 +505,14 @@ size_t mpnn_tcl_scratch_bytes(int B, int N) {
 
 int launch_mpnn_tcl(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int32_t* gidx, const float* xn,
                     const float* xg, float norm_max, float* q, int32_t* actions, void* scratch, cudaStream_t st) {
-    static bool attr = false;
-    static int n_sm = 148;
-    if (!attr) {
+    static unsigned long long attr = 0;
+    const int n_sm = device_sm_count();
+    if (first_use_on_device(&attr)) {
         ECO_CUDA(cudaFuncSetAttribute(tcl_contract_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CSMEM));
         ECO_CUDA(cudaFuncSetAttribute(tcl_contract_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CSMEM));
         ECO_CUDA(cudaFuncSetAttribute(tcl_linear_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, LSMEM));
         ECO_CUDA(cudaFuncSetAttribute(tcl_linear_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, LSMEM));
         ECO_CUDA(cudaFuncSetAttribute(tcl_linear_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, LSMEM));
-        int dev = 0;
-        ECO_CUDA(cudaGetDevice(&dev));
-        ECO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        attr = true;
     }
     unsigned char* buf = (unsigned char*)scratch;
     const int NP = g->NP, NB = NP >> 3;

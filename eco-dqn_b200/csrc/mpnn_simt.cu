@@ -387,12 +387,10 @@ size_t mpnn_simt_scratch_bytes(int B, int N) {
 int launch_mpnn_simt(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int32_t* gidx, const float* xn,
                      const float* xg, float norm_max, float* q, int32_t* actions, void* scratch,
                      cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_set = 0;
+    if (first_use_on_device(&attr_set))
         ECO_CUDA(cudaFuncSetAttribute(mpnn_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)sizeof(Smem)));
-        attr_set = true;
-    }
     transpose_weights_kernel<<<(128 * 64 + 255) / 256, 256, 0, st>>>(*w, (float*)scratch);
     ECO_LAUNCH_CHECK();
     prof_begin(ECO_PROF_MPNN, st);

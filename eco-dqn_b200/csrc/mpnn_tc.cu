@@ -830,16 +830,12 @@ int launch_mpnn_pack(const eco_mpnn_t* w, void* packed, cudaStream_t st) {
 
 int launch_mpnn_tc(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int32_t* gidx, const float* xn,
                    const float* xg, float norm_max, float* q, int32_t* actions, void* scratch, cudaStream_t st) {
-    static bool attr_set = false;
-    static int n_sm = 148;
-    if (!attr_set) {
+    static unsigned long long attr_set = 0;
+    const int n_sm = device_sm_count();
+    if (first_use_on_device(&attr_set)) {
         ECO_CUDA((cudaFuncSetAttribute(mpnn_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)));
         ECO_CUDA((cudaFuncSetAttribute(mpnn_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)));
         ECO_CUDA((cudaFuncSetAttribute(mpnn_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)));
-        int dev = 0;
-        ECO_CUDA(cudaGetDevice(&dev));
-        ECO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        attr_set = true;
     }
     const int packK = PACK_NPMAX / g->NP;                  // small graphs: several per CTA iteration
     const bool packed = packK >= 2 && B >= 2;

@@ -146,12 +146,11 @@ bool mpnn_tcl_supported(const eco_graphs_t* g) { return (g->reserved & 1) && g->
 int launch_tcl_contract(const eco_graphs_t* g, const int32_t* gidx, int B, const float* X1, int which1, const float* X2,
                         int which2, size_t x_stride, float* out, size_t out_stride, float scale, int edge,
                         float norm_max, cudaStream_t st) {
-    static bool attr = false;
+    static unsigned long long attr = 0;
     const int smem1 = XF_BYTES + 2 * OP_BYTES, smem2 = XF_BYTES + 4 * OP_BYTES;
-    if (!attr) {
+    if (first_use_on_device(&attr)) {
         ECO_CUDA(cudaFuncSetAttribute(graph_aggregate_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
         ECO_CUDA(cudaFuncSetAttribute(graph_aggregate_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
-        attr = true;
     }
     const int nslabs = (g->NP + SLAB - 1) / SLAB;
     const unsigned grid = (unsigned)((size_t)B * nslabs);

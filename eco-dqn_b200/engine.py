@@ -354,7 +354,11 @@ class BatchedSpinSystem:
 
     def rollout(self, weights=None, n_steps=None, policy="network", norm_max=None, record_history=False, impl=None):
         """n_steps x [Q-eval + argmax -> step] without host round trips (experiments/utils.py:169-207), or the
-        Greedy baseline with policy="greedy" (experiments/utils.py:218-227)."""
+        Greedy baseline with policy="greedy" (experiments/utils.py:218-227).
+
+        norm_max: the divisor of the degree feature (`norm / norm.max()`, mpnn.py:102).  None (default): every episode
+        is normalised by its OWN graph's max degree -- what the reference computes, because __test_network_batched
+        batches the attempts of one graph at a time.  0: the max degree over the whole graph set; > 0: that value."""
         n_steps = self.T - self.current_step if n_steps is None else int(n_steps)
         self._check_steppable(n_steps)
         pol = {"network": _lib.POLICY_NETWORK, "greedy": _lib.POLICY_GREEDY}[policy]
@@ -365,7 +369,7 @@ class BatchedSpinSystem:
                     torch.zeros(self.B, self.T, dtype=torch.float64, device=self.device))
         if pol == _lib.POLICY_NETWORK and weights is None:
             raise ValueError("network policy needs weights")
-        nm = float(norm_max) if norm_max is not None else 0.0
+        nm = float(norm_max) if norm_max is not None else -1.0
         with torch.cuda.device(self.device):
             check(lib().eco_rollout(C.byref(self.gs.c), C.byref(self.c),
                                     C.byref(weights.c) if weights is not None else None, n_steps, pol, nm,
@@ -414,14 +418,15 @@ class HostSession:
 
     def rollout(self, J_host, graph_idx_host, init_spins_host, best_cut_out, best_spins_out=None, policy="network",
                 norm_max=None):
-        """All arguments are HOST arrays/tensors (pinned recommended); synchronises the current stream."""
+        """All arguments are HOST arrays/tensors (pinned recommended); synchronises the current stream.
+        norm_max as in BatchedSpinSystem.rollout (None: per-episode graph, like the reference's per-graph batches)."""
         def hp(x):
             if x is None:
                 return C.c_void_p(0)
             return C.c_void_p(x.data_ptr()) if torch.is_tensor(x) else x.ctypes.data_as(C.c_void_p)
         pol = {"network": _lib.POLICY_NETWORK, "greedy": _lib.POLICY_GREEDY}[policy]
         check(lib().eco_session_rollout(self._h, hp(J_host), hp(graph_idx_host), hp(init_spins_host), pol,
-                                        float(norm_max) if norm_max is not None else 0.0, hp(best_cut_out),
+                                        float(norm_max) if norm_max is not None else -1.0, hp(best_cut_out),
                                         hp(best_spins_out), _stream()))
 
     def close(self):

@@ -92,3 +92,35 @@ def mpnn_forward(weights, obs):
     for layer in range(3):                                 # mpnn.py:68-72 (untied weights)
         h = update_layer(w, layer, h, e, norm, adj)
     return readout(w, h).squeeze(-1)
+
+
+@torch.no_grad()
+def mpnn_forward_blocked(weights, x, adj, rows_per_block=64, norm_max=None):
+    """mpnn_forward for ONE large graph without the [N, N, 63] intermediate of mpnn.py:90-98: the edge stage is
+    evaluated for `rows_per_block` target vertices i at a time with exactly the reference's per-row arithmetic
+    (concatenate [a_ij ; x_j], mask, linear, ReLU, sum over j), everything else as written.  Pinned against
+    mpnn_forward in tests/test_oracle_golden.py; used by the GPU parity tests at N = 1100 ... 2048 where the dense
+    tensor would need gigabytes per episode.
+
+    x: float32 [N, n_obs] vertex observations, adj: float32 [N, N].  Returns Q float32 [N]."""
+    w = weights if isinstance(next(iter(weights.values())), torch.Tensor) else as_torch_weights(weights)
+    x = torch.as_tensor(x, dtype=torch.float32)
+    adj = torch.as_tensor(adj, dtype=torch.float32)
+    N = adj.shape[0]
+    norm = degree_norm(adj.unsqueeze(0))[0]                # [N, 1]
+    h = F.relu(F.linear(x, w[KEYS[0]]))
+    emb = torch.empty(N, w[KEYS[1]].shape[0])
+    for i0 in range(0, N, rows_per_block):
+        a = adj[i0:i0 + rows_per_block]                    # [R, N]
+        ef = torch.empty(a.shape[0], N, 1 + x.shape[-1])
+        ef[..., 0] = a
+        ef[..., 1:] = x.unsqueeze(0)
+        ef.mul_((a != 0).unsqueeze(-1))
+        emb[i0:i0 + rows_per_block] = F.linear(ef, w[KEYS[1]]).relu_().sum(dim=1)
+    emb = emb / norm
+    nm = norm.max() if norm_max is None else torch.tensor(float(norm_max))
+    e = F.relu(F.linear(torch.cat([emb, norm / nm], dim=-1), w[KEYS[2]]))
+    h, e, norm, adj = h.unsqueeze(0), e.unsqueeze(0), norm.unsqueeze(0), adj.unsqueeze(0)
+    for layer in range(3):
+        h = update_layer(w, layer, h, e, norm, adj)
+    return readout(w, h).squeeze(-1)[0]

@@ -22,7 +22,7 @@ def golden_dir():
 def golden_cases():
     """ECO-DQN rollout cases (one graph, several attempts)."""
     return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith(("s2v_", "mincut_"))
-                  and f not in ("graphsets.npz", "generators.npz", "dqn_er40.npz"))
+                  and not f.startswith(("multi_", "dqn_")) and f not in ("graphsets.npz", "generators.npz"))
 
 
 def mincut_cases():

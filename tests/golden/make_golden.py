@@ -419,11 +419,145 @@ def dqn_case(graphs, net_path):
     print("wrote dqn_er40.npz, loss %.6g, dones %s" % (loss, batch[4][:, 0].tolist()))
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# round 2: multi-graph test_network, DQN.evaluate_agent, epsilon-greedy acting
+# ------------------------------------------------------------------------------------------------------------------
+def _quiet(fn, *a, **k):
+    with open(os.devnull, "w") as dn:
+        old = sys.stdout
+        sys.stdout = dn
+        try:
+            return fn(*a, **k)
+        finally:
+            sys.stdout = old
+
+
+def multi_graph_case(name, graphs, net, weights, seed, n_attempts):
+    """The reference's test_network over SEVERAL same-sized graphs with different maximum degrees: it batches the
+    attempts of one graph at a time, so `norm / norm.max()` (mpnn.py:102) is per graph."""
+    n = graphs[0].shape[0]
+    np.random.seed(seed)
+    res, raw, hist = _quiet(test_network, net, env_args_for(n), list(graphs), "cpu", 2, n_attempts=n_attempts,
+                            return_raw=True, return_history=True)
+    G = len(graphs)
+    out = dict(graphs=np.stack(graphs).astype(np.int8), seed=np.int32(seed), n_attempts=np.int32(n_attempts),
+               max_degree=np.array([(g != 0).sum(1).max() for g in graphs], dtype=np.int32),
+               init_spins=np.stack([np.array(raw["init spins"][j]) for j in range(G)]).astype(np.int8),
+               actions=np.array([[[int(a) for a in row[1:]] for row in hist["actions"][j]] for j in range(G)], dtype=np.int32),
+               rewards=np.array([[[float(x) for x in row[1:]] for row in hist["rewards"][j]] for j in range(G)], dtype=np.float64),
+               scores=np.array([[[float(x) for x in row] for row in hist["scores"][j]] for j in range(G)], dtype=np.float64),
+               cuts=np.array([raw["cuts"][j] for j in range(G)], dtype=np.float64),
+               sols=np.array([raw["sols"][j] for j in range(G)]).astype(np.int8),
+               greedy_cuts=np.array([raw["greedy cuts"][j] for j in range(G)], dtype=np.float64),
+               res_cut=np.array(res["cut"], dtype=np.float64), res_mean_cut=np.array(res["mean cut"], dtype=np.float64),
+               res_greedy_single=np.array(res["greedy (+1 init) cut"], dtype=np.float64),
+               res_greedy_rand=np.array(res["greedy (rand init) cut"], dtype=np.float64),
+               res_greedy_rand_mean=np.array(res["greedy (rand init) mean cut"], dtype=np.float64))
+    for k, v in weights.items():
+        out["w::" + k] = v
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print("wrote %s: max degrees %s, cuts %s" % (path, out["max_degree"].tolist(), out["res_cut"].tolist()))
+
+
+def dqn_eval_case(graphs, net_path):
+    """Reference DQN.evaluate_agent (dqn.py:514-602) and DQN.act (dqn.py:453-465) with seeded global RNGs."""
+    import random
+    import tempfile
+    import src.agents.dqn.dqn as dqn_mod
+    from src.agents.dqn.dqn import DQN
+    from src.agents.dqn.utils import TestMetric
+    from src.envs.utils import SetGraphGenerator
+    n, T = graphs[0].shape[0], 2 * graphs[0].shape[0]
+    gen = SetGraphGenerator(list(graphs), ordered=True)
+    log = []
+    orig_get = gen.get
+
+    def logged_get(*a, **k):
+        m = orig_get(*a, **k)
+        log.append([i for i in range(len(graphs)) if m is graphs[i]][0])
+        return m
+
+    gen.get = logged_get
+    env = ising_env.make("SpinSystem", gen, T, **env_args_for(n))
+    tmp = tempfile.mkdtemp()
+    out = {}
+    for metric, tag in ((TestMetric.BEST, "best"), (TestMetric.FINAL, "final")):
+        agent = DQN([env], lambda: MPNN(n_obs_in=7, n_layers=3, n_features=64, n_hid_readout=[], tied_weights=False),
+                    init_network_params=net_path, minibatch_size=4, test_episodes=6, logging=False, seed=3,
+                    test_save_path=os.path.join(tmp, "t"), network_save_path=os.path.join(tmp, "n"), test_metric=metric)
+        gen.i = 1
+        del log[:]
+        random.seed(77)
+        np.random.seed(77)
+        captured = []
+        real_mean = np.mean
+
+        def spy_mean(x, *a, **k):
+            captured.append(np.array(x, dtype=np.float64))
+            return real_mean(x, *a, **k)
+
+        dqn_mod.np.mean = spy_mean
+        try:
+            score, sol = agent.evaluate_agent()
+        finally:
+            dqn_mod.np.mean = real_mean
+        out[tag + "_score"], out[tag + "_solution"] = np.float64(score), np.float64(sol)
+        out[tag + "_scores"], out[tag + "_solutions"] = captured[0], captured[1]
+        out[tag + "_graph_order"] = np.array(log, dtype=np.int32)
+        print("evaluate_agent(%s): score %s solution %s graphs %s" % (tag, score, sol, log))
+
+    # epsilon-greedy acting: reference draws `random.uniform(0, 1)` then, when exploring, `np.random.randint(0, n)`
+    agent.epsilon = 0.5
+    gen.i = 0
+    random.seed(5)
+    np.random.seed(5)
+    obs = env.reset()
+    acts, spins0 = [], env.state[0, :n].copy()
+    for t in range(24):
+        a = agent.act(torch.FloatTensor(np.array(obs)).clone(), True)     # dqn.py:296
+        acts.append(int(a))
+        obs, _, _, _ = env.step(int(a))
+    out.update(graphs=np.stack(graphs).astype(np.int8), act_spins=spins0.astype(np.int8), act_actions=np.array(acts, dtype=np.int32),
+               act_epsilon=np.float64(0.5), act_graph=np.int32(0), seed_eval=np.int32(77), seed_act=np.int32(5),
+               gen_start=np.int32(1), minibatch_size=np.int32(4), test_episodes=np.int32(6))
+    sd = torch.load(net_path, map_location="cpu")
+    for k, v in sd.items():
+        out["w::" + k] = v.numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "dqn_eval_er40.npz"), **out)
+    print("wrote dqn_eval_er40.npz, act actions %s" % acts)
+
+
+def main_round2():
+    nets = os.path.join(REF, "experiments/pretrained_agent/networks/eco")
+    val = os.path.join(REF, "_graphs/validation")
+    er20 = _quiet(load_graph_set, os.path.join(val, "ER_20spin_p15_100graphs.pkl"))
+    er40 = _quiet(load_graph_set, os.path.join(val, "ER_40spin_p15_100graphs.pkl"))
+    net20, w20 = load_net(os.path.join(nets, "network_best_ER_20spin.pth"))
+    deg = [int((g != 0).sum(1).max()) for g in er20]
+    pick, seen = [], set()
+    for i, d in enumerate(deg):                 # four graphs with four different maximum degrees
+        if d not in seen:
+            seen.add(d)
+            pick.append(i)
+        if len(pick) == 4:
+            break
+    multi_graph_case("multi_er20", [er20[i] for i in pick], net20, w20, seed=21, n_attempts=4)
+    net40, w40 = load_net(os.path.join(nets, "network_best_ER_40spin.pth"))
+    deg = [int((g != 0).sum(1).max()) for g in er40]
+    pick = [int(np.argmin(deg)), int(np.argmax(deg)), 0]
+    multi_graph_case("multi_er40", [er40[i] for i in pick], net40, w40, seed=22, n_attempts=3)
+    dqn_eval_case([er40[i] for i in pick], os.path.join(nets, "network_best_ER_40spin.pth"))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "s2v":      # only the S2V cases (added later in round 1)
         main_s2v()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "mincut":   # only the Min-Cut cases (added later in round 1)
         main_mincut()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "round2":   # multi-graph test_network, evaluate_agent, act (round 2)
+        main_round2()
         sys.exit(0)
     main()

@@ -51,8 +51,13 @@ def test_test_network_matches_reference_frames(name):
     assert res["greedy (rand init) mean cut"][0] == float(z["res_greedy_rand_mean_cut"])
     assert np.array_equal(np.array(raw["greedy cuts"][0]), z["greedy_cuts"])
     acts = np.array([row[1:] for row in hist["actions"][0]])
-    same = (acts == z["actions"]).all(axis=1)
-    # trajectories are the reference's unless an fp32 near-tie flips an argmax; every identical one must agree exactly
+    # a trajectory may leave the reference's only at a step where the reference's own top Q-values are a near-tie
+    # (checked against the oracle's Q at the first differing step); every identical one must agree exactly
+    from test_gpu_round2 import assert_divergence_only_at_near_ties
+    from oracle.mpnn import weights_from_npz
+    b = float(z["basin_reward"])
+    same = assert_divergence_only_at_near_ties(z["J"], weights_from_npz(z), z["init_spins"], z["actions"], acts,
+                                               None if b < 0 else b)
     assert same.mean() >= 0.5, "too few identical trajectories: %s" % same
     rews = np.array([row[1:] for row in hist["rewards"][0]], dtype=np.float64)
     assert np.array_equal(rews[same].view(np.uint64), z["rewards"][same].view(np.uint64))

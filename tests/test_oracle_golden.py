@@ -164,3 +164,38 @@ def test_mincut_env_scalars_greedy_and_rollout(name):
     assert c1[0] == float(z["greedy_single_cut"]) and np.array_equal(s1[0], z["greedy_single_spins"])
     free = rollout(J, weights_from_npz(z), z["init_spins"], T, basin(z), min_cut=True)
     assert np.array_equal(free["actions"], z["actions"]) and np.array_equal(free["best_cut"], z["best_cut"])
+
+
+# ---- round 2 -------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["multi_er20", "multi_er40"])
+def test_oracle_reproduces_reference_test_network_over_several_graphs(name):
+    """The reference batches the attempts of ONE graph at a time, so the degree feature is normalised per graph
+    (mpnn.py:102); the oracle rollout, called per graph, follows the reference's actions / rewards / cuts bit for bit."""
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    w = weights_from_npz(z)
+    assert len(set(z["max_degree"].tolist())) > 1
+    for j, J in enumerate(z["graphs"]):
+        n = J.shape[0]
+        out = rollout(J.astype(np.float64), w, z["init_spins"][j], 2 * n, 1.0 / n)
+        assert np.array_equal(out["actions"], z["actions"][j])
+        assert np.array_equal(out["rewards"].view(np.uint64), z["rewards"][j].view(np.uint64))
+        assert np.array_equal(out["scores"], z["scores"][j])
+        assert np.array_equal(out["best_cut"], z["cuts"][j])
+        assert np.array_equal(out["best_spins"], z["sols"][j])
+        assert out["best_cut"].max() == z["res_cut"][j] and out["best_cut"].mean() == z["res_mean_cut"][j]
+
+
+def test_blocked_oracle_forward_equals_dense_forward():
+    """mpnn_forward_blocked (used for N > 500 on the GPU box) against the as-written dense forward."""
+    from oracle.mpnn import mpnn_forward_blocked
+    for name in ("er200_g0", "ba60_g2", "er20_g0"):
+        z = np.load(os.path.join(GOLDEN, name + ".npz"))
+        w = weights_from_npz(z)
+        J = z["J"].astype(np.float32)
+        for s in (0, z["obs"].shape[1] // 2):
+            rows = z["obs"][0, s]                                       # [7, n]
+            dense = mpnn_forward(w, np.concatenate([rows, J], axis=0)[None]).numpy()[0]
+            for rb in (7, 64):
+                blocked = mpnn_forward_blocked(w, rows.T, J, rows_per_block=rb).numpy()
+                assert np.abs(blocked - dense).max() <= 2e-6 * np.abs(dense).max(), (name, s, rb)
+            assert np.abs(dense - z["q"][0, s]).max() <= 1e-5 * np.abs(dense).max()
