@@ -58,6 +58,20 @@ def ba_graphs(count, n, m, seed):
     return out
 
 
+def er_graphs(count, n, p, seed):
+    """G(n, p) graphs with +-1 weights, like RandomErdosRenyiGraphGenerator with EdgeType.DISCRETE (reference
+    src/envs/utils.py:165-202: a symmetric Bernoulli(p) mask times a symmetric +-1 matrix, zero diagonal)."""
+    rng = np.random.default_rng(seed)
+    out = np.zeros((count, n, n), dtype=np.int8)
+    iu = np.triu_indices(n, 1)
+    for i in range(count):
+        keep = rng.random(len(iu[0])) < p
+        sign = (2 * rng.integers(0, 2, size=len(iu[0])) - 1).astype(np.int8)
+        out[i, iu[0], iu[1]] = keep * sign
+        out[i] += out[i].T
+    return out
+
+
 def load_weights():
     """The reference's pretrained eco/network_best_BA_200spin checkpoint, as recorded in the golden fixture (`w::<key>`)."""
     z = np.load(os.path.join(ROOT, "tests", "golden", "ba200_g0.npz"))

@@ -44,8 +44,9 @@ constexpr int SUBS = 2;            // warps per (group, TMEM lane quadrant): the
 constexpr int THREADS = 256 * SUBS;
 constexpr int GROUP_THREADS = 128 * SUBS;
 constexpr int NWARPS = THREADS / 32;
-constexpr int LAUNCH_THREADS = THREADS + 32;   // + warp 16: issues the N x N contractions (tcgen05.mma issue blocks while the
-                                               //   tensor queue is full -- 26 MMAs -- which must not hold up an epilogue warp)
+constexpr int ISSUERS = 3;                     // warp 16: the N x N contractions; warps 17, 18: the linear layers of group 0 / 1
+constexpr int LAUNCH_THREADS = THREADS + 32 * ISSUERS;   // (tcgen05.mma issue blocks while the tensor queue is full, which
+                                                         //  must not hold up an epilogue warp: the workers never issue)
 
 // ---- TMEM column map -------------------------------------------------------------------------------------
 constexpr uint32_t T_ACC0 = 0;       // 208 cols: aggregation / edge accumulator
@@ -71,7 +72,7 @@ constexpr int SM_MISC = SM_PP + MAXCHUNKS * SUBS * 64 * 4;   // c0, cross-warp r
 constexpr int SM_TOTAL = SM_MISC + 64 + 16 * 4 + 16 * 4;
 static_assert(NPMAX * NPMAX * 2 <= 2 * 128 * NPMAX * 2, "|A| must fit in the H+E region");
 static_assert(7 * NPMAX * 4 <= 128 * CHUNK * 2, "xf must fit in a chunk buffer");
-static_assert(SM_TOTAL + 128 <= 227 * 1024, "shared memory budget (dynamic + static)");
+static_assert(SM_TOTAL + 256 <= 227 * 1024, "shared memory budget (dynamic + static)");
 
 __global__ void mpnn_pack_kernel(const eco_mpnn_t w, uint32_t* __restrict__ out) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -93,8 +94,10 @@ struct Ctx {
     unsigned char* smem;
     uint32_t tmem;
     uint64_t* bar_all;     // completion of CTA-wide MMA batches (edge contraction, aggregation)
-    uint64_t* bar_grp;     // completion of this group's linear MMAs
-    uint32_t phase_all, phase_grp;
+    uint64_t* bar_grp;     // completion of this group's linear MMAs (B1)
+    uint64_t* bar_g2;      // second / third per-group MMA barrier (B2, B3): several batches of a group in flight at once
+    uint64_t* bar_g3;
+    uint32_t phase_all, phase_grp, phase_g2, phase_g3;
     int tid, warp, lane, q, grp, sub;
     int N, NP, NB;
 };
@@ -118,11 +121,6 @@ __device__ __forceinline__ void cta_stage_sync() {   // operands written by ever
     tc_fence_before();
     workers_sync();
 }
-__device__ __forceinline__ void grp_stage_sync(const Ctx& c) {   // same, among the 128 threads of one group
-    fence_proxy_async();
-    tc_fence_before();
-    asm volatile("bar.sync %0, %1;" ::"r"(c.grp + 1), "n"(GROUP_THREADS) : "memory");
-}
 __device__ __forceinline__ void wait_all(Ctx& c) {
     mbar_wait(c.bar_all, c.phase_all);
     c.phase_all ^= 1;
@@ -131,6 +129,16 @@ __device__ __forceinline__ void wait_all(Ctx& c) {
 __device__ __forceinline__ void wait_grp(Ctx& c) {
     mbar_wait(c.bar_grp, c.phase_grp);
     c.phase_grp ^= 1;
+    tc_fence_after();
+}
+__device__ __forceinline__ void wait_g2(Ctx& c) {
+    mbar_wait(c.bar_g2, c.phase_g2);
+    c.phase_g2 ^= 1;
+    tc_fence_after();
+}
+__device__ __forceinline__ void wait_g3(Ctx& c) {
+    mbar_wait(c.bar_g3, c.phase_g3);
+    c.phase_g3 ^= 1;
     tc_fence_after();
 }
 
@@ -220,16 +228,20 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         if (TLINE && dbg != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && dbg_n < 1024)       \
             dbg[(threadIdx.x >> 5) * 1024 + dbg_n++] = ((unsigned long long)(id) << 48) | (clock64() & 0xFFFFFFFFFFFFull); \
     } while (0)
-    __shared__ uint64_t bars[5];      // 0: edge contraction; 1, 2: linear MMAs of group 0 / 1; 3, 4: aggregation columns of group 0 / 1
+    __shared__ uint64_t bars[9];      // 0: edge contraction; 1, 2: linear MMAs of group 0 / 1 (B1); 3, 4: aggregation columns of
+                                      // group 0 / 1; 5, 6: B2 of group 0 / 1; 7, 8: B3 of group 0 / 1
     __shared__ uint64_t sig[2];       // workers -> contraction issuer: 0 edge operands ready, 1 layer inputs ready
+    __shared__ uint64_t gsig[2][2];   // the warps of group g -> its linear-layer issuer: operands of the next MMA batch are
+                                      // written (one arrival per warp; consecutive batches alternate between the two)
     __shared__ uint64_t bar_ops[2];   // arrival of the bulk copies of the adjacency operand images: 0 = A, 1 = |A|
     __shared__ uint32_t tmem_base_s;
     Ctx c;
-    c.smem = smem; c.phase_all = 0; c.phase_grp = 0;
+    c.smem = smem; c.phase_all = 0; c.phase_grp = 0; c.phase_g2 = 0; c.phase_g3 = 0;
     c.tid = threadIdx.x; c.lane = c.tid & 31;
     c.warp = __shfl_sync(0xffffffffu, c.tid >> 5, 0);     // warp-uniform: MMA issue code stays on the uniform datapath
-    c.q = c.warp & 3; c.sub = (c.warp >> 2) % SUBS; c.grp = c.warp / (4 * SUBS);
-    c.bar_all = &bars[0]; c.bar_grp = &bars[1 + c.grp];
+    c.q = c.warp & 3; c.sub = (c.warp >> 2) % SUBS;
+    c.grp = c.warp < NWARPS ? c.warp / (4 * SUBS) : (c.warp == NWARPS + 2 ? 1 : 0);
+    c.bar_all = &bars[0]; c.bar_grp = &bars[1 + c.grp]; c.bar_g2 = &bars[5 + c.grp]; c.bar_g3 = &bars[7 + c.grp];
     const int K = PACKED ? packK : 1;                     // episodes per pack
     const int NPs = g.NP, Ns = g.N;                       // per-episode sizes; NP / N below are the pack's
     c.NP = K * NPs; c.NB = c.NP >> 3; c.N = PACKED ? c.NP : g.N;
@@ -260,9 +272,10 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
 
     if (c.warp == 0) tmem_alloc(&tmem_base_s, 512);
     if (c.tid == 0) {
-        for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+        for (int i = 0; i < 9; ++i) mbar_init(&bars[i], 1);
         mbar_init(&bar_ops[0], 1); mbar_init(&bar_ops[1], 1);
         mbar_init(&sig[0], 1); mbar_init(&sig[1], 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&gsig[i >> 1][i & 1], 4 * SUBS);
         fence_mbar_init();
     }
     tc_fence_before();
@@ -280,7 +293,20 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     const int cs = c.grp == 0 ? 0 : chunk_split, ce = c.grp == 0 ? chunk_split : nchunks;
     int ncols0 = NP;                                      // columns of group 0's chunks
     if (chunk_split < nchunks) { int w_; chunk_span(chunk_split, nblocks, nchunks, ncols0, w_); }
-    uint32_t phase_half = 0;
+    uint32_t phase_half = 0, phase_other = 0;
+    // this group's (at most two) chunks: first column and width, fixed for the whole launch
+    const int nmine = (c.warp != NWARPS) ? ce - cs : 0;
+    int cA0 = 0, cAw = 0, cB0 = 0, cBw = 0;
+    if (nmine > 0) chunk_span(cs, nblocks, nchunks, cA0, cAw);
+    if (nmine > 1) chunk_span(cs + 1, nblocks, nchunks, cB0, cBw);
+    // worker warp -> its group's issuer: "my part of the operands of batch k is written" (smem: generic proxy, fenced for
+    // the async proxy; TMEM loads of the accumulator the batch overwrites have completed)
+    auto signal_issuer = [&](int k) {
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (c.lane == 0) mbar_arrive(&gsig[c.grp][k & 1]);
+    };
 
     // The adjacency operands come ready-made (graph_prepare.cu: bf16 images of J and |J| in this kernel's core-matrix
     // layout): one bulk copy each, issued as soon as the previous episode's last reader of the destination retired, so
@@ -353,9 +379,11 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         uint32_t sp0 = 0, sp1 = 0, op = 0;
         for (int b = blockIdx.x; b < npacks; b += gridDim.x) {
             mbar_wait(&sig[0], sp0); sp0 ^= 1u;
+            TL(50);
             mbar_wait(&bar_ops[0], op);               // A and |A| of this episode have landed (async proxy -> async proxy)
             mbar_wait(&bar_ops[1], op); op ^= 1u;
             tc_fence_after();
+            TL(51);
             if (elect_one()) {                        // edge contraction  S |A| + D A
                 const uint32_t idesc = instr_desc_bf16(128, NP, false, false);
                 const uint64_t bd_abs = smem_desc(smem_u32(sAbs), NB * 128, 128);
@@ -368,9 +396,11 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                 mma_commit(c.bar_all);
             }
             __syncwarp();
+            TL(52);
             for (int l = 0; l < 3; ++l) {
                 mbar_wait(&sig[1], sp1); sp1 ^= 1u;
                 tc_fence_after();
+                TL(53);
                 if (elect_one()) {                    // agg^T = H^T A  (both hi and lo rows in one M=128 chain), per half
                     const uint64_t ad = smem_desc(smem_u32(sH), 2048, 128);
                     const uint64_t bstep = (uint64_t)((2 * NB * 128) >> 4);
@@ -385,6 +415,69 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                     }
                 }
                 __syncwarp();
+                TL(54);
+            }
+        }
+    }
+    if (c.warp > NWARPS && nmine > 0) {
+        // ================= linear-layer issuer of group c.grp ================================================
+        // Follows the group's schedule (see stage 1 / stage 2 below): waits for the group's k-th signal, issues the batch,
+        // commits it to B1 / B2 / B3.  Signals alternate between gsig[g][0] and gsig[g][1]; a signal is never raised
+        // before the batch two signals earlier was committed and waited for, so one phase bit per barrier is enough.
+        uint32_t ph[2] = {0, 0};
+        auto wait_sig = [&](int k) {
+            mbar_wait(&gsig[c.grp][k & 1], ph[k & 1]);
+            ph[k & 1] ^= 1u;
+            tc_fence_after();
+        };
+        for (int b = blockIdx.x; b < npacks; b += gridDim.x) {
+            wait_sig(0);                                                                 // g(a) is in E^T[a]
+            if (elect_one()) { issue_part(c, T_ACC0 + cA0, T_WEF, sE, cA0 >> 3, cAw, false); mma_commit(c.bar_grp); }
+            __syncwarp();
+            if (nmine > 1) {
+                wait_sig(1);
+                if (elect_one()) { issue_part(c, T_ACC0 + cB0, T_WEF, sE, cB0 >> 3, cBw, false); mma_commit(c.bar_g2); }
+                __syncwarp();
+            }
+            for (int l = 0; l < 3; ++l) {
+                wait_sig(0);                                                             // S0: layer weights in TMEM
+                if (elect_one()) issue_part(c, acc1, T_WM + 32, sE, cA0 >> 3, cAw, false);   // M1e(a), ahead
+                __syncwarp();
+                wait_sig(1);                                                             // S1: agg(a) in the chunk buffer
+                if (elect_one()) {
+                    issue_part(c, acc1, T_WM, sT, 0, cAw, true);                         // M1a(a): += W_m[:, :64] agg
+                    mma_commit(c.bar_grp);                                               //   -> B1
+                    issue_part(c, T_ACC0 + cA0, T_WU, sH, cA0 >> 3, cAw, false);         // M2h(a): W_u[:, :64] h, ahead
+                    mma_commit(c.bar_g2);                                                //   -> B2
+                }
+                __syncwarp();
+                if (nmine > 1) {
+                    wait_sig(0);                                                         // S2: agg(b) in the chunk buffer
+                    if (elect_one()) {
+                        issue_part(c, T_ACC0 + cB0, T_WU, sH, cB0 >> 3, cBw, false);     // M2h(b), ahead
+                        mma_commit(c.bar_g3);                                            //   -> B3
+                    }
+                    __syncwarp();
+                }
+                wait_sig(1);                                                             // S3: m(a) in H^T[a]
+                if (elect_one()) {
+                    issue_part(c, T_ACC0 + cA0, T_WU + 32, sH, cA0 >> 3, cAw, true);     // M2m(a): += W_u[:, 64:] m
+                    mma_commit(c.bar_grp);                                               //   -> B1
+                    if (nmine > 1) {
+                        issue_part(c, acc1, T_WM + 32, sE, cB0 >> 3, cBw, false);        // M1(b) = W_m [agg ; e]
+                        issue_part(c, acc1, T_WM, sT, 0, cBw, true);
+                        mma_commit(c.bar_g2);                                            //   -> B2
+                    }
+                }
+                __syncwarp();
+                if (nmine > 1) {
+                    wait_sig(0);                                                         // S4: m(b) in H^T[b]
+                    if (elect_one()) {
+                        issue_part(c, T_ACC0 + cB0, T_WU + 32, sH, cB0 >> 3, cBw, true); // M2m(b)
+                        mma_commit(c.bar_grp);                                           //   -> B1
+                    }
+                    __syncwarp();
+                }
             }
         }
     }
@@ -602,7 +695,27 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             sttm_weights<64>(c, wu, T_WU);
         }
 
-        // ================= stage 1: h0 (CUDA cores), edge embeddings e =====================================
+        // ================= stage 1: edge embeddings e, h0 (CUDA cores) =====================================
+        // g = (S|A| + D A) / (2 deg) goes straight into the chunk's own columns of E^T (e overwrites it once W_ef g has
+        // retired) and W_ef g accumulates in the chunk's own -- just consumed -- columns of ACC0: no chunk buffer, no
+        // second accumulator, so both chunks of a group are in flight and h0 is computed under their MMAs.
+        {
+            for (int k = 0; k < nmine; ++k) {
+                const int c0 = k ? cB0 : cA0, width = k ? cBw : cAw;
+                // feature 63 = deg / deg_max   (mpnn.py:100-102)
+                epilogue(c, T_ACC0, c0, width, [&](int bc, float (&v)[8]) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int n = c0 + bc + 8 * (i >> 2) + 2 * (c.lane & 3) + (i & 1);
+                        const int f = 16 * c.q + (c.lane >> 2) + 8 * ((i >> 1) & 1);
+                        v[i] = f == 63 ? __fdividef(PACKED ? rdmaxv[n] : rdmax, rdeg[n]) : (0.5f * v[i]) * rdeg[n];
+                    }
+                    store_block(c, sE, c0 + bc, v);
+                });
+                signal_issuer(k);                   // -> W_ef g of this chunk (B1 / B2)
+                TL(10);
+            }
+        }
         {   // h0 = ReLU(W_init x): thread owns features fa, fb and 4 vertices of every 16-vertex block (epilogue mapping)
             for (int blk = c.grp * SUBS + c.sub; blk < nsteps_A; blk += 2 * SUBS) {
                 float v[8];
@@ -622,44 +735,48 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                 store_block(c, sH, 16 * blk, v);
             }
         }
-        tmem_st_wait();
+        tmem_st_wait();              // layer-0 weights (visible to the MMAs after the layer's first barrier)
         TL(8);
-        cta_stage_sync();            // xf (overlaying group 1's chunk buffer) is dead from here; weights visible to the MMAs
-        for (int ci = cs; ci < ce; ++ci) {
-            int c0, width;
-            chunk_span(ci, nblocks, nchunks, c0, width);
-            // g = (S|A| + D A) / (2 deg); feature 63 = deg / deg_max   (mpnn.py:100-102)
-            epilogue(c, T_ACC0, c0, width, [&](int bc, float (&v)[8]) {
+        {
+            for (int k = 0; k < nmine; ++k) {
+                const int c0 = k ? cB0 : cA0, width = k ? cBw : cAw;
+                TL(15);
+                if (k == 0) wait_grp(c); else wait_g2(c);
+                TL(12);
+                epilogue(c, T_ACC0, c0, width, [&](int bc, float (&v)[8]) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int n = c0 + bc + 8 * (i >> 2) + 2 * (c.lane & 3) + (i & 1);
-                    const int f = 16 * c.q + (c.lane >> 2) + 8 * ((i >> 1) & 1);
-                    v[i] = f == 63 ? __fdividef(PACKED ? rdmaxv[n] : rdmax, rdeg[n]) : (0.5f * v[i]) * rdeg[n];
-                }
-                store_block(c, sT, bc, v);
-            });
-            TL(10);
-            grp_stage_sync(c);
-            TL(11);
-            if (c.q == 0 && c.sub == 0) {
-                tc_fence_after();
-                if (elect_one()) { issue_part(c, acc1, T_WEF, sT, 0, width, false); mma_commit(c.bar_grp); }
-                __syncwarp();
+                    for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+                    store_block(c, sE, c0 + bc, v);
+                });
+                TL(13);
             }
-            wait_grp(c);
-            TL(12);
-            epilogue(c, acc1, 0, width, [&](int bc, float (&v)[8]) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
-                store_block(c, sE, c0 + bc, v);
-            });
-            TL(13);
         }
 
         // ================= stage 2: three message-passing layers (mpnn.py:114-120) ==========================
         // per chunk:  m = ReLU(W_m [agg ; e]) accumulates in the group's ACC1, h' = ReLU(W_u [h ; m]) accumulates in the
-        // chunk's own (already consumed) columns of ACC0.  The halves that do not depend on the running epilogue
-        // (W_m e, W_u h) are issued ahead, so they execute while the group's warps are busy in the epilogue.
+        // chunk's own (already consumed) columns of ACC0; m is written over the chunk's columns of H^T once W_u h and
+        // every aggregation MMA that reads them retired, so the chunk buffer only ever holds agg.  A group's two chunks
+        // a, b are interleaved -- the MMAs of one run under the epilogue of the other:
+        //   E1 agg(a)->T | M1a(a) M2h(a) | E2 agg(b)->T | M2h(b) | E3 m(a)->H[a] | M2m(a) M1(b) | E4 h'(a) | E5 m(b)->H[b]
+        //   | M2m(b) | E6 h'(b);   B1 / B2 / B3 = the group's three MMA barriers.
+        // The halves that do not depend on the running epilogue (W_m e, W_u h) are issued ahead.
+        auto epi_agg = [&](int c0, int width, bool wait_b1) {          // agg = (H^T A) / deg -> chunk buffer
+            bool waited = !wait_b1;
+            epilogue(c, T_ACC0, c0, width, [&](int bc, float (&v)[8]) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = v[i] * rdeg[c0 + bc + 8 * (i >> 2) + 2 * (c.lane & 3) + (i & 1)];
+                if (!waited) { wait_grp(c); waited = true; }           // the previous reader of the chunk buffer retired
+                store_block(c, sT, bc, v);
+            });
+            if (!waited) wait_grp(c);
+        };
+        auto epi_m = [&](int c0, int width) {                           // m = ReLU(acc1) -> the chunk's columns of H^T
+            epilogue(c, acc1, 0, width, [&](int bc, float (&v)[8]) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+                store_block(c, sH, c0 + bc, v);
+            });
+        };
         for (int l = 0; l < 3; ++l) {
             TL(20);
             cta_stage_sync();                   // every h / e column of the previous stage is written
@@ -675,16 +792,9 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                 tc_fence_before();
                 workers_sync();
             }
-            int ci = cs;
-            if (ci < ce && c.q == 0 && c.sub == 0) {          // W_m e-half of the first chunk does not depend on the aggregation
-                int c0, width;
-                chunk_span(ci, nblocks, nchunks, c0, width);
-                tc_fence_after();
-                if (elect_one()) issue_part(c, acc1, T_WM + 32, sE, c0 >> 3, width, false);
-                __syncwarp();
-            }
+            if (nmine > 0) signal_issuer(0);                // S0 -> M1e(a): the W_m e-half of the first chunk, ahead
             TL(22);
-            if (cs < ce) {                                    // this group's aggregation columns
+            if (nmine > 0) {                                  // this group's aggregation columns
                 mbar_wait(&bars[3 + c.grp], phase_half);
                 phase_half ^= 1u;
                 tc_fence_after();
@@ -692,106 +802,100 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             TL(23);
             // A has no reader left once the LAST half retired (the halves retire in order)
             if (l == 2 && c.tid == (chunk_split < nchunks ? THREADS / 2 : 0) && b + (int)gridDim.x < npacks) fetch_ops(0, b + gridDim.x);
-            while (ci < ce) {
-                int c0, width;
-                chunk_span(ci, nblocks, nchunks, c0, width);
-                epilogue(c, T_ACC0, c0, width, [&](int bc, float (&v)[8]) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = v[i] * rdeg[c0 + bc + 8 * (i >> 2) + 2 * (c.lane & 3) + (i & 1)];
-                    store_block(c, sT, bc, v);
-                });
-                TL(30);
-                grp_stage_sync(c);
-                TL(31);
-                if (c.q == 0 && c.sub == 0) {
-                    tc_fence_after();
-                    if (elect_one()) {
-                        issue_part(c, acc1, T_WM, sT, 0, width, true);                    // += W_m[:, :64] agg
-                        mma_commit(c.bar_grp);
-                        issue_part(c, T_ACC0 + c0, T_WU, sH, c0 >> 3, width, false);       // h-half of W_u, ahead
-                    }
-                    __syncwarp();
-                }
-                const int nxt = ci + 1;
-                TL(32);
-                wait_grp(c);
-                TL(33);
-                epilogue(c, acc1, 0, width, [&](int bc, float (&v)[8]) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
-                    store_block(c, sT, bc, v);
-                });
-                TL(34);
-                grp_stage_sync(c);
-                TL(35);
-                if (c.q == 0 && c.sub == 0) {
-                    tc_fence_after();
-                    if (elect_one()) {
-                        issue_part(c, T_ACC0 + c0, T_WU + 32, sT, 0, width, true);         // += W_u[:, 64:] m
-                        mma_commit(c.bar_grp);
-                        if (nxt < ce) {                                                  // next chunk's e-half, ahead
-                            int n0, nw;
-                            chunk_span(nxt, nblocks, nchunks, n0, nw);
-                            issue_part(c, acc1, T_WM + 32, sE, n0 >> 3, nw, false);
-                        }
-                    }
-                    __syncwarp();
-                }
-                TL(36);
-                wait_grp(c);
-                TL(37);
+            // h' of a chunk: next layer's H^T, or (last layer) the readout partials straight from the fp32 registers
+            auto epi_h = [&](int ci, int c0, int width) {
                 if (l < 2) {
                     epilogue(c, T_ACC0, c0, width, [&](int bc, float (&v)[8]) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
                         store_block(c, sH, c0 + bc, v);
                     });
-                } else {
-                    // readout partials straight from the fp32 registers (mpnn.py:143-159)
-                    // (pooled sums are kept per chunk and added in chunk order, so the result does not depend on
-                    //  which group happened to process which chunk)
-                    const float wa = __ldg(w.w_read + 64 + fa), wb = __ldg(w.w_read + 64 + fa + 8);
-                    float pool_a = 0.f, pool_b = 0.f;
-                    epilogue(c, T_ACC0, c0, width, [&](int bc, float (&v)[8]) {
-                        float qv[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {     // j: columns {0,1,8,9} + 2(lane&3)
-                            const int ia = 4 * (j >> 1) + (j & 1), ib = ia + 2;
-                            const int n = c0 + bc + 8 * (j >> 1) + 2 * (c.lane & 3) + (j & 1);
-                            const float ha = fmaxf(v[ia], 0.f), hb = fmaxf(v[ib], 0.f);
-                            if (vertex_ok(n)) { pool_a += ha; pool_b += hb; }
-                            qv[j] = fmaf(wa, ha, wb * hb);
-                        }
-                        if (PACKED) {             // a 16-vertex block lies inside one graph: its pooled partial on its own
-                            pool_a += __shfl_xor_sync(0xffffffffu, pool_a, 1); pool_a += __shfl_xor_sync(0xffffffffu, pool_a, 2);
-                            pool_b += __shfl_xor_sync(0xffffffffu, pool_b, 1); pool_b += __shfl_xor_sync(0xffffffffu, pool_b, 2);
-                            if ((c.lane & 3) == 0) {
-                                pp_blk[((c0 + bc) >> 4) * 64 + fa] = pool_a;
-                                pp_blk[((c0 + bc) >> 4) * 64 + fa + 8] = pool_b;
-                            }
-                            pool_a = 0.f; pool_b = 0.f;
-                        }
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            qv[j] += __shfl_xor_sync(0xffffffffu, qv[j], 4);
-                            qv[j] += __shfl_xor_sync(0xffffffffu, qv[j], 8);
-                            qv[j] += __shfl_xor_sync(0xffffffffu, qv[j], 16);
-                        }
-                        if ((c.lane >> 2) == 0) {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                qpart[c.q * NPMAX + c0 + bc + 8 * (j >> 1) + 2 * (c.lane & 3) + (j & 1)] = qv[j];
-                        }
-                    });
-                    pool_a += __shfl_xor_sync(0xffffffffu, pool_a, 1); pool_a += __shfl_xor_sync(0xffffffffu, pool_a, 2);
-                    pool_b += __shfl_xor_sync(0xffffffffu, pool_b, 1); pool_b += __shfl_xor_sync(0xffffffffu, pool_b, 2);
-                    if (!PACKED && (c.lane & 3) == 0) {
-                        ppart[(ci * SUBS + c.sub) * 64 + fa] = pool_a;
-                        ppart[(ci * SUBS + c.sub) * 64 + fa + 8] = pool_b;
-                    }
+                    return;
                 }
+                // (mpnn.py:143-159; pooled sums are kept per chunk and added in chunk order, so the result does not
+                //  depend on which group happened to process which chunk)
+                const float wa = __ldg(w.w_read + 64 + fa), wb = __ldg(w.w_read + 64 + fa + 8);
+                float pool_a = 0.f, pool_b = 0.f;
+                epilogue(c, T_ACC0, c0, width, [&](int bc, float (&v)[8]) {
+                    float qv[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {     // j: columns {0,1,8,9} + 2(lane&3)
+                        const int ia = 4 * (j >> 1) + (j & 1), ib = ia + 2;
+                        const int n = c0 + bc + 8 * (j >> 1) + 2 * (c.lane & 3) + (j & 1);
+                        const float ha = fmaxf(v[ia], 0.f), hb = fmaxf(v[ib], 0.f);
+                        if (vertex_ok(n)) { pool_a += ha; pool_b += hb; }
+                        qv[j] = fmaf(wa, ha, wb * hb);
+                    }
+                    if (PACKED) {             // a 16-vertex block lies inside one graph: its pooled partial on its own
+                        pool_a += __shfl_xor_sync(0xffffffffu, pool_a, 1); pool_a += __shfl_xor_sync(0xffffffffu, pool_a, 2);
+                        pool_b += __shfl_xor_sync(0xffffffffu, pool_b, 1); pool_b += __shfl_xor_sync(0xffffffffu, pool_b, 2);
+                        if ((c.lane & 3) == 0) {
+                            pp_blk[((c0 + bc) >> 4) * 64 + fa] = pool_a;
+                            pp_blk[((c0 + bc) >> 4) * 64 + fa + 8] = pool_b;
+                        }
+                        pool_a = 0.f; pool_b = 0.f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        qv[j] += __shfl_xor_sync(0xffffffffu, qv[j], 4);
+                        qv[j] += __shfl_xor_sync(0xffffffffu, qv[j], 8);
+                        qv[j] += __shfl_xor_sync(0xffffffffu, qv[j], 16);
+                    }
+                    if ((c.lane >> 2) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            qpart[c.q * NPMAX + c0 + bc + 8 * (j >> 1) + 2 * (c.lane & 3) + (j & 1)] = qv[j];
+                    }
+                });
+                pool_a += __shfl_xor_sync(0xffffffffu, pool_a, 1); pool_a += __shfl_xor_sync(0xffffffffu, pool_a, 2);
+                pool_b += __shfl_xor_sync(0xffffffffu, pool_b, 1); pool_b += __shfl_xor_sync(0xffffffffu, pool_b, 2);
+                if (!PACKED && (c.lane & 3) == 0) {
+                    ppart[(ci * SUBS + c.sub) * 64 + fa] = pool_a;
+                    ppart[(ci * SUBS + c.sub) * 64 + fa + 8] = pool_b;
+                }
+            };
+            if (nmine > 0) {
+                // ---- E1: agg(a) -> chunk buffer
+                epi_agg(cA0, cAw, false);
+                signal_issuer(1);                           // S1 -> M1a(a) (B1), M2h(a) (B2)
+                TL(30);
+                if (nmine > 1) {
+                    // ---- E2: agg(b) -> chunk buffer, once M1a(a) has read it (B1)
+                    epi_agg(cB0, cBw, true);
+                    signal_issuer(0);                       // S2 -> M2h(b) (B3)
+                    TL(31);
+                } else {
+                    wait_grp(c);                                                            // B1
+                }
+                // ---- E3: m(a) -> H^T[a]: W_u h (a) retired (B2) and so did every aggregation MMA (they read all of H^T)
+                wait_g2(c);
+                if (c.grp == 0 && chunk_split < nchunks) {
+                    mbar_wait(&bars[4], phase_other);
+                    phase_other ^= 1u;
+                }
+                TL(33);
+                epi_m(cA0, cAw);
+                signal_issuer(1);                           // S3 -> M2m(a) (B1), M1(b) (B2)
+                TL(34);
+                // ---- E4: h'(a)
+                wait_grp(c);                                                                // B1: M2m(a)
+                TL(37);
+                epi_h(cs, cA0, cAw);
                 TL(38);
-                ci = nxt;
+                if (nmine > 1) {
+                    // ---- E5: m(b) -> H^T[b]
+                    wait_g2(c);                                                             // B2: M1(b)
+                    wait_g3(c);                                                             // B3: M2h(b)
+                    TL(33);
+                    epi_m(cB0, cBw);
+                    signal_issuer(0);                       // S4 -> M2m(b) (B1)
+                    TL(35);
+                    // ---- E6: h'(b)
+                    wait_grp(c);
+                    TL(37);
+                    epi_h(cs + 1, cB0, cBw);
+                    TL(38);
+                }
             }
         }
         TL(40);
@@ -819,7 +923,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
 }  // namespace
 
 bool mpnn_tc_supported(const eco_graphs_t* g) { return g->N <= NPMAX && (g->reserved & 1) && g->tc_ops != nullptr; }
-size_t mpnn_tc_scratch_bytes(int, int) { return (NWARPS + 1) * 1024 * 8 + 256; }   // room for the optional debug timeline
+size_t mpnn_tc_scratch_bytes(int, int) { return (NWARPS + ISSUERS) * 1024 * 8 + 256; }   // room for the optional debug timeline
 size_t mpnn_tc_packed_bytes() { return (size_t)PK_WORDS * 4; }
 
 int launch_mpnn_pack(const eco_mpnn_t* w, void* packed, cudaStream_t st) {
@@ -843,7 +947,7 @@ int launch_mpnn_tc(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int3
     const int grid = units < n_sm ? units : n_sm;
     prof_begin(ECO_PROF_MPNN, st);
     static const bool timeline = getenv("ECO_TC_TIMELINE") != nullptr;
-    if (timeline) ECO_CUDA(cudaMemsetAsync(scratch, 0, (NWARPS + 1) * 1024 * 8, st));
+    if (timeline) ECO_CUDA(cudaMemsetAsync(scratch, 0, (NWARPS + ISSUERS) * 1024 * 8, st));
     unsigned long long* dbg = timeline ? (unsigned long long*)scratch : nullptr;
     // (the clock trace of tools/tc_timeline.py is its own instantiation: the production kernels carry no trace code)
     if (packed) mpnn_tc_kernel<true, false><<<grid, LAUNCH_THREADS, SM_TOTAL, st>>>(*g, *w, B, gidx, xn, xg, norm_max, q, actions, nullptr, packK);
