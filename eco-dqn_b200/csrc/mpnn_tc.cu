@@ -230,7 +230,8 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     } while (0)
     __shared__ uint64_t bars[9];      // 0: edge contraction; 1, 2: linear MMAs of group 0 / 1 (B1); 3, 4: aggregation columns of
                                       // group 0 / 1; 5, 6: B2 of group 0 / 1; 7, 8: B3 of group 0 / 1
-    __shared__ uint64_t sig[2];       // workers -> contraction issuer: 0 edge operands ready, 1 layer inputs ready
+    __shared__ uint64_t sig[2];       // workers -> contraction issuer: [1] layer inputs ready  ([0] unused)
+    __shared__ uint64_t sdbar[4];     // worker warps -> contraction issuer: blocks 4r .. 4r+3 of the edge operands S, D are in TMEM
     __shared__ uint64_t gsig[2][2];   // the warps of group g -> its linear-layer issuer: operands of the next MMA batch are
                                       // written (one arrival per warp; consecutive batches alternate between the two)
     __shared__ uint64_t bar_ops[2];   // arrival of the bulk copies of the adjacency operand images: 0 = A, 1 = |A|
@@ -276,6 +277,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         mbar_init(&bar_ops[0], 1); mbar_init(&bar_ops[1], 1);
         mbar_init(&sig[0], 1); mbar_init(&sig[1], 1);
         for (int i = 0; i < 4; ++i) mbar_init(&gsig[i >> 1][i & 1], 4 * SUBS);
+        for (int i = 0; i < 4; ++i) mbar_init(&sdbar[i], NWARPS);
         fence_mbar_init();
     }
     tc_fence_before();
@@ -378,24 +380,29 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         // ================= contraction issuer ===============================================================
         uint32_t sp0 = 0, sp1 = 0, op = 0;
         for (int b = blockIdx.x; b < npacks; b += gridDim.x) {
-            mbar_wait(&sig[0], sp0); sp0 ^= 1u;
-            TL(50);
             mbar_wait(&bar_ops[0], op);               // A and |A| of this episode have landed (async proxy -> async proxy)
             mbar_wait(&bar_ops[1], op); op ^= 1u;
-            tc_fence_after();
             TL(51);
-            if (elect_one()) {                        // edge contraction  S |A| + D A
-                const uint32_t idesc = instr_desc_bf16(128, NP, false, false);
-                const uint64_t bd_abs = smem_desc(smem_u32(sAbs), NB * 128, 128);
-                const uint64_t bd_a = smem_desc(smem_u32(sA), NB * 128, 128);
-                const uint64_t kstep = (uint64_t)((2 * NB * 128) >> 4);
-                for (int ks = 0; ks < nsteps_A; ++ks) {
-                    mma_ts(c.tmem + T_ACC0, c.tmem + T_S + 8 * ks, bd_abs + ks * kstep, idesc, ks > 0);
-                    mma_ts(c.tmem + T_ACC0, c.tmem + T_D + 8 * ks, bd_a + ks * kstep, idesc, true);
+            // edge contraction  S |A| + D A, k-step by k-step behind the workers that produce S and D: the MMAs of the
+            // blocks of round r run while round r + 1 is being computed
+            for (int r = 0; 4 * r < nsteps_A; ++r) {
+                mbar_wait(&sdbar[r], sp0);
+                tc_fence_after();
+                if (r == 0) TL(50);
+                if (elect_one()) {
+                    const uint32_t idesc = instr_desc_bf16(128, NP, false, false);
+                    const uint64_t bd_abs = smem_desc(smem_u32(sAbs), NB * 128, 128);
+                    const uint64_t bd_a = smem_desc(smem_u32(sA), NB * 128, 128);
+                    const uint64_t kstep = (uint64_t)((2 * NB * 128) >> 4);
+                    for (int ks = 4 * r; ks < min(4 * r + 4, nsteps_A); ++ks) {
+                        mma_ts(c.tmem + T_ACC0, c.tmem + T_S + 8 * ks, bd_abs + ks * kstep, idesc, ks > 0);
+                        mma_ts(c.tmem + T_ACC0, c.tmem + T_D + 8 * ks, bd_a + ks * kstep, idesc, true);
+                    }
+                    if (4 * r + 4 >= nsteps_A) mma_commit(c.bar_all);
                 }
-                mma_commit(c.bar_all);
+                __syncwarp();
             }
-            __syncwarp();
+            sp0 ^= 1u;
             TL(52);
             for (int l = 0; l < 3; ++l) {
                 mbar_wait(&sig[1], sp1); sp1 ^= 1u;
@@ -541,67 +548,75 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             workers_sync();               // qpart / pp_blk / tef may be reused
             return;
         }
-        float4 wpv[4] = {};
-        float wrf = 0.f;
-        if (c.tid < 256) {
-            const float4* wp = reinterpret_cast<const float4*>(w.w_pool + (c.tid >> 2) * 64 + (c.tid & 3) * 16);
+        // (not PACKED: see readout_pool / readout_q below)
+    };
+    // Not PACKED: the readout of an episode is split in two parts that each run inside ONE group, under waits of the NEXT
+    // episode that are idle anyway -- group 0 under its layer-0 aggregation, group 1 under its layer-1 aggregation (the CTA
+    // barrier on top of layer 1 orders the two).  Group-local named barrier: the other group is never held up.
+    auto grp_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(c.grp + 1), "n"(GROUP_THREADS) : "memory"); };
+    auto readout_pool = [&]() {           // group 0 (threads 0 .. 255): c0 = w_r[0:64] . ReLU(W_p mean_i h_i) as 8 warp partials
+        TL(60);
+        const float4* wp = reinterpret_cast<const float4*>(w.w_pool + (c.tid >> 2) * 64 + (c.tid & 3) * 16);
+        float4 wpv[4];
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) wpv[k4] = __ldg(wp + k4);
-            wrf = __ldg(w.w_read + (c.tid >> 2));
-        }
-        const float bread = __ldg(w.b_read);
+        for (int k4 = 0; k4 < 4; ++k4) wpv[k4] = __ldg(wp + k4);
+        const float wrf = __ldg(w.w_read + (c.tid >> 2));
         if (c.tid < 64) {                 // (the layer-2 epilogues of both groups are behind a CTA barrier already)
             float t = 0.f;
             for (int k = 0; k < nchunks * SUBS; ++k) t += ppart[k * 64 + c.tid];
             pooled[c.tid] = t / (float)N;
         }
-        workers_sync();
-        if (c.tid < 256) {   // p = W_p pooled: 4 lanes per output feature, then c0 = w_r[0:64] . ReLU(p) + b
-            const int part = c.tid & 3;
-            float p = 0.f;
+        grp_sync();
+        TL(61);
+        const int part = c.tid & 3;       // p = W_p pooled: 4 lanes per output feature
+        float p = 0.f;
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-                const float4 wv = wpv[k4];
-                const float* pv = pooled + part * 16 + 4 * k4;
-                p = fmaf(wv.x, pv[0], p); p = fmaf(wv.y, pv[1], p); p = fmaf(wv.z, pv[2], p); p = fmaf(wv.w, pv[3], p);
-            }
-            p += __shfl_xor_sync(0xffffffffu, p, 1);
-            p += __shfl_xor_sync(0xffffffffu, p, 2);
-            float t = part == 0 ? wrf * fmaxf(p, 0.f) : 0.f;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-            if (c.lane == 0) s_c0[1 + c.warp] = t;
+        for (int k4 = 0; k4 < 4; ++k4) {
+            const float4 wv = wpv[k4];
+            const float* pv = pooled + part * 16 + 4 * k4;
+            p = fmaf(wv.x, pv[0], p); p = fmaf(wv.y, pv[1], p); p = fmaf(wv.z, pv[2], p); p = fmaf(wv.w, pv[3], p);
         }
-        workers_sync();
-        float c0v = bread;                                  // every thread adds the 8 partials in the same order
+        p += __shfl_xor_sync(0xffffffffu, p, 1);
+        p += __shfl_xor_sync(0xffffffffu, p, 2);
+        float t = part == 0 ? wrf * fmaxf(p, 0.f) : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (c.lane == 0) s_c0[1 + c.warp] = t;
+        TL(62);
+    };
+    auto readout_q = [&](const int be) {  // group 1 (threads 256 .. 511): Q of every vertex, argmax (lowest index on ties)
+        TL(63);
+        float c0v = __ldg(w.b_read);                        // every thread adds the 8 partials in the same order
 #pragma unroll
         for (int ww = 0; ww < 8; ++ww) c0v += s_c0[1 + ww];
-        {
-            float bv = -INFINITY;
-            int bi = 0x7fffffff;
-            if (c.tid < N) {
-                const int i = c.tid;
-                bv = c0v + ((qpart[i] + qpart[NPMAX + i]) + (qpart[2 * NPMAX + i] + qpart[3 * NPMAX + i]));
-                bi = i;
-                if (q_out) q_out[(size_t)be * NP + i] = bv;
-            }
+        float bv = -INFINITY;
+        int bi = 0x7fffffff;
+        const int i = c.tid - GROUP_THREADS;
+        if (i < N) {
+            bv = c0v + ((qpart[i] + qpart[NPMAX + i]) + (qpart[2 * NPMAX + i] + qpart[3 * NPMAX + i]));
+            bi = i;
+            if (q_out) q_out[(size_t)be * NP + i] = bv;
+        }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (c.lane == 0) { red_val[c.warp - NWARPS / 2] = bv; red_idx[c.warp - NWARPS / 2] = bi; }
+        grp_sync();
+        if (c.warp == NWARPS / 2 && act_out) {              // the group's 8 warp results
+            bv = c.lane < NWARPS / 2 ? red_val[c.lane] : -INFINITY;
+            bi = c.lane < NWARPS / 2 ? red_idx[c.lane] : 0x7fffffff;
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {
                 const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
                 const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
                 if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
             }
-            if (c.lane == 0) { red_val[c.warp] = bv; red_idx[c.warp] = bi; }
+            if (c.lane == 0) act_out[be] = bi;
         }
-        workers_sync();
-        if (c.tid == 0 && act_out) {
-            float bv = red_val[0];
-            int bi = red_idx[0];
-            for (int ww = 1; ww < THREADS / 32; ++ww)
-                if (red_val[ww] > bv || (red_val[ww] == bv && red_idx[ww] < bi)) { bv = red_val[ww]; bi = red_idx[ww]; }
-            act_out[be] = bi;
-        }
-        workers_sync();                   // red_val / s_c0 / ppart may be reused
+        TL(64);
     };
     int last_b = -1;
 
@@ -650,7 +665,9 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         TL(3);
         // S = R+ + R-, D = R+ - R- with R+- = ReLU(P +- w0), P = W_x x  -> TMEM A operands (mpnn.py:89-100 factorised)
         {
-            for (int blk = c.grp * SUBS + c.sub; blk < nsteps_A; blk += 2 * SUBS) {
+            for (int r = 0; 4 * r < nsteps_A; ++r) {
+                const int blk = 4 * r + c.grp * SUBS + c.sub;
+                if (blk < nsteps_A) {
                 uint32_t sh[4], sl[4], dh[4], dl[4];
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
@@ -675,20 +692,22 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                 tmem_st_16x128b_x2(tmem_addr(c.tmem, 32 * c.q + 16, T_S + 8 * blk), sl);
                 tmem_st_16x128b_x2(tmem_addr(c.tmem, 32 * c.q, T_D + 8 * blk), dh);
                 tmem_st_16x128b_x2(tmem_addr(c.tmem, 32 * c.q + 16, T_D + 8 * blk), dl);
+                }
+                if (r == 0) sttm_weights<32>(c, wef, T_WEF);
+                tmem_st_wait();                       // -> issuer: this warp's share of round r is in TMEM
+                tc_fence_before();
+                __syncwarp();
+                if (c.lane == 0) mbar_arrive(&sdbar[r]);
             }
         }
-        sttm_weights<32>(c, wef, T_WEF);
         TL(4);
-        tmem_st_wait();
-        TL(5);
-        cta_stage_sync();
+        workers_sync();                               // W_ef (stored by all 16 warps) is complete before any group signals its issuer
         TL(6);
-        if (c.tid == 0) mbar_arrive(&sig[0]);      // -> issuer: S / D are in TMEM (the images of A / |A| arrive by bulk copy)
         {   // layer-0 weights: L2 -> registers while the edge contraction runs, registers -> TMEM once S / D are dead
             uint4 wm[64 / (8 * SUBS)], wu[64 / (8 * SUBS)];
             ldg_weights<64>(c, pk + PK_WM, wm);
             ldg_weights<64>(c, pk + PK_WU, wu);
-            if (last_b >= 0) readout(last_b);       // the previous episode's readout, under this episode's edge contraction
+            if (PACKED && last_b >= 0) readout(last_b);   // the previous pack's readout, under this pack's edge contraction
             wait_all(c);
             TL(7);
             sttm_weights<64>(c, wm, T_WM);
@@ -703,12 +722,19 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             for (int k = 0; k < nmine; ++k) {
                 const int c0 = k ? cB0 : cA0, width = k ? cBw : cAw;
                 // feature 63 = deg / deg_max   (mpnn.py:100-102)
+                const bool has63 = c.q == 3 && (c.lane >> 2) == 7;     // feature 63 = 16 q + lane/4 + 8: this thread's second row
                 epilogue(c, T_ACC0, c0, width, [&](int bc, float (&v)[8]) {
+                    const int n0 = c0 + bc + 2 * (c.lane & 3);
+                    const float2 r0 = *reinterpret_cast<const float2*>(rdeg + n0), r1 = *reinterpret_cast<const float2*>(rdeg + n0 + 8);
+                    const float rd[4] = {r0.x, r0.y, r1.x, r1.y};
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int n = c0 + bc + 8 * (i >> 2) + 2 * (c.lane & 3) + (i & 1);
-                        const int f = 16 * c.q + (c.lane >> 2) + 8 * ((i >> 1) & 1);
-                        v[i] = f == 63 ? __fdividef(PACKED ? rdmaxv[n] : rdmax, rdeg[n]) : (0.5f * v[i]) * rdeg[n];
+                    for (int i = 0; i < 8; ++i) v[i] = (0.5f * v[i]) * rd[2 * (i >> 2) + (i & 1)];
+                    if (has63) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {                   // v[2], v[3], v[6], v[7]: columns n0 + {0, 1, 8, 9}
+                            const int n = n0 + 8 * (j >> 1) + (j & 1);
+                            v[2 + 4 * (j >> 1) + (j & 1)] = __fdividef(PACKED ? rdmaxv[n] : rdmax, rd[j]);
+                        }
                     }
                     store_block(c, sE, c0 + bc, v);
                 });
@@ -763,8 +789,11 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         auto epi_agg = [&](int c0, int width, bool wait_b1) {          // agg = (H^T A) / deg -> chunk buffer
             bool waited = !wait_b1;
             epilogue(c, T_ACC0, c0, width, [&](int bc, float (&v)[8]) {
+                const int n0 = c0 + bc + 2 * (c.lane & 3);
+                const float2 r0 = *reinterpret_cast<const float2*>(rdeg + n0), r1 = *reinterpret_cast<const float2*>(rdeg + n0 + 8);
+                const float rd[4] = {r0.x, r0.y, r1.x, r1.y};
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = v[i] * rdeg[c0 + bc + 8 * (i >> 2) + 2 * (c.lane & 3) + (i & 1)];
+                for (int i = 0; i < 8; ++i) v[i] = v[i] * rd[2 * (i >> 2) + (i & 1)];
                 if (!waited) { wait_grp(c); waited = true; }           // the previous reader of the chunk buffer retired
                 store_block(c, sT, bc, v);
             });
@@ -793,6 +822,10 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                 workers_sync();
             }
             if (nmine > 0) signal_issuer(0);                // S0 -> M1e(a): the W_m e-half of the first chunk, ahead
+            if (!PACKED && last_b >= 0) {                   // the previous episode's readout, under the aggregation
+                if (l == 0 && c.grp == 0) readout_pool();
+                if (l == 1 && c.grp == 1) readout_q(last_b);
+            }
             TL(22);
             if (nmine > 0) {                                  // this group's aggregation columns
                 mbar_wait(&bars[3 + c.grp], phase_half);
@@ -912,7 +945,14 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         last_b = b;
         TL(41);
     }
-    if (c.warp < NWARPS && last_b >= 0) readout(last_b);
+    if (c.warp < NWARPS && last_b >= 0) {
+        if (PACKED) readout(last_b);
+        else {
+            if (c.grp == 0) readout_pool();
+            workers_sync();
+            if (c.grp == 1) readout_q(last_b);
+        }
+    }
 #undef TL
 
     tc_fence_before();
