@@ -488,6 +488,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             }
         }
     }
+    const float bread = __ldg(w.b_read);
     if (c.warp < NWARPS && (int)blockIdx.x < npacks) load_inputs(blockIdx.x);
 
     // ================= readout + argmax of one episode (mpnn.py:143-159; experiments/utils.py:57-66) =================
@@ -496,7 +497,6 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     auto readout = [&](const int be) {
         if (PACKED) {
             // be = pack.  All K episodes at once, every sum in a fixed order.
-            const float bread = __ldg(w.b_read);
             const int bpe = NPs >> 4;                     // 16-vertex blocks per episode
             for (int idx = c.tid; idx < K * 64; idx += THREADS) {          // pooled[e][f] = mean_i h_i[f]
                 const int e = idx >> 6, f = idx & 63;
@@ -586,7 +586,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     };
     auto readout_q = [&](const int be) {  // group 1 (threads 256 .. 511): Q of every vertex, argmax (lowest index on ties)
         TL(63);
-        float c0v = __ldg(w.b_read);                        // every thread adds the 8 partials in the same order
+        float c0v = bread;                                  // every thread adds the 8 partials in the same order
 #pragma unroll
         for (int ww = 0; ww < 8; ++ww) c0v += s_c0[1 + ww];
         float bv = -INFINITY;
