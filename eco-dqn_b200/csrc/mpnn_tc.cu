@@ -77,6 +77,11 @@ static_assert(SM_TOTAL + 256 <= 227 * 1024, "shared memory budget (dynamic + sta
 __global__ void mpnn_pack_kernel(const eco_mpnn_t w, uint32_t* __restrict__ out) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= PK_WORDS) return;
+    if (idx >= PK_WPT) {                 // W_p^T, plain fp32
+        const int k = (idx - PK_WPT) >> 6, f = (idx - PK_WPT) & 63;
+        out[idx] = __float_as_uint(w.w_pool[f * 64 + k]);
+        return;
+    }
     const float* src;
     int kw, rel, base;   // words per row, index within the matrix, matrix offset
     if (idx < PK_WM) { src = w.w_edge_feat; kw = 32; rel = idx; base = PK_WEF; }
@@ -369,8 +374,68 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             }
         }
     };
+    // ================= readout + argmax of one episode by ONE warp (mpnn.py:143-159; experiments/utils.py:57-66) ==========
+    // Not PACKED.  Reads only the pooled partial sums and the per-vertex partial dot products that the last layer's
+    // epilogues left in shared memory, which the next episode does not touch before ITS last layer: the contraction
+    // issuer runs it for the previous episode in the long gaps between two aggregations (part a after layer 0's, part b
+    // after layer 1's), so it costs the epilogue warps nothing.  The CTA's last episode is read out by warp 0 with the
+    // same code (same order of every sum: an episode's Q does not depend on where in the launch it was evaluated).
+    const float bread = __ldg(w.b_read);
+    auto readout_warp_a = [&]() -> float {            // c0 = w_r[0:64] . ReLU(W_p mean_i h_i) + b
+        TL(60);
+        float pa = 0.f, pb = 0.f;
+        for (int k = 0; k < nchunks * SUBS; ++k) { pa += ppart[k * 64 + c.lane]; pb += ppart[k * 64 + 32 + c.lane]; }
+        pooled[c.lane] = pa / (float)N;               // (in place: a lane only ever read its own two columns)
+        pooled[32 + c.lane] = pb / (float)N;
+        __syncwarp();
+        // p = W_p pooled from the transposed copy (rows k, k + 1 of W_p^T per 512-byte warp load): this lane accumulates
+        // outputs f = 4 (lane % 16) .. + 3 over the k of its parity, the two parities are added at the end
+        const float4* wt = reinterpret_cast<const float4*>(pk + PK_WPT) + c.lane;
+        const int f4 = 4 * (c.lane & 15), kpar = c.lane >> 4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+        for (int k0 = 0; k0 < 64; k0 += 32) {         // 16 x 16 bytes in flight per lane
+            float4 a[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) a[j] = __ldg(wt + (k0 / 2 + j) * 32);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float pv = pooled[k0 + 2 * j + kpar];
+                acc.x = fmaf(a[j].x, pv, acc.x); acc.y = fmaf(a[j].y, pv, acc.y);
+                acc.z = fmaf(a[j].z, pv, acc.z); acc.w = fmaf(a[j].w, pv, acc.w);
+            }
+        }
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 16); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
+        const float4 wr = __ldg(reinterpret_cast<const float4*>(w.w_read + f4));
+        float t = kpar == 0 ? fmaf(wr.x, fmaxf(acc.x, 0.f), fmaf(wr.y, fmaxf(acc.y, 0.f),
+                              fmaf(wr.z, fmaxf(acc.z, 0.f), wr.w * fmaxf(acc.w, 0.f)))) : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        TL(62);
+        return bread + t;
+    };
+    auto readout_warp_b = [&](const int be, const float c0v) {    // Q of every vertex, argmax (lowest index on ties)
+        TL(63);
+        float bv = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int i = c.lane; i < N; i += 32) {
+            const float qv = c0v + ((qpart[i] + qpart[NPMAX + i]) + (qpart[2 * NPMAX + i] + qpart[3 * NPMAX + i]));
+            if (q_out) q_out[(size_t)be * NP + i] = qv;
+            if (qv > bv) { bv = qv; bi = i; }         // (i ascending: the first maximum stays)
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (c.lane == 0 && act_out) act_out[be] = bi;
+        TL(64);
+    };
     if (c.warp == NWARPS) {
         // ================= contraction issuer ===============================================================
+        float c0_prev = 0.f;
         uint32_t sp0 = 0, sp1 = 0, op = 0;
         for (int b = blockIdx.x; b < npacks; b += gridDim.x) {
             mbar_wait(&bar_ops[0], op);               // A and |A| of this episode have landed (async proxy -> async proxy)
@@ -416,6 +481,10 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                 }
                 __syncwarp();
                 TL(54);
+                if (!PACKED && b != (int)blockIdx.x) {            // the previous episode's readout, in the gap before the next layer
+                    if (l == 0) c0_prev = readout_warp_a();
+                    if (l == 1) readout_warp_b(b - gridDim.x, c0_prev);
+                }
             }
         }
     }
@@ -481,7 +550,6 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             }
         }
     }
-    const float bread = __ldg(w.b_read);
     if (c.warp < NWARPS && (int)blockIdx.x < npacks) load_inputs(blockIdx.x);
 
     // ================= readout + argmax of one episode (mpnn.py:143-159; experiments/utils.py:57-66) =================
@@ -541,75 +609,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             workers_sync();               // qpart / pp_blk / tef may be reused
             return;
         }
-        // (not PACKED: see readout_pool / readout_q below)
-    };
-    // Not PACKED: the readout of an episode is split in two parts that each run inside ONE group, under waits of the NEXT
-    // episode that are idle anyway -- group 0 under its layer-0 aggregation, group 1 under its layer-1 aggregation (the CTA
-    // barrier on top of layer 1 orders the two).  Group-local named barrier: the other group is never held up.
-    auto grp_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(c.grp + 1), "n"(GROUP_THREADS) : "memory"); };
-    auto readout_pool = [&]() {           // group 0 (threads 0 .. 255): c0 = w_r[0:64] . ReLU(W_p mean_i h_i) as 8 warp partials
-        TL(60);
-        const float4* wp = reinterpret_cast<const float4*>(w.w_pool + (c.tid >> 2) * 64 + (c.tid & 3) * 16);
-        float4 wpv[4];
-#pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) wpv[k4] = __ldg(wp + k4);
-        const float wrf = __ldg(w.w_read + (c.tid >> 2));
-        if (c.tid < 64) {                 // (the layer-2 epilogues of both groups are behind a CTA barrier already)
-            float t = 0.f;
-            for (int k = 0; k < nchunks * SUBS; ++k) t += ppart[k * 64 + c.tid];
-            pooled[c.tid] = t / (float)N;
-        }
-        grp_sync();
-        TL(61);
-        const int part = c.tid & 3;       // p = W_p pooled: 4 lanes per output feature
-        float p = 0.f;
-#pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {
-            const float4 wv = wpv[k4];
-            const float* pv = pooled + part * 16 + 4 * k4;
-            p = fmaf(wv.x, pv[0], p); p = fmaf(wv.y, pv[1], p); p = fmaf(wv.z, pv[2], p); p = fmaf(wv.w, pv[3], p);
-        }
-        p += __shfl_xor_sync(0xffffffffu, p, 1);
-        p += __shfl_xor_sync(0xffffffffu, p, 2);
-        float t = part == 0 ? wrf * fmaxf(p, 0.f) : 0.f;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (c.lane == 0) s_c0[1 + c.warp] = t;
-        TL(62);
-    };
-    auto readout_q = [&](const int be) {  // group 1 (threads 256 .. 511): Q of every vertex, argmax (lowest index on ties)
-        TL(63);
-        float c0v = bread;                                  // every thread adds the 8 partials in the same order
-#pragma unroll
-        for (int ww = 0; ww < 8; ++ww) c0v += s_c0[1 + ww];
-        float bv = -INFINITY;
-        int bi = 0x7fffffff;
-        const int i = c.tid - GROUP_THREADS;
-        if (i < N) {
-            bv = c0v + ((qpart[i] + qpart[NPMAX + i]) + (qpart[2 * NPMAX + i] + qpart[3 * NPMAX + i]));
-            bi = i;
-            if (q_out) q_out[(size_t)be * NP + i] = bv;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-        }
-        if (c.lane == 0) { red_val[c.warp - NWARPS / 2] = bv; red_idx[c.warp - NWARPS / 2] = bi; }
-        grp_sync();
-        if (c.warp == NWARPS / 2 && act_out) {              // the group's 8 warp results
-            bv = c.lane < NWARPS / 2 ? red_val[c.lane] : -INFINITY;
-            bi = c.lane < NWARPS / 2 ? red_idx[c.lane] : 0x7fffffff;
-#pragma unroll
-            for (int o = 4; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-            }
-            if (c.lane == 0) act_out[be] = bi;
-        }
-        TL(64);
+        // (not PACKED: readout_warp_a / readout_warp_b above)
     };
     int last_b = -1;
 
@@ -815,10 +815,6 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                 workers_sync();
             }
             if (nmine > 0) signal_issuer(0);                // S0 -> M1e(a): the W_m e-half of the first chunk, ahead
-            if (!PACKED && last_b >= 0) {                   // the previous episode's readout, under the aggregation
-                if (l == 0 && c.grp == 0) readout_pool();
-                if (l == 1 && c.grp == 1) readout_q(last_b);
-            }
             TL(22);
             if (nmine > 0) {                                  // this group's aggregation columns
                 mbar_wait(&bars[3 + c.grp], phase_half);
@@ -940,11 +936,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     }
     if (c.warp < NWARPS && last_b >= 0) {
         if (PACKED) readout(last_b);
-        else {
-            if (c.grp == 0) readout_pool();
-            workers_sync();
-            if (c.grp == 1) readout_q(last_b);
-        }
+        else if (c.warp == 0) readout_warp_b(last_b, readout_warp_a());   // (behind the episode's last CTA barrier)
     }
 #undef TL
 
