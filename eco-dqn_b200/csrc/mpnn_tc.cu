@@ -505,7 +505,9 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             __syncwarp();
             if (nmine > 1) {
                 wait_sig(1);
-                if (elect_one()) { issue_part(c, T_ACC0 + cB0, T_WEF, sE, cB0 >> 3, cBw, false); mma_commit(c.bar_g2); }
+                // (chunk b accumulates in ACC1, which is free until the first layer: its epilogue runs under layer 0's aggregation,
+                //  which overwrites every column of ACC0)
+                if (elect_one()) { issue_part(c, acc1, T_WEF, sE, cB0 >> 3, cBw, false); mma_commit(c.bar_g2); }
                 __syncwarp();
             }
             for (int l = 0; l < 3; ++l) {
@@ -756,19 +758,21 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         }
         tmem_st_wait();              // layer-0 weights (visible to the MMAs after the layer's first barrier)
         TL(8);
-        {
-            for (int k = 0; k < nmine; ++k) {
-                const int c0 = k ? cB0 : cA0, width = k ? cBw : cAw;
-                TL(15);
-                if (k == 0) wait_grp(c); else wait_g2(c);
-                TL(12);
-                epilogue(c, T_ACC0, c0, width, [&](int bc, float (&v)[8]) {
+        // e = ReLU(W_ef g): chunk a here; chunk b at the top of layer 0, in the wait for the aggregation (nothing reads e(b)
+        // before the group's second batch of that layer)
+        auto epi_e = [&](uint32_t acc, int acc_col, int c0, int width) {
+            epilogue(c, acc, acc_col, width, [&](int bc, float (&v)[8]) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
-                    store_block(c, sE, c0 + bc, v);
-                });
-                TL(13);
-            }
+                for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+                store_block(c, sE, c0 + bc, v);
+            });
+        };
+        if (nmine > 0) {
+            TL(15);
+            wait_grp(c);
+            TL(12);
+            epi_e(T_ACC0, cA0, cA0, cAw);
+            TL(13);
         }
 
         // ================= stage 2: three message-passing layers (mpnn.py:114-120) ==========================
@@ -814,8 +818,16 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                 tc_fence_before();
                 workers_sync();
             }
+            if (l == 0 && nmine > 1) {                      // e(b), from the group's ACC1 (see stage 1)
+                wait_g2(c);
+                epi_e(acc1, 0, cB0, cBw);
+                TL(13);
+            }
             if (nmine > 0) signal_issuer(0);                // S0 -> M1e(a): the W_m e-half of the first chunk, ahead
             TL(22);
+            // readout weights of this thread's two features: requested before the wait (last layer only)
+            float wa = 0.f, wb = 0.f;
+            if (l == 2) { wa = __ldg(w.w_read + 64 + fa); wb = __ldg(w.w_read + 64 + fa + 8); }
             if (nmine > 0) {                                  // this group's aggregation columns
                 mbar_wait(&bars[3 + c.grp], phase_half);
                 phase_half ^= 1u;
@@ -836,7 +848,6 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                 }
                 // (mpnn.py:143-159; pooled sums are kept per chunk and added in chunk order, so the result does not
                 //  depend on which group happened to process which chunk)
-                const float wa = __ldg(w.w_read + 64 + fa), wb = __ldg(w.w_read + 64 + fa + 8);
                 float pool_a = 0.f, pool_b = 0.f;
                 epilogue(c, T_ACC0, c0, width, [&](int bc, float (&v)[8]) {
                     float qv[4];
