@@ -303,7 +303,7 @@ def dqn_update_sample(timesteps=3000, n_envs=16):
                     seed=5, test_metric=TestMetric.BEST, test_save_path=os.path.join(tmp, "s%d" % rank),
                     network_save_path=os.path.join(tmp, "n%d" % rank), n_envs=n_envs)
         acc = {"s": 0.0, "n": 0}
-        orig = agent.train_step
+        orig = agent._train_step_device      # what learn() calls: the update for a set of replay rows, loss kept on the device
 
         def timed(tr):
             torch.cuda.synchronize()
@@ -314,8 +314,8 @@ def dqn_update_sample(timesteps=3000, n_envs=16):
             acc["n"] += 1
             return out
 
-        agent.train_step = timed
-        agent.learn(timesteps=1000)          # warm-up: fills the replay, first updates
+        agent._train_step_device = timed
+        agent.learn(timesteps=1000)          # warm-up: fills the replay, first updates (captures the update's CUDA graph)
         acc["s"], acc["n"] = 0.0, 0
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -596,7 +596,12 @@ def run_ours(args):
         line.update(side)
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        # every rank leaves together; a hard exit instead of destroy_process_group(), which can block while a captured
+        # update (CUDA graph) still references the communicator
+        sys.stdout.flush()
+        dist.barrier()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 def main():

@@ -45,7 +45,8 @@ class DQN:
                  update_exploration=True, initial_exploration_rate=1, final_exploration_rate=0.1,
                  final_exploration_step=1000000, adam_epsilon=1e-8, loss="mse", save_network_frequency=10000,
                  network_save_path='network', evaluate=True, test_envs=None, test_episodes=20, test_frequency=10000,
-                 test_save_path='test_scores', test_metric=TestMetric.BEST, logging=True, seed=None, n_envs=1):
+                 test_save_path='test_scores', test_metric=TestMetric.BEST, logging=True, seed=None, n_envs=1,
+                 dp_mode="peer", cuda_graph=True):
         self.device = engine._require_cuda()
         self.rank, self.world = sharding.world_info()
         self.double_dqn = double_dqn
@@ -73,6 +74,11 @@ class DQN:
         self.logging = logging
         self._loss_kind = None                # ECO_LOSS_* when the gradient kernels can take the loss
         self._grad_scratch = None
+        if dp_mode not in ("peer", "nccl"):
+            raise ValueError("dp_mode must be 'peer' (gradient exchange over CUDA IPC peer memory, fused with Adam) or 'nccl'")
+        self.dp_mode = dp_mode                # how the ranks' gradients are averaged (world > 1)
+        self.cuda_graph = bool(cuda_graph)    # replay the update (TD target .. Adam .. re-pack) as one CUDA graph
+        self._cg = None
         if callable(loss):
             self.loss = loss
         else:
@@ -157,6 +163,24 @@ class DQN:
         self.replay_buffer = ReplayBuffer(replay_buffer_size, self._env.NP, self.device)
         self.replay_buffers = {n: self.replay_buffer}
         self._start_episodes(first)
+        # the update's batch normaliser (mpnn.py:102: the largest degree in the minibatch) stays on the device: the kernels
+        # read `*dmax` of the graph set they are given when norm_max == 0, so the update passes a copy of the graph-set
+        # struct whose dmax points at a one-float buffer it fills itself
+        self._nm_buf = torch.ones(1, dtype=torch.float32, device=self.device)
+        self._graphs_nm = type(self._graphs.c)()
+        C.memmove(C.byref(self._graphs_nm), C.byref(self._graphs.c), C.sizeof(self._graphs_nm))
+        self._graphs_nm.dmax = self._nm_buf.data_ptr()
+        self._fused_dp = False
+        if self.world > 1 and isinstance(self.optimizer, KernelAdam):
+            if self.dp_mode == "peer" and self.max_grad_norm is None:
+                def gather(mine):
+                    out = [torch.zeros(64, dtype=torch.uint8, device=self.device) for _ in range(self.world)]
+                    torch.distributed.all_gather(out, mine.to(self.device))
+                    return torch.stack(out)
+                self.optimizer.attach_peers(self.world, self.rank, gather)
+                self._fused_dp = True
+            else:
+                self.optimizer.grad_scale = 1.0 / self.world       # SUM all-reduce, the mean is taken inside the Adam kernel
 
     # ------------------------------------------------------------------ environment plumbing
     @staticmethod
@@ -207,15 +231,16 @@ class DQN:
         adj = self._graphs.J[graph.long(), :n, :n].to(torch.float32)
         return torch.cat([rows, adj], dim=1)
 
-    def _q_kernel(self, network, xn, xg, graph, norm_max, want_q=True):
+    def _q_kernel(self, network, xn, xg, graph, norm_max, want_q=True, graphs_c=None):
         """Q-values / argmax through the CUDA forward kernels for arbitrary (replayed) features."""
+        graphs_c = self._graphs.c if graphs_c is None else graphs_c
         B = xn.shape[0]
         w = network.engine_weights(self.device)
         q = torch.zeros(B, self._env.NP, dtype=torch.float32, device=self.device) if want_q else None
         act = torch.zeros(B, dtype=torch.int32, device=self.device)
         scratch = self._env._scratch_for(B)
         xn, xg, graph = xn.contiguous(), xg.contiguous(), graph.to(torch.int32).contiguous()
-        check(lib().eco_mpnn_forward(C.byref(self._graphs.c), C.byref(w.c), B, engine._ptr(graph), engine._ptr(xn),
+        check(lib().eco_mpnn_forward(C.byref(graphs_c), C.byref(w.c), B, engine._ptr(graph), engine._ptr(xn),
                                      engine._ptr(xg), float(norm_max), engine._ptr(q), engine._ptr(act),
                                      engine._ptr(scratch), self._env.mpnn_impl, engine._stream()))
         return (q[:, :self.n_spins] if want_q else None), act
@@ -246,6 +271,7 @@ class DQN:
 
             if env.current_step == self.max_steps:            # lock-step: every episode ends together
                 if verbose:
+                    losses_eps = [float(x) for x in losses_eps]
                     loss_str = "{:.2e}".format(np.mean(losses_eps)) if (is_training_ready and losses_eps) else "N/A"
                     print("timestep : {}, episode time: {}, score : {}, mean loss: {}, time : {} s".format(
                         timestep, env.current_step, np.round(float(self._scores.mean()), 3), loss_str,
@@ -256,11 +282,13 @@ class DQN:
 
             if is_training_ready:
                 for _ in range(self._crossings(t_before, timestep, self.update_frequency)):
-                    loss = self.train_step(self.replay_buffer.sample(self.minibatch_size, self._gen))
+                    # (the loss stays on the device: one host read per episode / at the end instead of one per update)
+                    loss = self._train_step_device(self.replay_buffer.sample_indices(self.minibatch_size, self._gen))
                     losses.append([timestep, loss])
                     losses_eps.append(loss)
                 if self._crossings(t_before, timestep, self.update_target_frequency):
                     self.target_network.load_state_dict(self.network.state_dict())
+                    self.target_network.engine_weights(self.device)      # re-pack now: a replayed graph would not
 
             if self._crossings(t_before + 1, timestep + 1, self.test_frequency) and self.evaluate and is_training_ready:
                 test_score, test_solution = self.evaluate_agent()
@@ -275,6 +303,9 @@ class DQN:
                 main, ext = os.path.splitext(self.network_save_path)
                 self.save(main + str(timestep) + (ext if ext else '.pth'))
 
+        if losses and torch.is_tensor(losses[0][1]):          # one device -> host copy for all the recorded losses
+            vals = torch.stack([l for _, l in losses]).reshape(-1).cpu().tolist()
+            losses = [[ts, v] for (ts, _), v in zip(losses, vals)]
         if self.rank == 0:
             path = self.test_save_path if os.path.splitext(self.test_save_path)[-1] else self.test_save_path + '.pkl'
             for p, obj in ((path, test_scores), (self.losses_save_path, losses), (self.solution_save_path, test_solutions)):
@@ -292,11 +323,44 @@ class DQN:
         return (t1 + period - 1) // period - (t0 + period - 1) // period
 
     def train_step(self, transitions):
-        """reference dqn.py:403-451 on a dict of compact transitions (see ReplayBuffer.FIELDS)."""
-        t = transitions
+        """reference dqn.py:403-451 on a dict of compact transitions (see ReplayBuffer.FIELDS); returns the loss as a float
+        like the reference (one host read: `learn` uses the device-side form below instead)."""
+        return float(self._update(transitions))
+
+    def _update(self, t):
+        """One update entirely on the device -- no host read: Double-DQN target through the forward kernels, loss and
+        gradients through eco_mpnn_grad, gradient mean over ranks + Adam (+ re-pack).  Returns the loss as a device tensor."""
         graph = t["graph"]
+        if self._loss_kind is None:
+            return self._update_autograd(t)
         with torch.no_grad():
             # the reference feeds the whole minibatch through the network: norm.max() is the batch's max degree
+            self._nm_buf.copy_(self._graphs.gstat[graph.long(), 0].max().clamp(min=1).to(torch.float32).reshape(1))
+            gc = self._graphs_nm                       # norm_max = 0 -> the kernels read *dmax = _nm_buf
+            if self.double_dqn:
+                _, greedy = self._q_kernel(self.network, t["xn_next"], t["xg_next"], graph, 0.0, want_q=False, graphs_c=gc)
+                q_tgt, _ = self._q_kernel(self.target_network, t["xn_next"], t["xg_next"], graph, 0.0, graphs_c=gc)
+                q_value_target = q_tgt.gather(1, greedy.long().unsqueeze(1))
+            else:
+                q_tgt, _ = self._q_kernel(self.target_network, t["xn_next"], t["xg_next"], graph, 0.0, graphs_c=gc)
+                q_value_target = q_tgt.max(1, True)[0]
+            if self.clip_Q_targets:
+                q_value_target = q_value_target.clamp(min=0)
+            td_target = t["reward"].unsqueeze(1) + (1 - t["done"].unsqueeze(1)) * self.gamma * q_value_target
+            # forward + backward of the online network in the hand-written kernels (eco_mpnn_grad, csrc/mpnn_grad.cu)
+            loss = self._grad_kernel(t["xn"], t["xg"], graph, 0.0, t["action"], td_target, graphs_c=gc)
+            if self.world > 1 and not self._fused_dp:
+                self._allreduce_grads()
+            if self.max_grad_norm is not None:
+                torch.nn.utils.clip_grad_norm_(self.network.parameters(), self.max_grad_norm)
+            self.optimizer.step()
+        return loss
+
+    def _update_autograd(self, t):
+        """A user-supplied loss callable: autograd through the PyTorch module (networks/mpnn.py::forward); its gradients
+        feed the same Adam kernel."""
+        graph = t["graph"]
+        with torch.no_grad():
             norm_max = float(self._graphs.gstat[graph.long(), 0].max().clamp(min=1).item())
             if self.double_dqn:
                 _, greedy = self._q_kernel(self.network, t["xn_next"], t["xg_next"], graph, norm_max, want_q=False)
@@ -308,27 +372,68 @@ class DQN:
             if self.clip_Q_targets:
                 q_value_target[q_value_target < 0] = 0
             td_target = t["reward"].unsqueeze(1) + (1 - t["done"].unsqueeze(1)) * self.gamma * q_value_target
-
-        if self._loss_kind is not None:
-            # forward + backward of the online network in the hand-written kernels (eco_mpnn_grad, csrc/mpnn_grad.cu)
-            loss = self._grad_kernel(t["xn"], t["xg"], graph, norm_max, t["action"], td_target)
-        else:
-            # a user-supplied loss callable: autograd through the PyTorch module
-            q_all = self.network(self._obs_from(t["xn"], t["xg"], graph))
-            if q_all.dim() == 1:
-                q_all = q_all.unsqueeze(0)
-            q_value = q_all.gather(1, t["action"].unsqueeze(1))
-            loss = self.loss(q_value, td_target, reduction='mean')
-            self.optimizer.zero_grad()
-            loss.backward()
+        q_all = self.network(self._obs_from(t["xn"], t["xg"], graph))
+        if q_all.dim() == 1:
+            q_all = q_all.unsqueeze(0)
+        q_value = q_all.gather(1, t["action"].unsqueeze(1))
+        loss = self.loss(q_value, td_target, reduction='mean')
+        self.optimizer.zero_grad()
+        loss.backward()
         if self.world > 1:
-            self._allreduce_grads()
+            sharding.allreduce_mean_grads(self.network.parameters())
         if self.max_grad_norm is not None:
             torch.nn.utils.clip_grad_norm_(self.network.parameters(), self.max_grad_norm)
-        self.optimizer.step()
-        return loss.item()
+        if isinstance(self.optimizer, KernelAdam):
+            scale, self.optimizer.grad_scale = self.optimizer.grad_scale, 1.0      # (already averaged)
+            dp, self.optimizer._dp = self.optimizer._dp, None
+            self.optimizer.step()
+            self.optimizer.grad_scale, self.optimizer._dp = scale, dp
+        else:
+            self.optimizer.step()
+        return loss.detach()
 
-    def _grad_kernel(self, xn, xg, graph, norm_max, action, td_target):
+    def _train_step_device(self, idx):
+        """The update for the replay rows `idx` (device int64 [minibatch]); with cuda_graph the captured update is replayed."""
+        if self._loss_kind is None or not self.cuda_graph or not isinstance(self.optimizer, KernelAdam):
+            return self._update(self.replay_buffer.gather(idx)).detach().reshape(())
+        if self._cg is None:
+            self._capture_update(idx)
+        self._g_idx.copy_(idx)
+        self.optimizer.sync_lr()
+        self._cg.replay()
+        return self._g_loss.clone().reshape(())
+
+    def _capture_update(self, idx):
+        """Capture `_update` on the rows of a static index buffer.  The two warm-up runs (allocations, lazy initialisation,
+        NCCL channels) are real updates, so parameters and optimizer state are saved before and put back after."""
+        opt = self.optimizer
+        self._g_idx = idx.clone()
+        saved = [p.detach().clone() for p in self.network.parameters()]
+        state = (opt.exp_avg.clone(), opt.exp_avg_sq.clone(), opt.step_dev.clone())
+        opt.sync_lr()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._update(self.replay_buffer.gather(self._g_idx))
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(self.device)
+
+        def restore():
+            with torch.no_grad():
+                for p, q in zip(self.network.parameters(), saved):
+                    p.copy_(q)
+                opt.exp_avg.copy_(state[0]); opt.exp_avg_sq.copy_(state[1]); opt.step_dev.copy_(state[2])
+            self.network.engine_weights(self.device).repack()
+        restore()
+        if self.world > 1:
+            torch.distributed.barrier()       # (the exchange epochs of eco_dp_adam count on their own: nothing to rewind)
+        self._cg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._cg):
+            self._g_loss = self._update(self.replay_buffer.gather(self._g_idx))
+        torch.cuda.synchronize(self.device)
+
+    def _grad_kernel(self, xn, xg, graph, norm_max, action, td_target, graphs_c=None):
         """loss and d loss / d weights of the regression step (dqn.py:436-447) through eco_mpnn_grad; the gradient
         lands in `p.grad` of every parameter (views of one flat buffer, state_dict order)."""
         B = xn.shape[0]
@@ -341,7 +446,7 @@ class DQN:
         xn, xg, graph = xn.contiguous(), xg.contiguous(), graph.to(torch.int32).contiguous()
         action = action.to(torch.int32).contiguous()
         target = td_target.reshape(-1).to(torch.float32).contiguous()
-        check(lib().eco_mpnn_grad(C.byref(self._graphs.c), C.byref(w.c), B, engine._ptr(graph), engine._ptr(xn),
+        check(lib().eco_mpnn_grad(C.byref(self._graphs.c if graphs_c is None else graphs_c), C.byref(w.c), B, engine._ptr(graph), engine._ptr(xn),
                                   engine._ptr(xg), float(norm_max), engine._ptr(action), engine._ptr(target),
                                   self._loss_kind, engine._ptr(loss), engine._ptr(flat), engine._ptr(self._grad_scratch),
                                   engine._stream()))
@@ -358,8 +463,10 @@ class DQN:
         return loss
 
     def _allreduce_grads(self):
-        """One collective per update over a flat buffer of the 12 gradient tensors (sharding.allreduce_mean_grads)."""
-        sharding.allreduce_mean_grads(self.network.parameters())
+        """dp_mode "nccl": one SUM all-reduce over the flat gradient buffer that eco_mpnn_grad wrote (the per-tensor
+        gradients are views of it); the division by the world size is folded into the Adam kernel (grad_scale)."""
+        flat = self.optimizer._flat_grad()
+        torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.SUM)
 
     def act(self, state, is_training_ready=True):
         """epsilon-greedy (reference dqn.py:453-465).  One environment: the reference's own draws, in its order

@@ -238,6 +238,32 @@ int    eco_mpnn_grad(const eco_graphs_t* g, const eco_mpnn_t* w, int32_t B, cons
 int    eco_mpnn_adam(const eco_mpnn_t* w, const float* grad_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int32_t step,
                      float lr, float beta1, float beta2, float eps, float weight_decay, void* stream);
 
+/* The same step with its state on the device, for updates captured in a CUDA graph: *step_dev (int32, 0 before the first
+ * step) is read as "steps done so far" and advanced by one; *lr_dev is the learning rate (the caller rewrites it when the
+ * schedule of dqn.py:467-487 moves); the gradient is multiplied by grad_scale first (1 / world after a sum all-reduce). */
+int    eco_mpnn_adam_dev(const eco_mpnn_t* w, const float* grad_dev, float* exp_avg_dev, float* exp_avg_sq_dev,
+                         int32_t* step_dev, const float* lr_dev, float beta1, float beta2, float eps, float weight_decay,
+                         float grad_scale, void* stream);
+
+/* Data-parallel form of the update (the reference is single-process: src/agents/dqn/dqn.py:403-451
+ * runs on one device).  One process per GPU of one NVSwitch box; every rank calls eco_dp_adam once per update with ITS
+ * gradient and gets the Adam step of the MEAN gradient applied to its parameters: the kernel publishes the gradient in a
+ * buffer shared through CUDA IPC, waits for the peers' (system-scope flags over NVLink), sums all ranks' gradients straight
+ * from peer memory in rank order (bit-identical on every rank) and updates -- all-reduce and optimizer in one launch.
+ *   eco_dp_create    allocates this rank's exchange region;  eco_dp_handle  its 64-byte IPC handle (exchange them with any
+ *   host-side all-gather);  eco_dp_open  maps the peers' regions ([world][64] handle bytes, own entry ignored).
+ *   *err_dev (int32, device) becomes non-zero if a peer never arrives (the kernel traps instead of hanging).
+ * Every rank must call eco_dp_adam the same number of times; step_dev / lr_dev as for eco_mpnn_adam_dev. */
+#define ECO_DP_HANDLE_BYTES 64
+typedef struct eco_dp eco_dp_t;
+int  eco_dp_create(eco_dp_t** out, int32_t world, int32_t rank);
+int  eco_dp_handle(const eco_dp_t* dp, void* handle64_host);
+int  eco_dp_open(eco_dp_t* dp, const void* handles_host);
+int  eco_dp_adam(eco_dp_t* dp, const eco_mpnn_t* w, const float* grad_dev, float* exp_avg_dev, float* exp_avg_sq_dev,
+                 int32_t* step_dev, const float* lr_dev, float beta1, float beta2, float eps, float weight_decay,
+                 int32_t* err_dev, void* stream);
+void eco_dp_destroy(eco_dp_t* dp);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Rollout: n_steps x [Q-eval + argmax -> env step] with no host round trip.  Replaces the hot loop of
  * __test_network_batched (reference experiments/utils.py:169-207) and, with ECO_POLICY_GREEDY, the Greedy

@@ -203,3 +203,85 @@ def test_kernel_adam_matches_torch_adam(weight_decay):
     w_live = a.engine_weights(dev)
     w_new = eng.MPNNWeights(a.state_dict(), device=dev)
     assert w_live.aliases and torch.equal(w_live._packed, w_new._packed)
+
+
+def _fill_replay(agent, timesteps):
+    """Act (randomly: training has not started) until `timesteps` transitions are stored; no update runs."""
+    start = agent.replay_start_size
+    agent.replay_start_size = 10 ** 9
+    agent.learn(timesteps=timesteps)
+    agent.replay_start_size = start
+
+
+def _opt_state(agent):
+    o = agent.optimizer
+    return ([p.detach().clone() for p in agent.network.parameters()], o.exp_avg.clone(), o.exp_avg_sq.clone(), o.step_dev.clone())
+
+
+def _restore(agent, st):
+    o = agent.optimizer
+    with torch.no_grad():
+        for p, q in zip(agent.network.parameters(), st[0]):
+            p.copy_(q)
+        o.exp_avg.copy_(st[1]); o.exp_avg_sq.copy_(st[2]); o.step_dev.copy_(st[3])
+    agent.network.engine_weights(agent.device).repack()
+
+
+def test_captured_update_equals_eager_update(tmp_path):
+    """The update replayed as one CUDA graph (TD target, eco_mpnn_grad, Adam with its step counter and learning rate on the
+    device, operand re-pack) gives bit for bit the parameters of the same updates launched eagerly, including across a
+    learning-rate change and a target-network sync."""
+    gs = np.load(os.path.join(GOLDEN, "graphsets.npz"))
+    agent = make_agent(tmp_path, list(gs["er20"][:6]), 40, n_envs=8, init_weight_std=0.05, minibatch_size=16,
+                       replay_buffer_size=1000, replay_start_size=64)
+    _fill_replay(agent, 320)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    idxs = [agent.replay_buffer.sample_indices(16, gen) for _ in range(6)]
+    st0 = _opt_state(agent)
+    tgt0 = {k: v.clone() for k, v in agent.target_network.state_dict().items()}
+
+    def run(step_fn):
+        _restore(agent, st0)
+        agent.target_network.load_state_dict(tgt0)
+        agent.target_network.engine_weights(agent.device)
+        out = []
+        for k, idx in enumerate(idxs):
+            if k == 2:
+                agent.optimizer.param_groups[0]['lr'] = 3e-4
+            if k == 4:
+                agent.target_network.load_state_dict(agent.network.state_dict())
+                agent.target_network.engine_weights(agent.device)
+            out.append(float(step_fn(idx)))
+        agent.optimizer.param_groups[0]['lr'] = 1e-4
+        return out, [p.detach().clone() for p in agent.network.parameters()], int(agent.optimizer.steps)
+
+    l_eager, p_eager, n_eager = run(lambda idx: agent._update(agent.replay_buffer.gather(idx)))
+    assert agent._cg is None
+    l_graph, p_graph, n_graph = run(agent._train_step_device)
+    assert agent._cg is not None and n_eager == n_graph == int(st0[3].item()) + 6
+    assert l_eager == l_graph
+    for a, b in zip(p_eager, p_graph):
+        assert torch.equal(a, b)
+    assert not torch.equal(p_eager[2], st0[0][2])
+
+
+def test_peer_adam_with_one_rank_equals_device_adam():
+    """eco_dp_adam with world = 1 (the exchange degenerates to this rank's own slot) equals eco_mpnn_adam_dev."""
+    from eco_dqn_b200.networks.mpnn import MPNN
+    from eco_dqn_b200.agents.dqn.utils import KernelAdam
+    torch.manual_seed(1)
+    nets = [MPNN().cuda(), MPNN().cuda()]
+    nets[1].load_state_dict(nets[0].state_dict())
+    opts = [KernelAdam(n, lr=1e-3, weight_decay=0.01) for n in nets]
+    opts[1].attach_peers(1, 0, lambda mine: mine.reshape(1, 64))
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    for step in range(4):
+        grads = [torch.randn(p.shape, device="cuda", generator=gen) * 10.0 ** (step - 2) for p in nets[0].parameters()]
+        for net, opt in zip(nets, opts):
+            for p, g in zip(net.parameters(), grads):
+                p.grad = g.clone()
+            opt.step()
+        for a, b in zip(nets[0].parameters(), nets[1].parameters()):
+            assert torch.equal(a, b)
+    assert opts[1].steps == 4 and int(opts[1].err_dev.item()) == 0
+    opts[1].close()
