@@ -7,24 +7,32 @@
 //
 //   orientation   D^T[feature, vertex] = W[feature, k] * X^T[k, vertex]   (linears:   A-operand = weights, TMEM)
 //                 D^T[feature, vertex] = H^T[feature, j] * A[j, vertex]   (aggregate: B-operand = adjacency, smem)
-//   precision     fp32-accurate on bf16 tensor cores: every activation / weight x is stored as hi = bf16(x),
-//                 lo = bf16(x - hi).  hi and lo rows are STACKED in the M dimension (128 = 64 features x {hi,lo}),
-//                 so one M=128 MMA chain yields both partial products and the split costs no extra instructions for
-//                 the aggregation (A in {-1,0,1} is exact) and 2 chains (4 products) for the linears.
+//   precision     every activation / weight x is stored as hi = bf16(x), lo = bf16(x - hi): two bf16 terms, about 16
+//                 mantissa bits per operand, fp32 accumulation (measured against the reference's fp32 Q-values: at most
+//                 0.03 of the parity tolerance 1e-3 |q| + 1e-4 max|q|; one fp16 / tf32 term per operand measured 10-20x
+//                 OVER it, tools/precision_study.py).  hi and lo rows are STACKED in the M dimension (128 = 64 features x
+//                 {hi,lo}), so one M=128 MMA chain yields both partial products and the split costs no extra
+//                 instructions for the aggregation (A in {-1,0,1} is exact) and 2 chains (4 products) for the linears.
 //                 Stacked row order r = 32q + 16s + t  <->  feature 16q + t, s in {hi, lo}: the two halves of a
 //                 feature sit in the same TMEM lane quadrant, so one warp adds them after two 16x256b loads.
 //   smem          adjacency bf16 (N x N, K-major core matrices), H^T and E^T stacked hi/lo (one copy serves as
-//                 K-major A-operand of the aggregation AND MN-major B-operand of the linears), two 48-vertex
-//                 chunk buffers.  No swizzle: 8x16-byte core matrices, written conflict-free by the epilogues.
-//   TMEM          cols 0..207 aggregation accumulator, 208..335 linear accumulators, 336.. weight A-operands
-//                 (tcgen05.st from registers, straight from L2); the edge-stage A-operands S = R+ + R-,
-//                 D = R+ - R- live in TMEM too (g = (|A| S + A D) / (2 deg), SURVEY.md section 7 identity).
+//                 K-major A-operand of the aggregation AND MN-major B-operand of the linears), one 64-vertex chunk
+//                 buffer per warp group.  No swizzle: 8x16-byte core matrices, written conflict-free by the epilogues.
+//   TMEM          cols 0..207 aggregation accumulator (the linears of a chunk accumulate in place in its consumed
+//                 columns), 208..335 one 64-column accumulator per group, 336.. weight A-operands (tcgen05.st from
+//                 registers, straight from L2); the edge-stage A-operands S = R+ + R-, D = R+ - R- live in TMEM too
+//                 (g = (|A| S + A D) / (2 deg), SURVEY.md section 7 identity).
 //   edge stage    ReLU(W_e [a_ij ; x_j]) = ReLU(a_ij w0 + P_j): two dense N x N contractions instead of the
-//                 reference's [B,N,N,63] intermediate.
-//   schedule      the 8 warps form two groups of 4 (one warp per TMEM lane quadrant).  The N x N contractions are
-//                 issued once per layer for the whole CTA; the per-vertex linears run on 48-vertex chunks, even
-//                 chunks on group 0 and odd chunks on group 1, each group with its own accumulator columns, chunk
-//                 buffer, mbarrier and named barrier, so one group's MMAs overlap the other group's epilogue.
+//                 reference's [B,N,N,63] intermediate; the MMAs of k-step block r are issued as soon as the workers have
+//                 stored S / D of round r, so the contraction runs behind the CUDA-core stage that feeds it.
+//   schedule      19 warps.  Warps 0-15 only ever run epilogues (TMEM -> registers -> split -> smem): two groups of 8
+//                 (2 warps per TMEM lane quadrant), each owning up to two column chunks (208 vertices: 64, 48 | 48, 48)
+//                 that it processes interleaved -- the MMAs of one chunk run under the epilogue of the other.  Warp 16
+//                 issues the N x N contractions (edge stage, aggregation per column half) and, in the gaps, reads out
+//                 the PREVIOUS episode (pooling, W_p, Q, argmax).  Warps 17 / 18 issue the linear-layer MMAs of group
+//                 0 / 1: a worker warp that has written its part of a batch's operands fences and arrives on the
+//                 issuer's mbarrier (no CTA or group barrier inside a layer); the issuer commits every batch to one of
+//                 the group's three mbarriers (B1, B2, B3) that the workers wait on before they touch its results.
 #include <cuda_bf16.h>
 #include <stdlib.h>
 

@@ -159,44 +159,64 @@ def test_network(network, env_args, graphs_test, device=None, step_factor=1, bat
     return ret
 
 
-Graph = namedtuple('Graph', 'name n_vertices n_edges matrix bk_val bk_sol')
+Graph = namedtuple('Graph', 'name n_vertices n_edges matrix bk_val bk_sol')      # reference experiments/utils.py:389
+
+
+def read_mc_instance(path):
+    """GSet-style `.mc` text instance -> (n_vertices, n_edges, rows, cols, weights): a header line `n m`, then one
+    `i j w` line per edge with 1-based vertex numbers (the format reference experiments/utils.py:395-406 parses).  The edge
+    list is kept as arrays so that it can go to the device as int8 dense or as CSR without a dense float64 detour."""
+    with open(path) as f:
+        header = f.readline().split()
+        if len(header) != 2:
+            raise AssertionError('First line in file should define graph dimensions.')      # the reference's assert text
+        n_vertices, n_edges = int(header[0]), int(header[1])
+        body = np.loadtxt(f, dtype=np.int64, ndmin=2) if n_edges > 0 else np.zeros((0, 3), dtype=np.int64)
+    if body.shape[1] != 3:
+        raise ValueError("%s: edge lines must be `i j w`" % path)
+    return n_vertices, n_edges, body[:, 0] - 1, body[:, 1] - 1, body[:, 2]
 
 
 def load_graph(graph_dir, graph_name):
-    """GSet-style instance + best-known value/solution files (reference experiments/utils.py:391-418)."""
-    matrix = None
-    with open(os.path.join(graph_dir, 'instances', graph_name + '.mc')) as f:
-        for line in f:
-            arr = list(map(int, line.strip().split(' ')))
-            if len(arr) == 2:
-                n_vertices, n_edges = arr
-                matrix = np.zeros((n_vertices, n_vertices))
-            else:
-                assert type(matrix) == np.ndarray, 'First line in file should define graph dimensions.'
-                i, j, w = arr[0] - 1, arr[1] - 1, arr[2]
-                matrix[[i, j], [j, i]] = w
+    """Same result as reference experiments/utils.py:391-418: the instance as a dense symmetric float matrix, the best-known
+    value (`bkvl/<name>.bkvl`) and solution (`bksol/<name>.bksol`: one 0/1 character per vertex, to which the reference
+    appends one random bit drawn with `np.random.choice([0, 1])` -- kept, it consumes the global RNG)."""
+    n_vertices, n_edges, rows, cols, weights = read_mc_instance(os.path.join(graph_dir, 'instances', graph_name + '.mc'))
+    matrix = np.zeros((n_vertices, n_vertices))
+    matrix[rows, cols] = weights
+    matrix[cols, rows] = weights
     with open(os.path.join(graph_dir, 'bkvl', graph_name + '.bkvl')) as f:
         bk_val = float(f.readline())
     with open(os.path.join(graph_dir, 'bksol', graph_name + '.bksol')) as f:
-        bk_sol = np.array([int(x) for x in list(f.readline().strip())] + [np.random.choice([0, 1])])
+        digits = np.frombuffer(f.readline().strip().encode('ascii'), dtype=np.uint8) - ord('0')
+    bk_sol = np.append(digits.astype(np.int64), np.random.choice([0, 1]))
     return Graph(graph_name, n_vertices, n_edges, matrix, bk_val, bk_sol)
 
 
+def to_dense_adjacency(g):
+    """One entry of a pickled graph set -- ndarray, networkx graph (edge attribute `weight`) or any scipy sparse matrix --
+    as a dense array, which is what every caller of the reference's loader receives (experiments/utils.py:424-430)."""
+    if isinstance(g, nx.Graph):
+        return nx.to_numpy_array(g)
+    if sp.sparse.issparse(g):
+        return g.toarray()
+    return g
+
+
 def load_graph_set(graph_save_loc):
-    """Pickled list of ndarray / nx.Graph / scipy csr graphs -> list of dense arrays (experiments/utils.py:420-432)."""
+    """Pickled list of graphs -> list of dense arrays (reference experiments/utils.py:420-432)."""
     with open(graph_save_loc, 'rb') as f:
-        graphs_test = pickle.load(f)
-
-    def graph_to_array(g):
-        if type(g) == nx.Graph:
-            g = nx.to_numpy_array(g)
-        elif type(g) == sp.sparse.csr_matrix:
-            g = g.toarray()
-        return g
-
-    graphs_test = [graph_to_array(g) for g in graphs_test]
+        graphs_test = [to_dense_adjacency(g) for g in pickle.load(f)]
     print('{} target graphs loaded from {}'.format(len(graphs_test), graph_save_loc))
     return graphs_test
+
+
+def load_graph_set_device(graph_save_loc, device=None, min_cut=False):
+    """The same pickle straight into an engine.GraphSet: int8 couplings, one upload, no float64 copies kept (all graphs of
+    the file must share N, as the reference's batched tester assumes per graph anyway)."""
+    with open(graph_save_loc, 'rb') as f:
+        graphs = [to_dense_adjacency(g) for g in pickle.load(f)]
+    return engine.GraphSet(engine.graphs_to_int8(np.stack(graphs)), device=device, min_cut=min_cut)
 
 
 def mk_dir(export_dir, quite=False):

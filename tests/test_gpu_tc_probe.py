@@ -17,9 +17,11 @@ def bf16_round(x):
 def test_tc_probe(mode, N, K):
     if (mode & 3) == 3:
         pytest.skip("unused A-source code")
+    import os
     import eco_dqn_b200
     import eco_dqn_b200._lib as _lib
-    L = eco_dqn_b200.lib()
+    eco_dqn_b200.lib()                  # the probe library links against the product library (test-only kernel, not shipped in it)
+    L = C.CDLL(os.path.join(os.path.dirname(_lib.LIB_PATH), "libecodqn_b200_probe.so"))
     fn = L.eco_tc_probe
     fn.restype = C.c_int
     fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]

@@ -86,3 +86,40 @@ def test_unsupported_configurations_raise_at_construction():
             check_supported(**dict(ok, **{key: bad}))
     with pytest.raises(AssertionError):
         check_supported(**dict(ok, observables=[Observable.TIME_SINCE_FLIP]))
+
+
+def test_graph_loaders_mc_text_and_pickled_sets(tmp_path):
+    """load_graph (GSet `.mc` text + best-known files) and load_graph_set (ndarray / networkx / scipy-sparse pickles) return
+    what the reference's loaders return (experiments/utils.py:391-432), including the extra random bit on the solution."""
+    import pickle
+    import networkx as nx
+    import scipy.sparse
+    from eco_dqn_b200.experiments.utils import load_graph, load_graph_set, read_mc_instance
+    for sub in ("instances", "bkvl", "bksol"):
+        (tmp_path / sub).mkdir()
+    edges = [(1, 2, 1), (1, 5, -1), (2, 3, 1), (4, 5, -1), (3, 5, 1)]
+    (tmp_path / "instances" / "toy.mc").write_text("5 5\n" + "".join("%d %d %d\n" % e for e in edges))
+    (tmp_path / "bkvl" / "toy.bkvl").write_text("3\n")
+    (tmp_path / "bksol" / "toy.bksol").write_text("0110\n")
+    np.random.seed(11)
+    extra = np.random.choice([0, 1])
+    np.random.seed(11)
+    g = load_graph(str(tmp_path), "toy")
+    want = np.zeros((5, 5))
+    for i, j, w in edges:
+        want[i - 1, j - 1] = want[j - 1, i - 1] = w
+    assert (g.name, g.n_vertices, g.n_edges, g.bk_val) == ("toy", 5, 5, 3.0)
+    assert np.array_equal(g.matrix, want) and g.matrix.dtype == np.float64
+    assert g.bk_sol.tolist() == [0, 1, 1, 0, int(extra)]
+    n, m, r, c, w = read_mc_instance(str(tmp_path / "instances" / "toy.mc"))
+    assert (n, m) == (5, 5) and r.tolist() == [0, 0, 1, 3, 2] and c.tolist() == [1, 4, 2, 4, 4] and w.tolist() == [1, -1, 1, -1, 1]
+    (tmp_path / "instances" / "bad.mc").write_text("5\n1 2 1\n")
+    with pytest.raises(AssertionError):
+        read_mc_instance(str(tmp_path / "instances" / "bad.mc"))
+    nxg = nx.Graph()
+    nxg.add_nodes_from(range(5))
+    nxg.add_weighted_edges_from([(i - 1, j - 1, w) for i, j, w in edges])
+    with open(tmp_path / "set.pkl", "wb") as f:
+        pickle.dump([want, nxg, scipy.sparse.csr_matrix(want)], f)
+    out = load_graph_set(str(tmp_path / "set.pkl"))
+    assert len(out) == 3 and all(np.array_equal(o, want) for o in out)
