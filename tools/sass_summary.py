@@ -17,7 +17,8 @@ for line in out.splitlines():
     m = re.match(r"\s*Function : (\S+)", line)
     if m:
         name = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
-        name = re.sub(r"\(.*", "", name).replace("eco::(anonymous namespace)::", "").replace("void ", "")
+        name = name.replace("(anonymous namespace)::", "").replace("void ", "")
+        name = re.sub(r"\(.*", "", name).replace("eco::", "")
         counts[name] = collections.Counter()
         size[name] = 0
         continue
