@@ -22,7 +22,7 @@ for line in out.splitlines():
         counts[name] = collections.Counter()
         size[name] = 0
         continue
-    if name and re.match(r"\s+/\*[0-9a-f]{4}\*/", line):
+    if name and re.match(r"\s+/\*[0-9a-f]{4,}\*/", line):
         size[name] += 1
         for key, pat in pats:
             if re.search(pat, line):
