@@ -441,6 +441,36 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         if (c.lane == 0 && act_out) act_out[be] = bi;
         TL(64);
     };
+    // Not PACKED: the next episode's inputs do not pass through registers.  The threads of group 1 copy them with cp.async
+    // (16 bytes each, no register, no wait) into the rows of `xf` -- their own chunk buffer, free once the group's last
+    // W_m agg batch of the episode retired -- well before the episode ends: vertex observations [3][NP], the degrees,
+    // the four graph-level observations and the graph's maximum degree.  Consumed after one cp.async.wait + CTA barrier at
+    // the top of the next episode.  (Padding vertices keep whatever the env kernels wrote for them: finite values that
+    // only ever reach padding columns -- the adjacency rows of padding vertices are zero.)
+    constexpr int XF_DEG = 4, XF_GL = 5, XF_GMAX = 6;      // rows of xf used by the staging (rows 0..2: the observations)
+    // ... and the two small input weights W_e [63][8], W_init [64][7] behind them (3.8 KB from L2 every episode: 30 values
+    // per thread that would otherwise be 30 dependent-latency global loads at the top of the episode, or 30 registers)
+    float* wsm_e = xf + 7 * NPMAX;
+    float* wsm_i = wsm_e + 63 * 8;
+    auto stage_inputs = [&](int e) {                        // threads 256 .. 511
+        const int i = c.tid - GROUP_THREADS, per_row = NP >> 2;
+        const int ge = graph_idx[e];
+        if (i < 4 * per_row) {
+            const int row = i / per_row, col = 4 * (i % per_row);
+            const float* src = row < 3 ? xn + ((size_t)e * 3 + row) * NP + col : g.deg + (size_t)ge * NP + col;
+            float* dst = xf + (row < 3 ? row : XF_DEG) * NPMAX + col;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+        } else if (i == 4 * per_row) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(xf + XF_GL * NPMAX)), "l"(xg + (size_t)e * 4) : "memory");
+        } else if (i == 4 * per_row + 1) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(xf + XF_GMAX * NPMAX)), "l"(g.gstat + (size_t)ge * 4) : "memory");
+        }
+        if (i < (63 * 8) / 4)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(wsm_e + 4 * i)), "l"(w.w_edge + 4 * i) : "memory");
+        if (i < (64 * 7) / 4)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(wsm_i + 4 * i)), "l"(w.w_init + 4 * i) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     if (c.warp == NWARPS) {
         // ================= contraction issuer ===============================================================
         float c0_prev = 0.f;
@@ -560,7 +590,10 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             }
         }
     }
-    if (c.warp < NWARPS && (int)blockIdx.x < npacks) load_inputs(blockIdx.x);
+    if (c.warp < NWARPS && (int)blockIdx.x < npacks) {
+        if (PACKED) load_inputs(blockIdx.x);
+        else if (c.grp == 1) stage_inputs(blockIdx.x);
+    }
 
     // ================= readout + argmax of one episode (mpnn.py:143-159; experiments/utils.py:57-66) =================
     // Reads only qpart / ppart, which the next episode does not touch before its last layer: it is run while the workers
@@ -624,28 +657,42 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     int last_b = -1;
 
     for (int b = blockIdx.x; b < npacks && c.warp < NWARPS; b += gridDim.x) {
-        const float rdmax = 1.f / (norm_max < 0.f ? (float)max(gmaxdeg, 1) : dmax_set);
-
         TL(1);
+        if (!PACKED) {                                      // the staged inputs of this episode have landed
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            TL(70);
+            workers_sync();
+            TL(71);
+            gl = *reinterpret_cast<const float4*>(xf + XF_GL * NPMAX);
+            gmaxdeg = *reinterpret_cast<const int*>(xf + XF_GMAX * NPMAX);
+            if (has_v) rdeg[c.tid] = __fdividef(1.f, xf[XF_DEG * NPMAX + c.tid]);
+        }
+        // (fast reciprocal: a correctly rounded 1.f / x is a subroutine call of several hundred cycles at the top of every episode)
+        const float rdmax = __fdividef(1.f, norm_max < 0.f ? (float)max(gmaxdeg, 1) : dmax_set);
+
         // ================= stage 0: operands of the edge contraction ======================================
         // this thread's rows of the two small input weights (features fa, fb), issued early so the latency is hidden
         const int fa = 16 * c.q + (c.lane >> 2), fb = fa + 8;
         float wxa[8], wxb[8], wia[7], wib[7];
+        {
+            const float* we = PACKED ? w.w_edge : wsm_e;      // (not PACKED: staged in shared memory with the inputs)
+            const float* wi = PACKED ? w.w_init : wsm_i;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {       // row 63 of the 63 x 8 edge weight does not exist: zero
-            wxa[k] = __ldg(w.w_edge + fa * 8 + k);
-            wxb[k] = fb < 63 ? __ldg(w.w_edge + fb * 8 + k) : 0.f;
+            for (int k = 0; k < 8; ++k) {   // row 63 of the 63 x 8 edge weight does not exist: zero
+                wxa[k] = we[fa * 8 + k];
+                wxb[k] = fb < 63 ? we[fb * 8 + k] : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 7; ++k) { wia[k] = wi[fa * 7 + k]; wib[k] = wi[fb * 7 + k]; }
         }
-#pragma unroll
-        for (int k = 0; k < 7; ++k) { wia[k] = __ldg(w.w_init + fa * 7 + k); wib[k] = __ldg(w.w_init + fb * 7 + k); }
-        if (has_v) {
+        if (PACKED && has_v) {
             const int i = c.tid;
             const bool ok = vertex_ok(i);
             xf[0 * NPMAX + i] = ok ? xin0 : 0.f;
             xf[1 * NPMAX + i] = ok ? xin1 : 0.f;
             xf[2 * NPMAX + i] = ok ? xin2 : 0.f;
             rdeg[i] = __fdividef(1.f, degv);
-            if (PACKED) {                      // the graph-level observations and deg_max differ from vertex to vertex
+            {                                  // the graph-level observations and deg_max differ from vertex to vertex
                 xf[3 * NPMAX + i] = ok ? gl.x : 0.f;
                 xf[4 * NPMAX + i] = ok ? gl.y : 0.f;
                 xf[5 * NPMAX + i] = ok ? gl.z : 0.f;
@@ -664,7 +711,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         uint4 wef[32 / (8 * SUBS)];
         ldg_weights<32>(c, pk + PK_WEF, wef);
         TL(2);
-        workers_sync();                                   // xf visible
+        if (PACKED) workers_sync();                       // xf visible
         TL(3);
         // S = R+ + R-, D = R+ - R- with R+- = ReLU(P +- w0), P = W_x x  -> TMEM A operands (mpnn.py:89-100 factorised)
         {
@@ -927,6 +974,8 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                     // ---- E5: m(b) -> H^T[b]
                     wait_g2(c);                                                             // B2: M1(b)
                     wait_g3(c);                                                             // B3: M2h(b)
+                    // the chunk buffer has no reader left in this episode: the next episode's inputs go there
+                    if (!PACKED && l == 2 && c.grp == 1 && b + (int)gridDim.x < npacks) stage_inputs(b + gridDim.x);
                     TL(33);
                     epi_m(cB0, cBw);
                     signal_issuer(0);                       // S4 -> M2m(b) (B1)
@@ -943,7 +992,10 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
 
         // ================= end of the episode's tensor work ==================================================
         // (its readout runs later, under the next episode's edge contraction)
-        if (b + (int)gridDim.x < npacks) load_inputs(b + gridDim.x);     // next episode's inputs: in flight from here
+        if (b + (int)gridDim.x < npacks) {                // next episode's inputs: in flight from here (or earlier, above)
+            if (PACKED) load_inputs(b + gridDim.x);
+            else if (c.grp == 1 && nmine < 2) stage_inputs(b + gridDim.x);
+        }
         workers_sync();
         if (PACKED && b + (int)gridDim.x < npacks) {      // the off-diagonal blocks of |A| were overwritten by H / E: clear
             zero_image(smem + SM_ABS);

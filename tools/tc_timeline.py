@@ -31,6 +31,7 @@ names = {1: "ep start", 2: "loads issued", 3: "xf sync", 4: "S/D done", 5: "A co
          8: "h0 done", 14: "Wef issued", 15: "before wait", 10: "g epi", 11: "grp sync", 12: "Wef done", 13: "e epi", 20: "layer top", 21: "cta sync",
          22: "weights+ahead issued", 23: "A.H done", 30: "agg epi", 31: "grp sync", 32: "issued", 33: "Wm done",
          34: "m epi", 35: "grp sync", 36: "issued", 37: "Wu done", 38: "h epi", 40: "layers done", 41: "ep end",
+         70: "staged inputs landed", 71: "cta sync",
          60: "readout start", 61: "readout: pooled", 62: "readout: W_p pooled", 63: "readout: Q, warp argmax", 64: "readout end",
          50: "issuer: S/D signalled", 51: "issuer: A, |A| landed", 52: "issuer: edge MMAs issued",
          53: "issuer: layer signalled", 54: "issuer: A.H issued"}
