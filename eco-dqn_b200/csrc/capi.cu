@@ -5,6 +5,8 @@
 #include <atomic>
 #include <vector>
 
+#include <stdlib.h>
+
 #include "eco_common.cuh"
 
 namespace eco {
@@ -417,6 +419,18 @@ int eco_rollout(const eco_graphs_t* g, eco_env_t* env, const eco_mpnn_t* w, int3
     if (rc) return rc;
     const bool masked = (env->reserved & ECO_ENV_IRREVERSIBLE) != 0;   // argmax over the spins still at -1 only
     float* qbuf = masked ? (float*)((char*)scratch + mpnn_kernel_scratch_bytes(env->B, env->N, impl)) : nullptr;
+    // Opt-in (ECO_FUSED_STEP=1): one launch per step, the resident tensor-core kernel's tail warp applies the flip itself
+    // (mpnn_tc.cu, FUSED).  Measured at BA-200 x 4096: 0.556 ms per step against 0.553 ms for the two launches -- the fused
+    // kernel ends with the last episode's readout + env step exposed -- so two launches stay the default.
+    static const bool fuse = getenv("ECO_FUSED_STEP") != nullptr;
+    if (fuse && !masked && pick_impl(g, w, impl) == ECO_MPNN_TCGEN05 && g->N <= 208 && w->packed && mpnn_tc_can_fuse(g, env)) {
+        for (int t = 0; t < n_steps; ++t) {
+            rc = launch_mpnn_tc_fused(g, w, env->B, env->graph_idx, env->xn, env->xg, norm_max, nullptr, act, scratch, env, ha,
+                                      hr, hs, st);
+            if (rc) return rc;
+        }
+        return ECO_OK;
+    }
     for (int t = 0; t < n_steps; ++t) {
         rc = eco_mpnn_forward(g, w, env->B, env->graph_idx, env->xn, env->xg, norm_max, qbuf, masked ? nullptr : act,
                               scratch, impl, stream);

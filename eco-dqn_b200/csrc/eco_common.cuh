@@ -118,6 +118,10 @@ int launch_mpnn_simt(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const in
 size_t mpnn_simt_scratch_bytes(int B, int N);
 int launch_mpnn_tc(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int32_t* gidx, const float* xn,
                    const float* xg, float norm_max, float* q, int32_t* actions, void* scratch, cudaStream_t st);
+bool mpnn_tc_can_fuse(const eco_graphs_t* g, const eco_env_t* env);
+int launch_mpnn_tc_fused(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int32_t* gidx, const float* xn,
+                         const float* xg, float norm_max, float* q, int32_t* actions, void* scratch, const eco_env_t* fused,
+                         int32_t* ha, double* hr, double* hs, cudaStream_t st);
 size_t mpnn_tc_scratch_bytes(int B, int N);
 size_t mpnn_tc_packed_bytes();
 int launch_mpnn_pack(const eco_mpnn_t* w, void* packed, cudaStream_t st);

@@ -39,6 +39,7 @@
 #include "eco_common.cuh"
 #include "tc_prims.cuh"
 #include "mpnn_pack.cuh"
+#include "env_step_device.cuh"
 
 namespace eco {
 namespace {
@@ -52,7 +53,8 @@ constexpr int SUBS = 2;            // warps per (group, TMEM lane quadrant): the
 constexpr int THREADS = 256 * SUBS;
 constexpr int GROUP_THREADS = 128 * SUBS;
 constexpr int NWARPS = THREADS / 32;
-constexpr int ISSUERS = 3;                     // warp 16: the N x N contractions; warps 17, 18: the linear layers of group 0 / 1
+constexpr int ISSUERS = 4;                     // warp 16: the N x N contractions; warps 17, 18: the linear layers of group 0 / 1;
+                                               // warp 19: the tail of every episode (readout, argmax, fused env step)
 constexpr int LAUNCH_THREADS = THREADS + 32 * ISSUERS;   // (tcgen05.mma issue blocks while the tensor queue is full, which
                                                          //  must not hold up an epilogue warp: the workers never issue)
 
@@ -219,12 +221,22 @@ __device__ __forceinline__ void issue_part(const Ctx& c, uint32_t acc_col, uint3
 // PACKED: K = packK >= 2 small graphs (NP <= 96) are processed side by side as ONE block-diagonal graph of K * NP <= 192
 // vertices ("pack"): the tensor part below does not know about it; only the inputs (per-vertex episode), the operand
 // images (diagonal blocks), feature 63 and the readout (pooling / argmax per episode) are per episode.
-template <bool PACKED, bool TLINE>
+// FUSED (rollouts of the ECO-DQN configuration): the warp that has just taken an episode's argmax also applies the flip --
+// SpinSystemBase.step for that episode (env_step_device.cuh), state and next observations written for the next launch --
+// so a rollout step is ONE launch instead of two.
+struct FusedEnv {
+    eco_env_t env;
+    int32_t* hist_a;
+    double* hist_r;
+    double* hist_s;
+};
+
+template <bool PACKED, bool TLINE, bool FUSED = false>
 __global__ void __launch_bounds__(LAUNCH_THREADS, 1)
 mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int32_t* __restrict__ graph_idx,
                const float* __restrict__ xn, const float* __restrict__ xg, const float norm_max,
                float* __restrict__ q_out, int32_t* __restrict__ act_out, unsigned long long* __restrict__ dbg,
-               const int packK) {
+               const int packK, const FusedEnv fe) {
     extern __shared__ __align__(128) unsigned char smem[];
     // optional timeline (tools/tc_timeline.py): CTA 0, lane 0 of every warp records (event id << 48 | clock)
     int dbg_n = 0;
@@ -237,6 +249,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                                       // group 0 / 1; 5, 6: B2 of group 0 / 1; 7, 8: B3 of group 0 / 1
     __shared__ uint64_t sig[2];       // workers -> contraction issuer: [1] layer inputs ready  ([0] unused)
     __shared__ uint64_t sdbar[4];     // worker warps -> contraction issuer: blocks 4r .. 4r+3 of the edge operands S, D are in TMEM
+    __shared__ uint64_t tail_sig, tail_done;   // workers -> tail warp: an episode's readout partials are complete; and back
     __shared__ uint64_t gsig[2][2];   // the warps of group g -> its linear-layer issuer: operands of the next MMA batch are
                                       // written (one arrival per warp; consecutive batches alternate between the two)
     __shared__ uint64_t bar_ops[2];   // arrival of the bulk copies of the adjacency operand images: 0 = A, 1 = |A|
@@ -247,6 +260,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     c.warp = __shfl_sync(0xffffffffu, c.tid >> 5, 0);     // warp-uniform: MMA issue code stays on the uniform datapath
     c.q = c.warp & 3; c.sub = (c.warp >> 2) % SUBS;
     c.grp = c.warp < NWARPS ? c.warp / (4 * SUBS) : (c.warp == NWARPS + 2 ? 1 : 0);
+    const bool linear_issuer = c.warp == NWARPS + 1 || c.warp == NWARPS + 2;
     c.bar_all = &bars[0]; c.bar_grp = &bars[1 + c.grp]; c.bar_g2 = &bars[5 + c.grp]; c.bar_g3 = &bars[7 + c.grp];
     const int K = PACKED ? packK : 1;                     // episodes per pack
     const int NPs = g.NP, Ns = g.N;                       // per-episode sizes; NP / N below are the pack's
@@ -283,6 +297,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         mbar_init(&sig[0], 1); mbar_init(&sig[1], 1);
         for (int i = 0; i < 4; ++i) mbar_init(&gsig[i >> 1][i & 1], 4 * SUBS);
         for (int i = 0; i < 4; ++i) mbar_init(&sdbar[i], NWARPS);
+        mbar_init(&tail_sig, 1); mbar_init(&tail_done, 1);
         fence_mbar_init();
     }
     tc_fence_before();
@@ -301,9 +316,9 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     const int chunk_split = nch0;                          // global index of group 1's first chunk
     const int cs = c.grp == 0 ? 0 : nch0;
     const int ncols0 = 16 * nb0;                           // columns of group 0's chunks
-    uint32_t phase_half = 0, phase_other = 0;
+    uint32_t phase_half = 0, phase_other = 0, phase_tail = 0;
     // this group's (at most two) chunks: first column and width, fixed for the whole launch
-    const int nmine = (c.warp != NWARPS) ? (c.grp == 0 ? nch0 : nch1) : 0;
+    const int nmine = (c.warp < NWARPS || linear_issuer) ? (c.grp == 0 ? nch0 : nch1) : 0;
     const int nbm = c.grp == 0 ? nb0 : nb1;                // this group's blocks: chunk a = the first ceil(nbm / 2) of them
     const int cA0 = c.grp == 0 ? 0 : ncols0, cAw = nmine > 1 ? 16 * ((nbm + 1) / 2) : 16 * nbm;
     const int cB0 = cA0 + cAw, cBw = 16 * nbm - cAw;
@@ -384,10 +399,10 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     };
     // ================= readout + argmax of one episode by ONE warp (mpnn.py:143-159; experiments/utils.py:57-66) ==========
     // Not PACKED.  Reads only the pooled partial sums and the per-vertex partial dot products that the last layer's
-    // epilogues left in shared memory, which the next episode does not touch before ITS last layer: the contraction
-    // issuer runs it for the previous episode in the long gaps between two aggregations (part a after layer 0's, part b
-    // after layer 1's), so it costs the epilogue warps nothing.  The CTA's last episode is read out by warp 0 with the
-    // same code (same order of every sum: an episode's Q does not depend on where in the launch it was evaluated).
+    // epilogues left in shared memory, which the next episode does not touch before ITS last layer: warp 19 does nothing
+    // else -- it is woken at the end of every episode and works through the tail (pooling, W_p, Q, argmax and, FUSED, the
+    // environment step with its chains of dependent global loads) while the other 19 warps are already on the next
+    // episode, so the tail costs the epilogue warps nothing and never delays an MMA issue.
     const float bread = __ldg(w.b_read);
     auto readout_warp_a = [&]() -> float {            // c0 = w_r[0:64] . ReLU(W_p mean_i h_i) + b
         TL(60);
@@ -439,6 +454,8 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
         }
         if (c.lane == 0 && act_out) act_out[be] = bi;
+        if (FUSED)        // every lane holds the same (bv, bi) after the butterfly: the warp steps the episode it has just decided
+            env_step_group<32>(g, fe.env, be, c.lane, true, ECO_POLICY_ACTIONS, bi, nullptr, nullptr, fe.hist_a, fe.hist_r, fe.hist_s);
         TL(64);
     };
     // Not PACKED: the next episode's inputs do not pass through registers.  The threads of group 1 copy them with cp.async
@@ -473,7 +490,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     };
     if (c.warp == NWARPS) {
         // ================= contraction issuer ===============================================================
-        float c0_prev = 0.f;
+
         uint32_t sp0 = 0, sp1 = 0, op = 0;
         for (int b = blockIdx.x; b < npacks; b += gridDim.x) {
             mbar_wait(&bar_ops[0], op);               // A and |A| of this episode have landed (async proxy -> async proxy)
@@ -519,14 +536,21 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                 }
                 __syncwarp();
                 TL(54);
-                if (!PACKED && b != (int)blockIdx.x) {            // the previous episode's readout, in the gap before the next layer
-                    if (l == 0) c0_prev = readout_warp_a();
-                    if (l == 1) readout_warp_b(b - gridDim.x, c0_prev);
-                }
             }
         }
     }
-    if (c.warp > NWARPS && nmine > 0) {
+    if (!PACKED && c.warp == NWARPS + 3) {
+        // ================= episode tail ====================================================================
+        uint32_t ph = 0;
+        for (int b = blockIdx.x; b < npacks; b += gridDim.x) {
+            mbar_wait(&tail_sig, ph);
+            ph ^= 1u;
+            readout_warp_b(b, readout_warp_a());
+            __syncwarp();
+            if (c.lane == 0) mbar_arrive(&tail_done);      // the partial sums may be overwritten (next episode's last layer)
+        }
+    }
+    if (linear_issuer && nmine > 0) {
         // ================= linear-layer issuer of group c.grp ================================================
         // Follows the group's schedule (see stage 1 / stage 2 below): waits for the group's k-th signal, issues the batch,
         // commits it to B1 / B2 / B3.  Signals alternate between gsig[g][0] and gsig[g][1]; a signal is never raised
@@ -883,6 +907,10 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             // readout weights of this thread's two features: requested before the wait (last layer only)
             float wa = 0.f, wb = 0.f;
             if (l == 2) { wa = __ldg(w.w_read + 64 + fa); wb = __ldg(w.w_read + 64 + fa + 8); }
+            if (!PACKED && l == 2 && last_b >= 0) {         // the tail warp has read the previous episode's partial sums
+                mbar_wait(&tail_done, phase_tail);
+                phase_tail ^= 1u;
+            }
             if (nmine > 0) {                                  // this group's aggregation columns
                 mbar_wait(&bars[3 + c.grp], phase_half);
                 phase_half ^= 1u;
@@ -1002,12 +1030,12 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             workers_sync();
         }
         if (c.tid == 0 && b + (int)gridDim.x < npacks) fetch_ops(1, b + gridDim.x);   // H / E (which |A| overlays) have no reader left
+        if (!PACKED && c.tid == 0) mbar_arrive(&tail_sig);       // -> tail warp: this episode's partial sums are complete
         last_b = b;
         TL(41);
     }
     if (c.warp < NWARPS && last_b >= 0) {
         if (PACKED) readout(last_b);
-        else if (c.warp == 0) readout_warp_b(last_b, readout_warp_a());   // (behind the episode's last CTA barrier)
     }
 #undef TL
 
@@ -1028,17 +1056,33 @@ int launch_mpnn_pack(const eco_mpnn_t* w, void* packed, cudaStream_t st) {
     return ECO_OK;
 }
 
+// Can a rollout step of this (graph set, environment) pair run as one fused launch?  The resident kernel must take the batch
+// unpacked (one episode per CTA iteration) and the environment must be the plain ECO-DQN configuration the sub-warp env step
+// implements (reversible spins, BLS reward, Max-Cut).
+bool mpnn_tc_can_fuse(const eco_graphs_t* g, const eco_env_t* env) {
+    const bool packed = PACK_NPMAX / g->NP >= 2 && env->B >= 2;
+    return mpnn_tc_supported(g) && !packed && env->reserved == 0 && !(g->reserved & ECO_GRAPHS_MIN_CUT) && env->N == g->N;
+}
+
 int launch_mpnn_tc(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int32_t* gidx, const float* xn,
                    const float* xg, float norm_max, float* q, int32_t* actions, void* scratch, cudaStream_t st) {
+    return launch_mpnn_tc_fused(g, w, B, gidx, xn, xg, norm_max, q, actions, scratch, nullptr, nullptr, nullptr, nullptr, st);
+}
+
+int launch_mpnn_tc_fused(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int32_t* gidx, const float* xn,
+                         const float* xg, float norm_max, float* q, int32_t* actions, void* scratch, const eco_env_t* fused,
+                         int32_t* ha, double* hr, double* hs, cudaStream_t st) {
     static unsigned long long attr_set = 0;
     const int n_sm = device_sm_count();
     if (first_use_on_device(&attr_set)) {
         ECO_CUDA((cudaFuncSetAttribute(mpnn_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)));
         ECO_CUDA((cudaFuncSetAttribute(mpnn_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)));
         ECO_CUDA((cudaFuncSetAttribute(mpnn_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)));
+        ECO_CUDA((cudaFuncSetAttribute(mpnn_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)));
     }
     const int packK = PACK_NPMAX / g->NP;                  // small graphs: several per CTA iteration
     const bool packed = packK >= 2 && B >= 2;
+    if (fused && packed) { set_error("launch_mpnn_tc_fused: packed batches cannot be fused"); return ECO_ERR_INVALID; }
     const int units = packed ? (B + packK - 1) / packK : B;
     const int grid = units < n_sm ? units : n_sm;
     prof_begin(ECO_PROF_MPNN, st);
@@ -1046,9 +1090,12 @@ int launch_mpnn_tc(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int3
     if (timeline) ECO_CUDA(cudaMemsetAsync(scratch, 0, (NWARPS + ISSUERS) * 1024 * 8, st));
     unsigned long long* dbg = timeline ? (unsigned long long*)scratch : nullptr;
     // (the clock trace of tools/tc_timeline.py is its own instantiation: the production kernels carry no trace code)
-    if (packed) mpnn_tc_kernel<true, false><<<grid, LAUNCH_THREADS, SM_TOTAL, st>>>(*g, *w, B, gidx, xn, xg, norm_max, q, actions, nullptr, packK);
-    else if (dbg) mpnn_tc_kernel<false, true><<<grid, LAUNCH_THREADS, SM_TOTAL, st>>>(*g, *w, B, gidx, xn, xg, norm_max, q, actions, dbg, 1);
-    else mpnn_tc_kernel<false, false><<<grid, LAUNCH_THREADS, SM_TOTAL, st>>>(*g, *w, B, gidx, xn, xg, norm_max, q, actions, nullptr, 1);
+    FusedEnv fe{};
+    if (fused) { fe.env = *fused; fe.hist_a = ha; fe.hist_r = hr; fe.hist_s = hs; }
+    if (packed) mpnn_tc_kernel<true, false><<<grid, LAUNCH_THREADS, SM_TOTAL, st>>>(*g, *w, B, gidx, xn, xg, norm_max, q, actions, nullptr, packK, fe);
+    else if (dbg) mpnn_tc_kernel<false, true><<<grid, LAUNCH_THREADS, SM_TOTAL, st>>>(*g, *w, B, gidx, xn, xg, norm_max, q, actions, dbg, 1, fe);
+    else if (fused) mpnn_tc_kernel<false, false, true><<<grid, LAUNCH_THREADS, SM_TOTAL, st>>>(*g, *w, B, gidx, xn, xg, norm_max, q, actions, nullptr, 1, fe);
+    else mpnn_tc_kernel<false, false><<<grid, LAUNCH_THREADS, SM_TOTAL, st>>>(*g, *w, B, gidx, xn, xg, norm_max, q, actions, nullptr, 1, fe);
     prof_end(ECO_PROF_MPNN, st);
     ECO_LAUNCH_CHECK();
     return ECO_OK;

@@ -24,7 +24,7 @@ env.reset(spins=(2 * rng.integers(0, 2, size=(B, n)) - 1).astype(np.int8))
 for _ in range(3):
     env.q_values(w)
 torch.cuda.synchronize()
-buf = env._scratch[:19 * 1024 * 8].view(torch.int64).cpu().numpy().reshape(19, 1024)
+buf = env._scratch[:20 * 1024 * 8].view(torch.int64).cpu().numpy().reshape(20, 1024)
 ev = [[(int(x) >> 48, int(x) & 0xFFFFFFFFFFFF) for x in row if x != 0] for row in buf]
 # episode boundaries: event 1 starts an episode; take the 3rd episode of the CTA
 names = {1: "ep start", 2: "loads issued", 3: "xf sync", 4: "S/D done", 5: "A conv done", 6: "cta sync", 7: "edge MMA done",
@@ -36,13 +36,13 @@ names = {1: "ep start", 2: "loads issued", 3: "xf sync", 4: "S/D done", 5: "A co
          50: "issuer: S/D signalled", 51: "issuer: A, |A| landed", 52: "issuer: edge MMAs issued",
          53: "issuer: layer signalled", 54: "issuer: A.H issued"}
 base = None
-for wi in (0, 8, 16):
-    first = 1 if wi < 16 else 50
+for wi in (0, 8, 16, 19):
+    first = 1 if wi < 16 else (50 if wi == 16 else 60)
     starts = [i for i, (e, _) in enumerate(ev[wi]) if e == first]
     seg = ev[wi][starts[2]:starts[3]] if len(starts) > 3 else ev[wi][starts[-1]:]
     t0 = seg[0][1] if base is None else base
     base = t0
-    print("---- warp %d (%s), episode 3 of CTA 0: %d cycles" % (wi, "group %d" % (wi // 8) if wi < 16 else "issuer", seg[-1][1] - seg[0][1]))
+    print("---- warp %d (%s), episode 3 of CTA 0: %d cycles" % (wi, "group %d" % (wi // 8) if wi < 16 else ("issuer" if wi == 16 else "tail"), seg[-1][1] - seg[0][1]))
     prev = t0
     for e, t in seg:
         print("%8d  +%6d  %s" % (t - t0, t - prev, names.get(e, str(e))))
