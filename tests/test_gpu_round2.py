@@ -281,3 +281,89 @@ def test_visited_set_long_revisit_heavy_episode(eng, n, p, T, n_hot):
         assert float(env.episodes()["best_score"][b]) == e.best_score
     if n_hot <= 6:
         assert int(env.episodes()["n_visited"].max()) <= 2 ** n_hot
+
+
+@pytest.mark.parametrize("n,B", [(16, 1), (40, 1), (97, 3), (112, 150), (130, 4), (150, 297), (177, 5), (192, 2), (208, 149)])
+@pytest.mark.parametrize("norm_max", [None, -1.0])
+def test_mpnn_tc_resident_kernel_every_chunk_layout_vs_oracle(eng, n, B, norm_max):
+    """The resident tcgen05 kernel in its unpacked form (one episode per CTA iteration: N > 96, or a single episode) at sizes
+    that exercise every chunk split of the two warp groups (one chunk in one group only ... 64, 48 | 48, 48), more episodes
+    than CTAs (the tail warp reads out episode e while the workers are on e + 1; the next episode's inputs are staged in
+    shared memory during the last layer) and fewer: Q against the ORACLE per row, argmax, run-to-run identical."""
+    from oracle.mpnn import mpnn_forward, KEYS
+    from eco_dqn_b200 import _lib
+    rng = np.random.default_rng(31 * n + B)
+    G = min(B, 3)
+    Js = _random_graphs(rng, G, n, 0.3 if n < 64 else 0.1)
+    gidx = rng.integers(0, G, size=B).astype(np.int32)
+    wd = {k: (rng.standard_normal(s) * (0.3 if len(s) > 1 else 0.1)).astype(np.float32)
+          for k, s in zip(KEYS, eng.STATE_DICT_SHAPES)}
+    env = eng.BatchedSpinSystem(eng.GraphSet(Js), B, 2 * n, 1.0 / n)
+    env.reset(spins=(2 * rng.integers(0, 2, size=(B, n)) - 1).astype(np.int8), graph_idx=gidx)
+    for t in range(6):
+        env.step(torch.from_numpy(rng.integers(0, n, size=B).astype(np.int32)))
+    w = eng.MPNNWeights(wd)
+    per_graph = norm_max is not None
+    nm = norm_max if per_graph else float(max((Js[g] != 0).sum(1).max() for g in gidx))
+    q, a = env.q_values(w, impl=_lib.MPNN_TCGEN05, norm_max=nm)
+    q, a = q.clone(), a.clone()
+    q2, a2 = env.q_values(w, impl=_lib.MPNN_TCGEN05, norm_max=nm)
+    assert torch.equal(q, q2) and torch.equal(a, a2)
+    q, a = q.cpu().numpy(), a.cpu().numpy()
+    assert np.array_equal(a, q.argmax(1))
+    sel = np.arange(B) if B <= 8 else np.unique(np.concatenate([np.arange(4), np.arange(B - 4, B), rng.integers(0, B, 8)]))
+    obs7 = env.observation().cpu().numpy()
+    for b in sel:
+        full = np.concatenate([obs7[b], Js[gidx[b]].astype(np.float32)], axis=0)[None]
+        if per_graph:
+            ref = mpnn_forward(wd, full).numpy()[0]
+        else:                                   # batch maximum: evaluate with an explicit divisor through the blocked oracle
+            from oracle.mpnn import mpnn_forward_blocked
+            ref = mpnn_forward_blocked(wd, obs7[b].T, Js[gidx[b]].astype(np.float32), rows_per_block=64, norm_max=nm).numpy()
+        tol = Q_RTOL * np.abs(ref) + Q_ATOL_FRAC * np.abs(ref).max()
+        assert (np.abs(q[b] - ref) <= tol).all(), (n, B, int(b), float(np.abs(q[b] - ref).max()), float(np.abs(ref).max()))
+
+
+_FUSED_SCRIPT = """
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+import eco_dqn_b200.engine as eng
+z = np.load(sys.argv[1])
+gs = eng.GraphSet(z["J"])
+B, n = z["spins"].shape
+env = eng.BatchedSpinSystem(gs, B, 2 * n, 1.0 / n)
+env.reset(spins=z["spins"], graph_idx=z["gidx"])
+w = eng.MPNNWeights({k[2:]: z[k] for k in z.files if k.startswith("w_")})
+ha, hr, hs = env.rollout(w, n_steps=int(z["steps"]), record_history=True)
+bc, bs, st = env.results()
+np.savez(sys.argv[2], ha=ha.cpu().numpy(), hr=hr.cpu().numpy(), hs=hs.cpu().numpy(), bc=bc.cpu().numpy(), bs=bs.cpu().numpy(),
+         xn=env.xn.cpu().numpy(), xg=env.xg.cpu().numpy(), ep=env._ep.cpu().numpy())
+"""
+
+
+def test_fused_step_option_equals_two_launches(eng, tmp_path):
+    """ECO_FUSED_STEP=1 (the MPNN kernel's tail warp applies the flip it has just chosen, one launch per step) against the
+    default two launches per step: actions, fp64 rewards and scores, best cuts / spins, the next observations and every
+    episode record bit for bit.  (The option is read once per process: the fused run is a child process.)"""
+    import subprocess
+    import sys
+    from oracle.mpnn import weights_from_npz
+    z = load("er200_g0")
+    rng = np.random.default_rng(2)
+    n, B, steps = 200, 300, 25
+    Js = np.stack([z["J"], _random_graphs(rng, 1, n, 0.1)[0]])
+    gidx = (np.arange(B) % 2).astype(np.int32)
+    spins = (2 * rng.integers(0, 2, size=(B, n)) - 1).astype(np.int8)
+    wd = weights_from_npz(z)
+    inp, out = str(tmp_path / "in.npz"), str(tmp_path / "out.npz")
+    np.savez(inp, J=Js, gidx=gidx, spins=spins, steps=steps, **{"w_" + k: v for k, v in wd.items()})
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for tag, extra in (("two", {}), ("fused", {"ECO_FUSED_STEP": "1"})):
+        env_vars = dict(os.environ, **extra)
+        env_vars.pop("ECO_FUSED_STEP", None) if tag == "two" else None
+        subprocess.run([sys.executable, "-c", _FUSED_SCRIPT % root, inp, out], check=True, env=env_vars, timeout=300)
+        res[tag] = {k: v.copy() for k, v in np.load(out).items()}
+    for k in res["two"]:
+        assert np.array_equal(res["two"][k].view(np.uint8), res["fused"][k].view(np.uint8)), k
+    assert (res["two"]["ha"][:, :steps] >= 0).all()
