@@ -443,9 +443,14 @@ def run_ours(args):
             launches = int(L.eco_launch_count(0))
             mpnn_ms, mpnn_n = prof_read(0)
             env_ms, env_n = prof_read(1)
+            roll_ms, roll_n = prof_read(2)      # one-launch rollouts: total time, rollout STEPS covered
             L.eco_profile_enable(0)
+            one_launch = roll_n > 0
+            if one_launch:                      # per step: forward + argmax + env step inside the resident kernel
+                mpnn_ms, mpnn_n, env_ms, env_n = roll_ms, roll_n, 0.0, 0
             return {"ms_total": float(ms.item()), "mpnn_ms": mpnn_ms / max(mpnn_n, 1), "mpnn_n": mpnn_n,
-                    "env_ms": env_ms / max(env_n, 1), "env_n": env_n, "launches": launches, "clocks": clocks, "best": bc}
+                    "env_ms": env_ms / max(env_n, 1), "env_n": env_n, "launches": launches, "clocks": clocks, "best": bc,
+                    "one_launch": one_launch}
 
         def side_block(self, name, r, steps, env_steps_per_rollout, ranks=1):
             """ms per [MPNN + env step], env-steps/s, roofline fraction of the MPNN forward of this size."""
@@ -454,7 +459,9 @@ def run_ours(args):
                     "graphs_per_gpu": self.gs.G, "gpus": ranks, "mpnn_impl": self.used_impl,
                     "env_steps_per_s": ranks * env_steps_per_rollout * steps / (r["ms_total"] / 1e3),
                     "ms_per_env_step_launch_pair": r["ms_total"] / steps / (env_steps_per_rollout / self.B),
-                    "mpnn_forward_ms": r["mpnn_ms"], "env_step_us": r["env_ms"] * 1e3,
+                    "mpnn_forward_ms": r["mpnn_ms"], "env_step_us": None if r["one_launch"] else r["env_ms"] * 1e3,
+                    "launches_per_rollout": "1 (forward + argmax + env step of all steps in one kernel)" if r["one_launch"]
+                    else "2 per step",
                     "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s",
                                  "frac": ach / pk["tflops"], "flops_per_launch": flops_mpnn(self.n) * self.B},
                     "mean_best_cut": float(r["best"].float().mean().item())}
@@ -467,6 +474,22 @@ def run_ours(args):
     r = head.timed(args.warmup, args.steps, sample_clocks=True)
     ms_total, bc = r["ms_total"], r["best"]
     value = world * B * T * args.steps / (ms_total / 1000.0)
+
+    # ---- the env-step kernel alone at the bench's batch (the rollout applies the step inside the MPNN kernel) ----
+    env_small = None
+    if rank == 0:
+        gen = torch.Generator(device="cuda").manual_seed(11)
+        acts = [torch.randint(0, n, (B,), generator=gen, device="cuda", dtype=torch.int32) for _ in range(36)]
+        head.env.reset(spins=head.spins, graph_idx=head.gidx)
+        for a in acts[:4]:
+            head.env.step(a)
+        torch.cuda.synchronize()
+        L.eco_profile_enable(1)
+        for a in acts[4:]:
+            head.env.step(a)
+        ems, en = prof_read(1)
+        L.eco_profile_enable(0)
+        env_small = (ems / max(en, 1), en)
 
     # ---- e2e: host buffers in, host buffers out, through the C-ABI session (H2D + D2H inside the timing) ----
     sess = engine.HostSession(G, n, B, T, 1.0 / n, wd, impl=impl)
@@ -559,20 +582,28 @@ def run_ours(args):
         if head.used_impl == "tcgen05" and os.path.exists(tpath):      # dram bytes per launch from the committed ncu capture
             tj = json.load(open(tpath))["mpnn_tc_kernel"]
             traffic, traffic_src = tj["dram_bytes_per_launch"], tj.get("source")
-        roof = {"bound": "tensor", "kernel": "mpnn_forward_argmax (%s)" % head.used_impl, "achieved": ach,
-                "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": traffic,
-                "traffic_source": traffic_src,
+        # one-launch rollout: a launch covers T steps of [forward + argmax + env step]; traffic / bytes are per STEP
+        spl = T if r["one_launch"] else 1
+        roof = {"bound": "tensor",
+                "kernel": ("mpnn_tc_kernel, one launch per rollout: T x (forward + argmax + env step)" if r["one_launch"]
+                           else "mpnn_forward_argmax (%s)" % head.used_impl),
+                "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
+                "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes": int(B * (n * n + 3 * n * 4 + 16 + n * 4 + 4)),     # int8 J + features + degrees + action
-                "peak_source": pk["source"] + " (bf16 sustained)", "avg_launch_ms": avg_mpnn_s * 1e3,
-                "launches_timed": r["mpnn_n"], "launches": T * args.steps,
+                "traffic_and_bytes_are": "per rollout step (one forward over the batch)",
+                "peak_source": pk["source"] + " (bf16 sustained)", "avg_launch_ms": avg_mpnn_s * 1e3 * spl,
+                "steps_per_launch": spl, "ms_per_forward": avg_mpnn_s * 1e3,
+                "launches_timed": r["mpnn_n"] // spl, "launches": T * args.steps // spl,
                 "share_of_step": avg_mpnn_s * 1e3 * T * args.steps / ms_total,
-                "flops_per_launch": flops_mpnn(n) * B}
-        avg_env_s = r["env_ms"] / 1000.0
+                "flops_per_launch": flops_mpnn(n) * B * spl}
+        avg_env_s, env_n = (r["env_ms"] / 1000.0, r["env_n"]) if not r["one_launch"] else (env_small[0] / 1000.0, env_small[1])
         roof_env = {"bound": "hbm", "kernel": "env_step", "achieved": bytes_env(n) * B / avg_env_s / 1e9,
                     "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": bytes_env(n) * B / avg_env_s / 1e9 / pk["hbm_gbs"],
-                    "avg_launch_us": avg_env_s * 1e6, "launches_timed": r["env_n"],
-                    "share_of_step": avg_env_s * 1e3 * T * args.steps / ms_total,
-                    "note": "B=4096 moves only %.1f MB per launch: launch-latency bound; see env_only" %
+                    "avg_launch_us": avg_env_s * 1e6, "launches_timed": env_n,
+                    "share_of_step": None if r["one_launch"] else avg_env_s * 1e3 * T * args.steps / ms_total,
+                    "note": ("the env-step kernel launched alone at the bench's batch (inside the rollout the step is applied by "
+                             "the MPNN kernel's tail warp); " if r["one_launch"] else "") +
+                            "B=4096 moves only %.1f MB per launch: launch-latency bound; see env_only" %
                             (bytes_env(n) * B / 1e6)}
         cpu = None
         if not args.skip_cpu and world == 1:          # side numbers: rank 0 at N = 1 only (the other ranks would wait)

@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libecodqn_b200.so")
+LIB_PATH = os.environ.get("ECO_DQN_B200_LIB") or os.path.join(HERE, "lib", "libecodqn_b200.so")   # (override: kernel experiments)
 
 ECO_OK, ECO_ERR_INVALID, ECO_ERR_UNSUPPORTED, ECO_ERR_CUDA, ECO_ERR_STATE = 0, -1, -2, -3, -4
 POLICY_ACTIONS, POLICY_NETWORK, POLICY_GREEDY = 0, 1, 2

@@ -25,10 +25,11 @@ void count_launch(int n) { g_launches += n; }
 struct Prof {
     bool on = false;
     int stride = 1;
-    long long count[2] = {0, 0};
-    bool sampled[2] = {false, false};
+    long long count[3] = {0, 0, 0};
+    long long units[3] = {0, 0, 0};    // what eco_profile_read reports as `launches`: recorded launches (kinds 0, 1), rollout steps (2)
+    bool sampled[3] = {false, false, false};
     std::vector<cudaEvent_t> pool;
-    std::vector<cudaEvent_t> rec[2];   // start/stop pairs per kind
+    std::vector<cudaEvent_t> rec[3];   // start/stop pairs per kind
     cudaEvent_t get() {
         cudaEvent_t e;
         if (!pool.empty()) { e = pool.back(); pool.pop_back(); return e; }
@@ -39,10 +40,11 @@ struct Prof {
 static Prof g_prof;
 // every `stride`-th launch of a kind is bracketed by two events (an event record between two kernels costs about as much
 // as a small kernel: bracketing every launch of a 400-step rollout adds ~4 % to it)
-void prof_begin(int kind, cudaStream_t st) {
+void prof_begin(int kind, cudaStream_t st, int units) {
     if (!g_prof.on) return;
-    g_prof.sampled[kind] = (g_prof.count[kind]++ % g_prof.stride) == 0;
+    g_prof.sampled[kind] = kind == ECO_PROF_ROLLOUT || (g_prof.count[kind]++ % g_prof.stride) == 0;
     if (!g_prof.sampled[kind]) return;
+    g_prof.units[kind] += units;
     cudaEvent_t e = g_prof.get();
     cudaEventRecord(e, st);
     g_prof.rec[kind].push_back(e);
@@ -153,18 +155,18 @@ int64_t eco_launch_count(int reset) {
 }
 
 int eco_profile_enable(int on) {
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < 3; ++k) {
         for (cudaEvent_t e : g_prof.rec[k]) g_prof.pool.push_back(e);
         g_prof.rec[k].clear();
+        g_prof.count[k] = g_prof.units[k] = 0;
     }
     g_prof.on = on != 0;
     g_prof.stride = on > 1 ? on : 1;
-    g_prof.count[0] = g_prof.count[1] = 0;
     return ECO_OK;
 }
 
 int eco_profile_read(int kind, double* total_ms, int64_t* launches) {
-    ECO_CHECK_ARG(kind >= 0 && kind < 2 && total_ms && launches, ECO_ERR_INVALID, "eco_profile_read: bad argument");
+    ECO_CHECK_ARG(kind >= 0 && kind < 3 && total_ms && launches, ECO_ERR_INVALID, "eco_profile_read: bad argument");
     ECO_CUDA(cudaDeviceSynchronize());
     double tot = 0.0;
     const auto& r = g_prof.rec[kind];
@@ -174,7 +176,7 @@ int eco_profile_read(int kind, double* total_ms, int64_t* launches) {
         tot += ms;
     }
     *total_ms = tot;
-    *launches = (int64_t)(r.size() / 2);
+    *launches = (int64_t)g_prof.units[kind];
     return ECO_OK;
 }
 
@@ -419,18 +421,15 @@ int eco_rollout(const eco_graphs_t* g, eco_env_t* env, const eco_mpnn_t* w, int3
     if (rc) return rc;
     const bool masked = (env->reserved & ECO_ENV_IRREVERSIBLE) != 0;   // argmax over the spins still at -1 only
     float* qbuf = masked ? (float*)((char*)scratch + mpnn_kernel_scratch_bytes(env->B, env->N, impl)) : nullptr;
-    // Opt-in (ECO_FUSED_STEP=1): one launch per step, the resident tensor-core kernel's tail warp applies the flip itself
-    // (mpnn_tc.cu, FUSED).  Measured at BA-200 x 4096: 0.556 ms per step against 0.553 ms for the two launches -- the fused
-    // kernel ends with the last episode's readout + env step exposed -- so two launches stay the default.
-    static const bool fuse = getenv("ECO_FUSED_STEP") != nullptr;
-    if (fuse && !masked && pick_impl(g, w, impl) == ECO_MPNN_TCGEN05 && g->N <= 208 && w->packed && mpnn_tc_can_fuse(g, env)) {
-        for (int t = 0; t < n_steps; ++t) {
-            rc = launch_mpnn_tc_fused(g, w, env->B, env->graph_idx, env->xn, env->xg, norm_max, nullptr, act, scratch, env, ha,
-                                      hr, hs, st);
-            if (rc) return rc;
-        }
-        return ECO_OK;
-    }
+    // The ECO-DQN configuration on the resident tensor-core kernel (N <= 208, >= 2 episodes per SM): the WHOLE rollout is one
+    // launch -- the kernel's tail warp applies each flip itself and every CTA takes its own episodes through all n_steps steps
+    // (mpnn_tc.cu, FUSED; episodes never interact, so there is nothing to synchronise between steps).  Bit-identical to the
+    // two-launches-per-step path below (tests/test_gpu_round2.py), which ECO_FUSED_STEP=0 selects.
+    static const bool fuse = !(getenv("ECO_FUSED_STEP") && atoi(getenv("ECO_FUSED_STEP")) == 0);
+    if (fuse && n_steps > 0 && !masked && pick_impl(g, w, impl) == ECO_MPNN_TCGEN05 && g->N <= 208 && w->packed &&
+        mpnn_tc_can_fuse(g, env))
+        return launch_mpnn_tc_fused(g, w, env->B, env->graph_idx, env->xn, env->xg, norm_max, nullptr, act, scratch, env, n_steps,
+                                    ha, hr, hs, st);
     for (int t = 0; t < n_steps; ++t) {
         rc = eco_mpnn_forward(g, w, env->B, env->graph_idx, env->xn, env->xg, norm_max, qbuf, masked ? nullptr : act,
                               scratch, impl, stream);

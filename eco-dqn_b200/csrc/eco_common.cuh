@@ -18,7 +18,7 @@ __host__ __device__ inline int tab_stride(int NP) { return 2 * NP + 4; }
 // ---- error plumbing -------------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
-void prof_begin(int kind, cudaStream_t st);   // no-ops unless eco_profile_enable(1)
+void prof_begin(int kind, cudaStream_t st, int units = 1);   // no-ops unless eco_profile_enable(1)
 void prof_end(int kind, cudaStream_t st);
 
 #define ECO_CHECK_ARG(cond, code, ...)            \
@@ -121,7 +121,7 @@ int launch_mpnn_tc(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int3
 bool mpnn_tc_can_fuse(const eco_graphs_t* g, const eco_env_t* env);
 int launch_mpnn_tc_fused(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int32_t* gidx, const float* xn,
                          const float* xg, float norm_max, float* q, int32_t* actions, void* scratch, const eco_env_t* fused,
-                         int32_t* ha, double* hr, double* hs, cudaStream_t st);
+                         int n_steps, int32_t* ha, double* hr, double* hs, cudaStream_t st);
 size_t mpnn_tc_scratch_bytes(int B, int N);
 size_t mpnn_tc_packed_bytes();
 int launch_mpnn_pack(const eco_mpnn_t* w, void* packed, cudaStream_t st);

@@ -257,11 +257,13 @@ constexpr int LSMEM = 2 * 3 * TILE_BYTES;
 // 8 MMAs: acc (+)= W[:, 64-feature group at TMEM column tw] * X, X a tile used as MN-major B operand
 __device__ __forceinline__ void issue_linear_half(uint32_t tmem, uint32_t acc_col, uint32_t tw, const unsigned char* x, int width,
                                                   bool accumulate) {
+    // (the lo rows of X meet W_hi only: M = 64 covers TMEM lanes 32q + 0..15, the hi rows of the stacked order -- mpnn_tc.cu)
     const uint32_t idesc = instr_desc_bf16(128, width, false, true);
+    const uint32_t idesc_lo = instr_desc_bf16(64, width, false, true);
     const uint64_t d = smem_desc(smem_u32(x), /*LBO (k groups)*/ 128, /*SBO (vertex groups)*/ 2048);
 #pragma unroll
     for (int i = 0; i < 8; ++i)     // i = 2*kq + s: features 16kq..16kq+15, split s
-        mma_ts(tmem + acc_col, tmem + tw + 8 * (i >> 1), d + (uint64_t)(16 * i), idesc, accumulate || i > 0);
+        mma_ts(tmem + acc_col, tmem + tw + 8 * (i >> 1), d + (uint64_t)(16 * i), (i & 1) ? idesc_lo : idesc, accumulate || i > 0);
 }
 
 template <int MODE>

@@ -12,7 +12,8 @@
 //                 0.03 of the parity tolerance 1e-3 |q| + 1e-4 max|q|; one fp16 / tf32 term per operand measured 10-20x
 //                 OVER it, tools/precision_study.py).  hi and lo rows are STACKED in the M dimension (128 = 64 features x
 //                 {hi,lo}), so one M=128 MMA chain yields both partial products and the split costs no extra
-//                 instructions for the aggregation (A in {-1,0,1} is exact) and 2 chains (4 products) for the linears.
+//                 instructions for the aggregation (A in {-1,0,1} is exact) and 2 chains for the linears: W_hi X_hi, W_lo X_hi
+//                 (M = 128) and W_hi X_lo (M = 64, the hi rows only: lo x lo is never computed -- issue_part()).
 //                 Stacked row order r = 32q + 16s + t  <->  feature 16q + t, s in {hi, lo}: the two halves of a
 //                 feature sit in the same TMEM lane quadrant, so one warp adds them after two 16x256b loads.
 //   smem          adjacency bf16 (N x N, K-major core matrices), H^T and E^T stacked hi/lo (one copy serves as
@@ -211,24 +212,33 @@ __device__ __forceinline__ void store_block(const Ctx& c, unsigned char* buf, in
 // used MN-major: k-step kq covers features 16kq..16kq+15, split s selects the hi / lo rows (256-byte steps).
 __device__ __forceinline__ void issue_part(const Ctx& c, uint32_t acc_col, uint32_t tw, const unsigned char* x, int cb0,
                                            int width, bool accumulate) {
+    // The lo x lo product is not computed: the MMAs that read the lo rows of X are issued with M = 64, whose 64 A / D rows are
+    // TMEM lanes 32q + 0..15 -- exactly the hi rows of the stacked order -- so they add W_hi X_lo to the hi rows and leave the lo
+    // rows (W_lo X_hi) alone.  Same cycles as M = 128, a quarter fewer MACs in every linear: the kernel runs against the
+    // board's power cap, and this alone took the SM clock from ~1.90 back to 1.965 GHz (+1.3 % env-steps/s).
     const uint32_t idesc = instr_desc_bf16(128, width, false, true);
+    const uint32_t idesc_lo = instr_desc_bf16(64, width, false, true);
     const uint64_t d = smem_desc(smem_u32(x) + cb0 * 2048, /*LBO (k groups)*/ 128, /*SBO (vertex groups)*/ 2048);
 #pragma unroll
     for (int i = 0; i < 8; ++i)     // i = 2*kq + s
-        mma_ts(c.tmem + acc_col, c.tmem + tw + 8 * (i >> 1), d + (uint64_t)(16 * i), idesc, accumulate || i > 0);
+        mma_ts(c.tmem + acc_col, c.tmem + tw + 8 * (i >> 1), d + (uint64_t)(16 * i), (i & 1) ? idesc_lo : idesc, accumulate || i > 0);
 }
 
 // PACKED: K = packK >= 2 small graphs (NP <= 96) are processed side by side as ONE block-diagonal graph of K * NP <= 192
 // vertices ("pack"): the tensor part below does not know about it; only the inputs (per-vertex episode), the operand
 // images (diagonal blocks), feature 63 and the readout (pooling / argmax per episode) are per episode.
 // FUSED (rollouts of the ECO-DQN configuration): the warp that has just taken an episode's argmax also applies the flip --
-// SpinSystemBase.step for that episode (env_step_device.cuh), state and next observations written for the next launch --
-// so a rollout step is ONE launch instead of two.
+// SpinSystemBase.step for that episode (env_step_device.cuh), state and next observations written back -- and, because
+// episodes never interact, the CTA then simply carries on: it takes ITS episodes through all `n_steps` steps of the rollout
+// in one launch (item = (step, episode), step-major), with no grid-wide synchronisation at all.  An episode's next
+// observations are read (cp.async.cg: L2, never a stale L1 line) at least one whole item after the tail warp wrote and
+// fenced them, which needs >= 2 episodes per CTA (checked by the launcher).  A rollout is ONE launch instead of 2 T.
 struct FusedEnv {
     eco_env_t env;
     int32_t* hist_a;
     double* hist_r;
     double* hist_s;
+    int n_steps;
 };
 
 template <bool PACKED, bool TLINE, bool FUSED = false>
@@ -267,6 +277,10 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     c.NP = K * NPs; c.NB = c.NP >> 3; c.N = PACKED ? c.NP : g.N;
     const int N = c.N, NP = c.NP, NB = c.NB;
     const int npacks = (B + K - 1) / K;
+    // this CTA's work: episodes (packs) blockIdx.x, + gridDim.x, ...; FUSED: that list once per rollout step
+    const int n_e = (int)blockIdx.x < npacks ? (npacks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int n_items = n_e * (FUSED ? fe.n_steps : 1);
+    auto item_ep = [&](int it) { return (int)blockIdx.x + (FUSED ? it % n_e : it) * (int)gridDim.x; };
     auto vertex_ok = [&](int n) { return PACKED ? (n % NPs) < Ns : n < N; };     // not a padding vertex
     // PACKED extras live behind the (at most 192 x 192) adjacency image
     float* rdmaxv = reinterpret_cast<float*>(smem + SM_A + PACK_NPMAX * PACK_NPMAX * 2);   // [192] 1 / deg_max of the vertex's graph
@@ -363,7 +377,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         if (c.warp < NWARPS) { zero_image(smem + SM_A); zero_image(smem + SM_ABS); }
         __syncthreads();
     }
-    if (c.tid == 0 && (int)blockIdx.x < npacks) { fetch_ops(0, blockIdx.x); fetch_ops(1, blockIdx.x); }
+    if (c.tid == 0 && n_items > 0) { fetch_ops(0, blockIdx.x); fetch_ops(1, blockIdx.x); }
 
     // per-episode inputs, requested one episode ahead (during the previous readout): this thread's vertex observations
     // and degree, the four graph-level observations, the graph's maximum degree
@@ -476,9 +490,9 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             const int row = i / per_row, col = 4 * (i % per_row);
             const float* src = row < 3 ? xn + ((size_t)e * 3 + row) * NP + col : g.deg + (size_t)ge * NP + col;
             float* dst = xf + (row < 3 ? row : XF_DEG) * NPMAX + col;
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
         } else if (i == 4 * per_row) {
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(xf + XF_GL * NPMAX)), "l"(xg + (size_t)e * 4) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(xf + XF_GL * NPMAX)), "l"(xg + (size_t)e * 4) : "memory");
         } else if (i == 4 * per_row + 1) {
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(xf + XF_GMAX * NPMAX)), "l"(g.gstat + (size_t)ge * 4) : "memory");
         }
@@ -492,7 +506,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         // ================= contraction issuer ===============================================================
 
         uint32_t sp0 = 0, sp1 = 0, op = 0;
-        for (int b = blockIdx.x; b < npacks; b += gridDim.x) {
+        for (int it = 0; it < n_items; ++it) {
             mbar_wait(&bar_ops[0], op);               // A and |A| of this episode have landed (async proxy -> async proxy)
             mbar_wait(&bar_ops[1], op); op ^= 1u;
             TL(51);
@@ -542,10 +556,11 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     if (!PACKED && c.warp == NWARPS + 3) {
         // ================= episode tail ====================================================================
         uint32_t ph = 0;
-        for (int b = blockIdx.x; b < npacks; b += gridDim.x) {
+        for (int it = 0; it < n_items; ++it) {
             mbar_wait(&tail_sig, ph);
             ph ^= 1u;
-            readout_warp_b(b, readout_warp_a());
+            readout_warp_b(item_ep(it), readout_warp_a());
+            if (FUSED) __threadfence();                    // the episode's new state / observations, before the arrival below
             __syncwarp();
             if (c.lane == 0) mbar_arrive(&tail_done);      // the partial sums may be overwritten (next episode's last layer)
         }
@@ -561,7 +576,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             ph[k & 1] ^= 1u;
             tc_fence_after();
         };
-        for (int b = blockIdx.x; b < npacks; b += gridDim.x) {
+        for (int it = 0; it < n_items; ++it) {
             wait_sig(0);                                                                 // g(a) is in E^T[a]
             if (elect_one()) { issue_part(c, T_ACC0 + cA0, T_WEF, sE, cA0 >> 3, cAw, false); mma_commit(c.bar_grp); }
             __syncwarp();
@@ -614,7 +629,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             }
         }
     }
-    if (c.warp < NWARPS && (int)blockIdx.x < npacks) {
+    if (c.warp < NWARPS && n_items > 0) {
         if (PACKED) load_inputs(blockIdx.x);
         else if (c.grp == 1) stage_inputs(blockIdx.x);
     }
@@ -680,7 +695,10 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     };
     int last_b = -1;
 
-    for (int b = blockIdx.x; b < npacks && c.warp < NWARPS; b += gridDim.x) {
+    for (int it = 0; it < n_items && c.warp < NWARPS; ++it) {
+        const int b = item_ep(it);
+        const bool has_next = it + 1 < n_items;
+        const int b_next = has_next ? item_ep(it + 1) : 0;
         TL(1);
         if (!PACKED) {                                      // the staged inputs of this episode have landed
             asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -918,7 +936,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             }
             TL(23);
             // A has no reader left once the LAST half retired (the halves retire in order)
-            if (l == 2 && c.tid == (chunk_split < nchunks ? THREADS / 2 : 0) && b + (int)gridDim.x < npacks) fetch_ops(0, b + gridDim.x);
+            if (l == 2 && c.tid == (chunk_split < nchunks ? THREADS / 2 : 0) && has_next) fetch_ops(0, b_next);
             // h' of a chunk: next layer's H^T, or (last layer) the readout partials straight from the fp32 registers
             auto epi_h = [&](int ci, int c0, int width) {
                 if (l < 2) {
@@ -1003,7 +1021,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                     wait_g2(c);                                                             // B2: M1(b)
                     wait_g3(c);                                                             // B3: M2h(b)
                     // the chunk buffer has no reader left in this episode: the next episode's inputs go there
-                    if (!PACKED && l == 2 && c.grp == 1 && b + (int)gridDim.x < npacks) stage_inputs(b + gridDim.x);
+                    if (!PACKED && l == 2 && c.grp == 1 && has_next) stage_inputs(b_next);
                     TL(33);
                     epi_m(cB0, cBw);
                     signal_issuer(0);                       // S4 -> M2m(b) (B1)
@@ -1020,16 +1038,16 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
 
         // ================= end of the episode's tensor work ==================================================
         // (its readout runs later, under the next episode's edge contraction)
-        if (b + (int)gridDim.x < npacks) {                // next episode's inputs: in flight from here (or earlier, above)
-            if (PACKED) load_inputs(b + gridDim.x);
-            else if (c.grp == 1 && nmine < 2) stage_inputs(b + gridDim.x);
+        if (has_next) {                                   // next episode's inputs: in flight from here (or earlier, above)
+            if (PACKED) load_inputs(b_next);
+            else if (c.grp == 1 && nmine < 2) stage_inputs(b_next);
         }
         workers_sync();
-        if (PACKED && b + (int)gridDim.x < npacks) {      // the off-diagonal blocks of |A| were overwritten by H / E: clear
+        if (PACKED && has_next) {                         // the off-diagonal blocks of |A| were overwritten by H / E: clear
             zero_image(smem + SM_ABS);
             workers_sync();
         }
-        if (c.tid == 0 && b + (int)gridDim.x < npacks) fetch_ops(1, b + gridDim.x);   // H / E (which |A| overlays) have no reader left
+        if (c.tid == 0 && has_next) fetch_ops(1, b_next);   // H / E (which |A| overlays) have no reader left
         if (!PACKED && c.tid == 0) mbar_arrive(&tail_sig);       // -> tail warp: this episode's partial sums are complete
         last_b = b;
         TL(41);
@@ -1061,17 +1079,19 @@ int launch_mpnn_pack(const eco_mpnn_t* w, void* packed, cudaStream_t st) {
 // implements (reversible spins, BLS reward, Max-Cut).
 bool mpnn_tc_can_fuse(const eco_graphs_t* g, const eco_env_t* env) {
     const bool packed = PACK_NPMAX / g->NP >= 2 && env->B >= 2;
-    return mpnn_tc_supported(g) && !packed && env->reserved == 0 && !(g->reserved & ECO_GRAPHS_MIN_CUT) && env->N == g->N;
+    // (>= 2 episodes per CTA: an episode's next observations are staged one item after its tail wrote them)
+    return mpnn_tc_supported(g) && !packed && env->reserved == 0 && !(g->reserved & ECO_GRAPHS_MIN_CUT) && env->N == g->N &&
+           env->B >= 2 * device_sm_count();
 }
 
 int launch_mpnn_tc(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int32_t* gidx, const float* xn,
                    const float* xg, float norm_max, float* q, int32_t* actions, void* scratch, cudaStream_t st) {
-    return launch_mpnn_tc_fused(g, w, B, gidx, xn, xg, norm_max, q, actions, scratch, nullptr, nullptr, nullptr, nullptr, st);
+    return launch_mpnn_tc_fused(g, w, B, gidx, xn, xg, norm_max, q, actions, scratch, nullptr, 1, nullptr, nullptr, nullptr, st);
 }
 
 int launch_mpnn_tc_fused(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int32_t* gidx, const float* xn,
                          const float* xg, float norm_max, float* q, int32_t* actions, void* scratch, const eco_env_t* fused,
-                         int32_t* ha, double* hr, double* hs, cudaStream_t st) {
+                         int n_steps, int32_t* ha, double* hr, double* hs, cudaStream_t st) {
     static unsigned long long attr_set = 0;
     const int n_sm = device_sm_count();
     if (first_use_on_device(&attr_set)) {
@@ -1085,18 +1105,23 @@ int launch_mpnn_tc_fused(const eco_graphs_t* g, const eco_mpnn_t* w, int B, cons
     if (fused && packed) { set_error("launch_mpnn_tc_fused: packed batches cannot be fused"); return ECO_ERR_INVALID; }
     const int units = packed ? (B + packK - 1) / packK : B;
     const int grid = units < n_sm ? units : n_sm;
-    prof_begin(ECO_PROF_MPNN, st);
+    const int prof_kind = fused ? ECO_PROF_ROLLOUT : ECO_PROF_MPNN;
+    prof_begin(prof_kind, st, fused ? n_steps : 1);
     static const bool timeline = getenv("ECO_TC_TIMELINE") != nullptr;
     if (timeline) ECO_CUDA(cudaMemsetAsync(scratch, 0, (NWARPS + ISSUERS) * 1024 * 8, st));
     unsigned long long* dbg = timeline ? (unsigned long long*)scratch : nullptr;
     // (the clock trace of tools/tc_timeline.py is its own instantiation: the production kernels carry no trace code)
     FusedEnv fe{};
-    if (fused) { fe.env = *fused; fe.hist_a = ha; fe.hist_r = hr; fe.hist_s = hs; }
+    fe.n_steps = 1;
+    if (fused) {
+        if (n_steps < 1 || B < 2 * grid) { set_error("launch_mpnn_tc_fused: needs n_steps >= 1 and two episodes per CTA"); return ECO_ERR_INVALID; }
+        fe.env = *fused; fe.hist_a = ha; fe.hist_r = hr; fe.hist_s = hs; fe.n_steps = n_steps;
+    }
     if (packed) mpnn_tc_kernel<true, false><<<grid, LAUNCH_THREADS, SM_TOTAL, st>>>(*g, *w, B, gidx, xn, xg, norm_max, q, actions, nullptr, packK, fe);
     else if (dbg) mpnn_tc_kernel<false, true><<<grid, LAUNCH_THREADS, SM_TOTAL, st>>>(*g, *w, B, gidx, xn, xg, norm_max, q, actions, dbg, 1, fe);
     else if (fused) mpnn_tc_kernel<false, false, true><<<grid, LAUNCH_THREADS, SM_TOTAL, st>>>(*g, *w, B, gidx, xn, xg, norm_max, q, actions, nullptr, 1, fe);
     else mpnn_tc_kernel<false, false><<<grid, LAUNCH_THREADS, SM_TOTAL, st>>>(*g, *w, B, gidx, xn, xg, norm_max, q, actions, nullptr, 1, fe);
-    prof_end(ECO_PROF_MPNN, st);
+    prof_end(prof_kind, st);
     ECO_LAUNCH_CHECK();
     return ECO_OK;
 }

@@ -296,9 +296,12 @@ int64_t eco_launch_count(int reset);
 /* Per-kernel device timing for bench.py's roofline: while enabled with on = k >= 1, every k-th MPNN forward kernel
  * (kind 0) and every k-th env-step kernel (kind 1) is bracketed by CUDA events on its launch stream (an event record
  * between two kernels costs about as much as a small kernel, so bench.py samples).  eco_profile_read synchronises the
- * device and returns the summed duration (ms) and the number of launches recorded since enabling. */
+ * device and returns the summed duration (ms) and the number of launches recorded since enabling.  Kind 2: the one-launch
+ * rollouts of eco_rollout (MPNN forward + argmax + env step of every step inside one kernel): every such launch is
+ * recorded and `launches` counts the rollout STEPS it covered, so total / launches is the time per [forward + env step]. */
 #define ECO_PROF_MPNN 0
 #define ECO_PROF_ENV_STEP 1
+#define ECO_PROF_ROLLOUT 2
 int eco_profile_enable(int on);
 int eco_profile_read(int kind, double* total_ms, int64_t* launches);
 

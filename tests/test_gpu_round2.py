@@ -341,16 +341,18 @@ np.savez(sys.argv[2], ha=ha.cpu().numpy(), hr=hr.cpu().numpy(), hs=hs.cpu().nump
 """
 
 
-def test_fused_step_option_equals_two_launches(eng, tmp_path):
-    """ECO_FUSED_STEP=1 (the MPNN kernel's tail warp applies the flip it has just chosen, one launch per step) against the
-    default two launches per step: actions, fp64 rewards and scores, best cuts / spins, the next observations and every
-    episode record bit for bit.  (The option is read once per process: the fused run is a child process.)"""
+@pytest.mark.parametrize("B", [300, 701])
+def test_one_launch_rollout_equals_two_launches_per_step(eng, tmp_path, B):
+    """The default rollout of the ECO-DQN configuration on the resident kernel -- ONE launch: the MPNN kernel's tail warp
+    applies the flip it has just chosen and every CTA takes its episodes through all steps -- against two launches per step
+    (ECO_FUSED_STEP=0): actions, fp64 rewards and scores, best cuts / spins, the next observations and every episode record
+    bit for bit, with two and with up to five episodes per CTA.  (The option is read once per process: child processes.)"""
     import subprocess
     import sys
     from oracle.mpnn import weights_from_npz
     z = load("er200_g0")
     rng = np.random.default_rng(2)
-    n, B, steps = 200, 300, 25
+    n, steps = 200, 25
     Js = np.stack([z["J"], _random_graphs(rng, 1, n, 0.1)[0]])
     gidx = (np.arange(B) % 2).astype(np.int32)
     spins = (2 * rng.integers(0, 2, size=(B, n)) - 1).astype(np.int8)
@@ -359,9 +361,8 @@ def test_fused_step_option_equals_two_launches(eng, tmp_path):
     np.savez(inp, J=Js, gidx=gidx, spins=spins, steps=steps, **{"w_" + k: v for k, v in wd.items()})
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = {}
-    for tag, extra in (("two", {}), ("fused", {"ECO_FUSED_STEP": "1"})):
+    for tag, extra in (("two", {"ECO_FUSED_STEP": "0"}), ("fused", {"ECO_FUSED_STEP": "1"})):
         env_vars = dict(os.environ, **extra)
-        env_vars.pop("ECO_FUSED_STEP", None) if tag == "two" else None
         subprocess.run([sys.executable, "-c", _FUSED_SCRIPT % root, inp, out], check=True, env=env_vars, timeout=300)
         res[tag] = {k: v.copy() for k, v in np.load(out).items()}
     for k in res["two"]:
