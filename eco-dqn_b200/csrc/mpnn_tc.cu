@@ -185,7 +185,8 @@ __device__ __forceinline__ void epilogue(const Ctx& c, uint32_t acc, int col0, i
         tmem_ld_wait();
         float v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(vh[i]) + __uint_as_float(vl[i]);
+        for (int i = 0; i < 8; i += 2)
+            add2(v[i], v[i + 1], __uint_as_float(vh[i]), __uint_as_float(vh[i + 1]), __uint_as_float(vl[i]), __uint_as_float(vl[i + 1]));
         fn(16 * blk, v);
     }
 }
@@ -775,10 +776,13 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                     const float rpa1 = fmaxf(pa1 + wxa[0], 0.f), rma1 = fmaxf(pa1 - wxa[0], 0.f);
                     const float rpb0 = fmaxf(pb0 + wxb[0], 0.f), rmb0 = fmaxf(pb0 - wxb[0], 0.f);
                     const float rpb1 = fmaxf(pb1 + wxb[0], 0.f), rmb1 = fmaxf(pb1 - wxb[0], 0.f);
-                    split2(rpa0 + rma0, rpa1 + rma1, sh[2 * half + 0], sl[2 * half + 0]);
-                    split2(rpb0 + rmb0, rpb1 + rmb1, sh[2 * half + 1], sl[2 * half + 1]);
-                    split2(rpa0 - rma0, rpa1 - rma1, dh[2 * half + 0], dl[2 * half + 0]);
-                    split2(rpb0 - rmb0, rpb1 - rmb1, dh[2 * half + 1], dl[2 * half + 1]);
+                    float sa0, sa1, sb0, sb1, da0, da1, db0, db1;
+                    add2(sa0, sa1, rpa0, rpa1, rma0, rma1); add2(sb0, sb1, rpb0, rpb1, rmb0, rmb1);
+                    sub2(da0, da1, rpa0, rpa1, rma0, rma1); sub2(db0, db1, rpb0, rpb1, rmb0, rmb1);
+                    split2(sa0, sa1, sh[2 * half + 0], sl[2 * half + 0]);
+                    split2(sb0, sb1, sh[2 * half + 1], sl[2 * half + 1]);
+                    split2(da0, da1, dh[2 * half + 0], dl[2 * half + 0]);
+                    split2(db0, db1, dh[2 * half + 1], dl[2 * half + 1]);
                 }
                 tmem_st_16x128b_x2(tmem_addr(c.tmem, 32 * c.q, T_S + 8 * blk), sh);
                 tmem_st_16x128b_x2(tmem_addr(c.tmem, 32 * c.q + 16, T_S + 8 * blk), sl);
@@ -820,7 +824,10 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                     const float2 r0 = *reinterpret_cast<const float2*>(rdeg + n0), r1 = *reinterpret_cast<const float2*>(rdeg + n0 + 8);
                     const float rd[4] = {r0.x, r0.y, r1.x, r1.y};
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = (0.5f * v[i]) * rd[2 * (i >> 2) + (i & 1)];
+                    for (int i = 0; i < 8; i += 2) {
+                        mul2(v[i], v[i + 1], v[i], v[i + 1], 0.5f, 0.5f);
+                        mul2(v[i], v[i + 1], v[i], v[i + 1], rd[2 * (i >> 2)], rd[2 * (i >> 2) + 1]);
+                    }
                     if (has63) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {                   // v[2], v[3], v[6], v[7]: columns n0 + {0, 1, 8, 9}
@@ -887,7 +894,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                 const float2 r0 = *reinterpret_cast<const float2*>(rdeg + n0), r1 = *reinterpret_cast<const float2*>(rdeg + n0 + 8);
                 const float rd[4] = {r0.x, r0.y, r1.x, r1.y};
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = v[i] * rd[2 * (i >> 2) + (i & 1)];
+                for (int i = 0; i < 8; i += 2) mul2(v[i], v[i + 1], v[i], v[i + 1], rd[2 * (i >> 2)], rd[2 * (i >> 2) + 1]);
                 if (!waited) { wait_grp(c); waited = true; }           // the previous reader of the chunk buffer retired
                 store_block(c, sT, bc, v);
             });

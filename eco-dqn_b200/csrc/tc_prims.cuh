@@ -163,6 +163,30 @@ __device__ __forceinline__ void tmem_st_16x128b_x2(uint32_t taddr, const uint32_
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// ---- packed fp32 (sm_100: two IEEE operations per instruction, FADD2 / FMUL2 on an even register pair) ----
+// Bit-identical to the scalar forms; used where the epilogues add / scale neighbouring accumulator columns.
+__device__ __forceinline__ void add2(float& x0, float& x1, float a0, float a1, float b0, float b1) {
+    uint64_t A, B, D;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(B) : "f"(b0), "f"(b1));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(D) : "l"(A), "l"(B));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(D));
+}
+__device__ __forceinline__ void sub2(float& x0, float& x1, float a0, float a1, float b0, float b1) {
+    uint64_t A, B, D;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(B) : "f"(b0), "f"(b1));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(D) : "l"(A), "l"(B));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(D));
+}
+__device__ __forceinline__ void mul2(float& x0, float& x1, float a0, float a1, float b0, float b1) {
+    uint64_t A, B, D;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(B) : "f"(b0), "f"(b1));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(D) : "l"(A), "l"(B));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(D));
+}
+
 // ---- bf16 hi/lo split ---------------------------------------------------------------------------------
 // x = hi + lo with hi = bf16(x), lo = bf16(x - hi): ~16 mantissa bits survive, A in {-1,0,1} is exact.
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {   // a -> low half, b -> high half
@@ -173,7 +197,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {   // a -> lo
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
     hi = pack_bf16x2(a, b);
     const float ah = __uint_as_float(hi << 16), bh = __uint_as_float(hi & 0xFFFF0000u);
-    lo = pack_bf16x2(a - ah, b - bh);
+    float la, lb;
+    sub2(la, lb, a, b, ah, bh);
+    lo = pack_bf16x2(la, lb);
 }
 
 }  // namespace tc
