@@ -769,13 +769,14 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
 #pragma unroll
                     for (int k = 0; k < NOBS; ++k) {
                         const float2 x = *reinterpret_cast<const float2*>(xf + k * NPMAX + n0);
-                        pa0 = fmaf(wxa[1 + k], x.x, pa0); pa1 = fmaf(wxa[1 + k], x.y, pa1);
-                        pb0 = fmaf(wxb[1 + k], x.x, pb0); pb1 = fmaf(wxb[1 + k], x.y, pb1);
+                        fma2(pa0, pa1, wxa[1 + k], wxa[1 + k], x.x, x.y, pa0, pa1);
+                        fma2(pb0, pb1, wxb[1 + k], wxb[1 + k], x.x, x.y, pb0, pb1);
                     }
-                    const float rpa0 = fmaxf(pa0 + wxa[0], 0.f), rma0 = fmaxf(pa0 - wxa[0], 0.f);
-                    const float rpa1 = fmaxf(pa1 + wxa[0], 0.f), rma1 = fmaxf(pa1 - wxa[0], 0.f);
-                    const float rpb0 = fmaxf(pb0 + wxb[0], 0.f), rmb0 = fmaxf(pb0 - wxb[0], 0.f);
-                    const float rpb1 = fmaxf(pb1 + wxb[0], 0.f), rmb1 = fmaxf(pb1 - wxb[0], 0.f);
+                    float rpa0, rpa1, rma0, rma1, rpb0, rpb1, rmb0, rmb1;
+                    add2(rpa0, rpa1, pa0, pa1, wxa[0], wxa[0]); sub2(rma0, rma1, pa0, pa1, wxa[0], wxa[0]);
+                    add2(rpb0, rpb1, pb0, pb1, wxb[0], wxb[0]); sub2(rmb0, rmb1, pb0, pb1, wxb[0], wxb[0]);
+                    rpa0 = fmaxf(rpa0, 0.f); rpa1 = fmaxf(rpa1, 0.f); rma0 = fmaxf(rma0, 0.f); rma1 = fmaxf(rma1, 0.f);
+                    rpb0 = fmaxf(rpb0, 0.f); rpb1 = fmaxf(rpb1, 0.f); rmb0 = fmaxf(rmb0, 0.f); rmb1 = fmaxf(rmb1, 0.f);
                     float sa0, sa1, sb0, sb1, da0, da1, db0, db1;
                     add2(sa0, sa1, rpa0, rpa1, rma0, rma1); add2(sb0, sb1, rpb0, rpb1, rmb0, rmb1);
                     sub2(da0, da1, rpa0, rpa1, rma0, rma1); sub2(db0, db1, rpb0, rpb1, rmb0, rmb1);
@@ -851,8 +852,8 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
 #pragma unroll
                     for (int k = 0; k < NOBS; ++k) {
                         const float2 x = *reinterpret_cast<const float2*>(xf + k * NPMAX + n0);
-                        a0 = fmaf(wia[k], x.x, a0); a1 = fmaf(wia[k], x.y, a1);
-                        b0 = fmaf(wib[k], x.x, b0); b1 = fmaf(wib[k], x.y, b1);
+                        fma2(a0, a1, wia[k], wia[k], x.x, x.y, a0, a1);
+                        fma2(b0, b1, wib[k], wib[k], x.x, x.y, b0, b1);
                     }
                     v[4 * half + 0] = fmaxf(a0, 0.f); v[4 * half + 1] = fmaxf(a1, 0.f);
                     v[4 * half + 2] = fmaxf(b0, 0.f); v[4 * half + 3] = fmaxf(b1, 0.f);

@@ -179,6 +179,14 @@ __device__ __forceinline__ void sub2(float& x0, float& x1, float a0, float a1, f
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(D) : "l"(A), "l"(B));
     asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(D));
 }
+__device__ __forceinline__ void fma2(float& x0, float& x1, float a0, float a1, float b0, float b1, float c0, float c1) {
+    uint64_t A, B, Cc, D;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(B) : "f"(b0), "f"(b1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(Cc) : "f"(c0), "f"(c1));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(D) : "l"(A), "l"(B), "l"(Cc));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(D));
+}
 __device__ __forceinline__ void mul2(float& x0, float& x1, float a0, float a1, float b0, float b1) {
     uint64_t A, B, D;
     asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a0), "f"(a1));
