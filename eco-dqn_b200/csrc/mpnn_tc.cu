@@ -212,7 +212,7 @@ __device__ __forceinline__ void store_block(const Ctx& c, unsigned char* buf, in
 // Half of a linear layer on a chunk (single issuing thread): acc (+)= W[:, 64*part .. 64*part+63] * X, X a stacked buffer
 // used MN-major: k-step kq covers features 16kq..16kq+15, split s selects the hi / lo rows (256-byte steps).
 __device__ __forceinline__ void issue_part(const Ctx& c, uint32_t acc_col, uint32_t tw, const unsigned char* x, int cb0,
-                                           int width, bool accumulate) {
+                                           int width /* the MMAs' N */, bool accumulate) {
     // The lo x lo product is not computed: the MMAs that read the lo rows of X are issued with M = 64, whose 64 A / D rows are
     // TMEM lanes 32q + 0..15 -- exactly the hi rows of the stacked order -- so they add W_hi X_lo to the hi rows and leave the lo
     // rows (W_lo X_hi) alone.  Same cycles as M = 128, a quarter fewer MACs in every linear: the kernel runs against the
@@ -277,6 +277,11 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     const int NPs = g.NP, Ns = g.N;                       // per-episode sizes; NP / N below are the pack's
     c.NP = K * NPs; c.NB = c.NP >> 3; c.N = PACKED ? c.NP : g.N;
     const int N = c.N, NP = c.NP, NB = c.NB;
+    // vertex columns the MMAs produce: NP is a multiple of 16 (block granularity of the epilogues), the instruction's N only
+    // has to be a multiple of 8 -- when N <= NP - 8 the last eight (all-padding) columns are left out of every MMA (N = 200:
+    // 3.8 % of the MACs).  Those accumulator columns are zeroed once per launch, so whatever the epilogues carry through the
+    // padding columns of H^T / E^T stays finite (0 x NaN in an aggregation would poison real vertices).
+    const int N8 = PACKED ? NP : ((N + 7) & ~7);
     const int npacks = (B + K - 1) / K;
     // this CTA's work: episodes (packs) blockIdx.x, + gridDim.x, ...; FUSED: that list once per rollout step
     const int n_e = (int)blockIdx.x < npacks ? (npacks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -319,6 +324,12 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     __syncthreads();
     tc_fence_after();
     c.tmem = tmem_base_s;
+    if (c.warp < 4 && N8 < NP) {                           // ACC0 columns N8 .. NP-1, all 128 lanes: zero, once
+        const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        tmem_st_32x32b_x8(tmem_addr(c.tmem, 32 * c.q, T_ACC0 + N8), z);
+        tmem_st_wait();
+        tc_fence_before();
+    }
     const float dmax_set = norm_max > 0.f ? norm_max : *g.dmax;
     const int nsteps_A = NP >> 4;                         // k-steps over vertices
     const int nblocks = NP >> 4;
@@ -337,6 +348,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     const int nbm = c.grp == 0 ? nb0 : nb1;                // this group's blocks: chunk a = the first ceil(nbm / 2) of them
     const int cA0 = c.grp == 0 ? 0 : ncols0, cAw = nmine > 1 ? 16 * ((nbm + 1) / 2) : 16 * nbm;
     const int cB0 = cA0 + cAw, cBw = 16 * nbm - cAw;
+    const int cAm = min(cAw, N8 - cA0), cBm = min(cBw, N8 - cB0);      // the MMAs' N of the two chunks (>= 8)
     // worker warp -> its group's issuer: "my part of the operands of batch k is written" (smem: generic proxy, fenced for
     // the async proxy; TMEM loads of the accumulator the batch overwrites have completed)
     auto signal_issuer = [&](int k) {
@@ -518,7 +530,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                 tc_fence_after();
                 if (r == 0) TL(50);
                 if (elect_one()) {
-                    const uint32_t idesc = instr_desc_bf16(128, NP, false, false);
+                    const uint32_t idesc = instr_desc_bf16(128, N8, false, false);
                     const uint64_t bd_abs = smem_desc(smem_u32(sAbs), NB * 128, 128);
                     const uint64_t bd_a = smem_desc(smem_u32(sA), NB * 128, 128);
                     const uint64_t kstep = (uint64_t)((2 * NB * 128) >> 4);
@@ -540,7 +552,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                     const uint64_t ad = smem_desc(smem_u32(sH), 2048, 128);
                     const uint64_t bstep = (uint64_t)((2 * NB * 128) >> 4);
                     for (int half = 0; half < 2; ++half) {
-                        const int n0 = half ? ncols0 : 0, ncols = half ? NP - ncols0 : ncols0;
+                        const int n0 = half ? ncols0 : 0, ncols = half ? N8 - ncols0 : min(ncols0, N8);
                         if (ncols == 0) break;
                         const uint32_t idesc = instr_desc_bf16(128, ncols, false, false);
                         const uint64_t bd = smem_desc(smem_u32(sA) + (n0 >> 3) * 128, NB * 128, 128);
@@ -579,42 +591,42 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         };
         for (int it = 0; it < n_items; ++it) {
             wait_sig(0);                                                                 // g(a) is in E^T[a]
-            if (elect_one()) { issue_part(c, T_ACC0 + cA0, T_WEF, sE, cA0 >> 3, cAw, false); mma_commit(c.bar_grp); }
+            if (elect_one()) { issue_part(c, T_ACC0 + cA0, T_WEF, sE, cA0 >> 3, cAm, false); mma_commit(c.bar_grp); }
             __syncwarp();
             if (nmine > 1) {
                 wait_sig(1);
                 // (chunk b accumulates in ACC1, which is free until the first layer: its epilogue runs under layer 0's aggregation,
                 //  which overwrites every column of ACC0)
-                if (elect_one()) { issue_part(c, acc1, T_WEF, sE, cB0 >> 3, cBw, false); mma_commit(c.bar_g2); }
+                if (elect_one()) { issue_part(c, acc1, T_WEF, sE, cB0 >> 3, cBm, false); mma_commit(c.bar_g2); }
                 __syncwarp();
             }
             for (int l = 0; l < 3; ++l) {
                 wait_sig(0);                                                             // S0: layer weights in TMEM
-                if (elect_one()) issue_part(c, acc1, T_WM + 32, sE, cA0 >> 3, cAw, false);   // M1e(a), ahead
+                if (elect_one()) issue_part(c, acc1, T_WM + 32, sE, cA0 >> 3, cAm, false);   // M1e(a), ahead
                 __syncwarp();
                 wait_sig(1);                                                             // S1: agg(a) in the chunk buffer
                 if (elect_one()) {
-                    issue_part(c, acc1, T_WM, sT, 0, cAw, true);                         // M1a(a): += W_m[:, :64] agg
+                    issue_part(c, acc1, T_WM, sT, 0, cAm, true);                         // M1a(a): += W_m[:, :64] agg
                     mma_commit(c.bar_grp);                                               //   -> B1
-                    issue_part(c, T_ACC0 + cA0, T_WU, sH, cA0 >> 3, cAw, false);         // M2h(a): W_u[:, :64] h, ahead
+                    issue_part(c, T_ACC0 + cA0, T_WU, sH, cA0 >> 3, cAm, false);         // M2h(a): W_u[:, :64] h, ahead
                     mma_commit(c.bar_g2);                                                //   -> B2
                 }
                 __syncwarp();
                 if (nmine > 1) {
                     wait_sig(0);                                                         // S2: agg(b) in the chunk buffer
                     if (elect_one()) {
-                        issue_part(c, T_ACC0 + cB0, T_WU, sH, cB0 >> 3, cBw, false);     // M2h(b), ahead
+                        issue_part(c, T_ACC0 + cB0, T_WU, sH, cB0 >> 3, cBm, false);     // M2h(b), ahead
                         mma_commit(c.bar_g3);                                            //   -> B3
                     }
                     __syncwarp();
                 }
                 wait_sig(1);                                                             // S3: m(a) in H^T[a]
                 if (elect_one()) {
-                    issue_part(c, T_ACC0 + cA0, T_WU + 32, sH, cA0 >> 3, cAw, true);     // M2m(a): += W_u[:, 64:] m
+                    issue_part(c, T_ACC0 + cA0, T_WU + 32, sH, cA0 >> 3, cAm, true);     // M2m(a): += W_u[:, 64:] m
                     mma_commit(c.bar_grp);                                               //   -> B1
                     if (nmine > 1) {
-                        issue_part(c, acc1, T_WM + 32, sE, cB0 >> 3, cBw, false);        // M1(b) = W_m [agg ; e]
-                        issue_part(c, acc1, T_WM, sT, 0, cBw, true);
+                        issue_part(c, acc1, T_WM + 32, sE, cB0 >> 3, cBm, false);        // M1(b) = W_m [agg ; e]
+                        issue_part(c, acc1, T_WM, sT, 0, cBm, true);
                         mma_commit(c.bar_g2);                                            //   -> B2
                     }
                 }
@@ -622,7 +634,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                 if (nmine > 1) {
                     wait_sig(0);                                                         // S4: m(b) in H^T[b]
                     if (elect_one()) {
-                        issue_part(c, T_ACC0 + cB0, T_WU + 32, sH, cB0 >> 3, cBw, true); // M2m(b)
+                        issue_part(c, T_ACC0 + cB0, T_WU + 32, sH, cB0 >> 3, cBm, true); // M2m(b)
                         mma_commit(c.bar_grp);                                           //   -> B1
                     }
                     __syncwarp();
