@@ -293,7 +293,13 @@ constexpr int TMA_WARPS = 4;
 // stream with its own ring, so the scalar bookkeeping of two episodes -- done by lanes 0 and 16 -- issues ONCE.
 // TPE lanes per episode stream (16 or 8): 32 / TPE streams per warp.  The ring lives in dynamic shared memory, one stage =
 // [spins NP | h 2NP | last_flip 2NP | J row NP | scalar block 96] bytes.
-template <int TPE, int STAGES>
+// FAST: the rollout configuration proper -- couplings in {-1,0,1} and T + 1 <= TMA_TSF_MAX -- with a vertex loop stripped to
+// what it has to do (end of round 2: the general loop spent ~35 instructions per vertex, a third of them on `is this the
+// flipped vertex?`, 64-bit address arithmetic for the per-graph gain table and generic loads of the time-since-flip table):
+// the flip is applied to the packed words of the one chunk that holds it BEFORE the loop, row 1 is gain / mlr by reciprocal
+// and two FMAs (small_div: bit-identical to the table, no memory access), the time-since-flip table is read with
+// shared-memory loads, every field is extracted with one PRMT.
+template <int TPE, int STAGES, bool FAST>
 __global__ void __launch_bounds__(TMA_WARPS * 32, 4)
 env_step_ring_kernel(const eco_graphs_t g, const eco_env_t env, const int32_t* __restrict__ actions,
                     double* __restrict__ reward_out, uint8_t* __restrict__ done_out, int32_t* __restrict__ hist_a,
@@ -410,7 +416,60 @@ env_step_ring_kernel(const eco_graphs_t g, const eco_env_t env, const int32_t* _
         if (l16 == 0 && active && env.use_basin) tv = *reinterpret_cast<const ulonglong2*>(tab + 2 * slot);
 
         int nimp = 0;
-        if (active) {
+        const SmallDiv gd = small_div_setup(mlr, FAST);   // (not ok: a graph without edges, mlr = 0 -- the general loop divides in fp64)
+        if (FAST && active && gd.ok) {
+            const int two_sa = 2 * s_a_new, ca = a >> 3, ka = a & 7;
+            const float* tsf_now = s_tsf + step_new;       // time-since-flip of vertex k: tsf_now[-last_flip[k]]
+#pragma unroll
+            for (int cc = 0; cc < 32 / TPE; ++cc) {
+                const int ch = l16 + TPE * cc;
+                if (ch >= NCH) continue;
+                uint2 sw = *reinterpret_cast<const uint2*>(S_spins + ch * 8);
+                const uint2 jw = *reinterpret_cast<const uint2*>(S_jrow + ch * 8);
+                const uint4 hw = *reinterpret_cast<const uint4*>(S_h + ch * 8);
+                uint4 lw = *reinterpret_cast<const uint4*>(S_lf + ch * 8);
+                if (ch == ca) {                            // the flipped vertex: new spin (a +-1 byte negated), last-flip step
+                    const uint32_t m8 = 0xFEu << (8 * (ka & 3));
+                    if (ka < 4) sw.x ^= m8; else sw.y ^= m8;
+                    const uint32_t sh = 16 * (ka & 1), keep = ~(0xFFFFu << sh), val = ((uint32_t)step_new & 0xFFFFu) << sh;
+                    if ((ka >> 1) == 0) lw.x = (lw.x & keep) | val;
+                    else if ((ka >> 1) == 1) lw.y = (lw.y & keep) | val;
+                    else if ((ka >> 1) == 2) lw.z = (lw.z & keep) | val;
+                    else lw.w = (lw.w & keep) | val;
+                }
+                const uint32_t sws[2] = {sw.x, sw.y}, jws[2] = {jw.x, jw.y};
+                const uint32_t hws[4] = {hw.x, hw.y, hw.z, hw.w}, lws[4] = {lw.x, lw.y, lw.z, lw.w};
+                float* x0 = env.xn + (size_t)b * 3 * NP + ch * 8;
+                uint32_t hn[4];
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    float f0[4], f1[4], f2[4];
+                    int hv[4];
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const int k = half * 4 + kk;
+                        const int si = sx8(sws[half], kk);
+                        const int hi = sx16(hws[k >> 1], k & 1) + sx8(jws[half], kk) * two_sa;
+                        hv[kk] = hi;
+                        const int gain = si * hi;
+                        nimp += gain > 0;
+                        f0[kk] = (float)si;
+                        f1[kk] = small_div((float)gain, gd);
+                        f2[kk] = tsf_now[-zx16(lws[k >> 1], k & 1)];
+                    }
+                    hn[2 * half] = __byte_perm((uint32_t)hv[0], (uint32_t)hv[1], 0x5410);
+                    hn[2 * half + 1] = __byte_perm((uint32_t)hv[2], (uint32_t)hv[3], 0x5410);
+                    *reinterpret_cast<float4*>(x0 + 4 * half) = make_float4(f0[0], f0[1], f0[2], f0[3]);
+                    *reinterpret_cast<float4*>(x0 + NP + 4 * half) = make_float4(f1[0], f1[1], f1[2], f1[3]);
+                    *reinterpret_cast<float4*>(x0 + 2 * NP + 4 * half) = make_float4(f2[0], f2[1], f2[2], f2[3]);
+                }
+                *reinterpret_cast<uint4*>(env.hfield + (size_t)b * NP + ch * 8) = make_uint4(hn[0], hn[1], hn[2], hn[3]);
+                if (ch == ca) {
+                    *reinterpret_cast<uint2*>(env.spins + (size_t)b * NP + ch * 8) = sw;
+                    *reinterpret_cast<uint4*>(env.last_flip + (size_t)b * NP + ch * 8) = lw;
+                }
+            }
+        } else if (active) {
 #pragma unroll
             for (int cc = 0; cc < 32 / TPE; ++cc) {       // NP <= 256: at most 32 chunks
                 const int ch = l16 + TPE * cc;            // this lane's 8-vertex chunk
@@ -490,7 +549,8 @@ env_step_ring_kernel(const eco_graphs_t g, const eco_env_t env, const int32_t* _
             *reinterpret_cast<ulonglong2*>(&ep->key[0]) = make_ulonglong2(k0, k1);
             *reinterpret_cast<double2*>(&ep->total_reward) = make_double2(__dadd_rn(total_reward, rew), rew);
             float4 xg;                                                      // rows 3..6 (spinsystem.py:509-527)
-            xg.x = (float)__ddiv_rn(fabs(__dsub_rn(score, nbs)), mlr);
+            const double gap = fabs(__dsub_rn(score, nbs));                 // integer-valued for integer couplings
+            xg.x = (gd.ok && gap <= 65536.0) ? small_div((float)gap, gd) : (float)__ddiv_rn(gap, mlr);
             xg.y = (float)dist;
             xg.z = __ldg(env.frac_tab + nimp);
             xg.w = __ldg(env.imm_tab + step_new);
@@ -657,11 +717,16 @@ int launch_env_step(const eco_graphs_t* g, eco_env_t* env, int policy, const int
                 constexpr int TPE = 16, STAGES = 3, NSTREAMS = TMA_WARPS * (32 / TPE);
                 const size_t ring_bytes = (size_t)NSTREAMS * STAGES * (6 * NP_ + sizeof(eco_episode_t));
                 static unsigned long long attr = 0;
-                if (first_use_on_device(&attr))
-                    ECO_CUDA(cudaFuncSetAttribute(env_step_ring_kernel<TPE, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+                if (first_use_on_device(&attr)) {
+                    ECO_CUDA((cudaFuncSetAttribute(env_step_ring_kernel<TPE, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)));
+                    ECO_CUDA((cudaFuncSetAttribute(env_step_ring_kernel<TPE, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)));
+                }
                 long long blocks = (B_ + NSTREAMS - 1) / NSTREAMS;
                 if (blocks > (long long)n_sm * 4) blocks = (long long)n_sm * 4;
-                env_step_ring_kernel<TPE, STAGES><<<(unsigned)blocks, TMA_WARPS * 32, ring_bytes, st>>>(*g, *env, actions, reward, done, ha, hr, hs);
+                // the stripped vertex loop: +-1 couplings (|gain| <= 255, |mlr| <= 255: small_div is exact), table in shared memory
+                const bool fast = (g->reserved & 1) && env->T + 1 <= TMA_TSF_MAX;
+                if (fast) env_step_ring_kernel<TPE, STAGES, true><<<(unsigned)blocks, TMA_WARPS * 32, ring_bytes, st>>>(*g, *env, actions, reward, done, ha, hr, hs);
+                else env_step_ring_kernel<TPE, STAGES, false><<<(unsigned)blocks, TMA_WARPS * 32, ring_bytes, st>>>(*g, *env, actions, reward, done, ha, hr, hs);
             } else ECO_SW(32);
         }
         else if (NP_ <= 1024) env_step_kernel<128, true><<<(unsigned)B_, 128, 0, st>>>(*g, *env, policy, actions, reward, done, ha, hr, hs);

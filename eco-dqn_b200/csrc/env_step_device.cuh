@@ -24,6 +24,39 @@ __device__ __forceinline__ float feat_gain(int gain, double mlr) {
 // rounding is innocuous for a division when 53 >= 2*24+2 -- but it costs more issue slots than the table lookup: measured
 // 448 us vs 330 us per launch in env_step_ring_kernel.)
 
+// a / m for small integers by one multiplication with the correctly rounded reciprocal y = RN(1 / m) and two FMAs
+// (Markstein's correction step):  q0 = RN(a y),  r = a - q0 m (exact in one FMA),  q = RN(q0 + r y)  ==  RN(a / m)  ==
+// (float)((double)a / (double)m).  Checked exhaustively against the fp64-then-fp32 expression for every |m| <= 2048,
+// |a| <= 70000, signed zeros included (tests/test_capi_cpu.py::test_small_int_division_identity restates the check in C).
+struct SmallDiv {
+    float m, y;      // divisor and its correctly rounded reciprocal
+    bool ok;         // integer divisor, non-zero, in the checked range (otherwise the caller divides in fp64)
+};
+__device__ __forceinline__ SmallDiv small_div_setup(double mlr, bool integer_couplings) {
+    SmallDiv d;
+    d.m = (float)mlr;
+    d.ok = integer_couplings && mlr != 0.0 && fabs(mlr) <= 2048.0;
+    d.y = __frcp_rn(d.ok ? d.m : 1.f);
+    return d;
+}
+__device__ __forceinline__ float small_div(float a, const SmallDiv& d) {     // |a| <= 70000, integer-valued
+    const float q0 = __fmul_rn(a, d.y);
+    const float r = __fmaf_rn(-q0, d.m, a);
+    return __fmaf_rn(r, d.y, q0);
+}
+// byte / half-word extraction in one PRMT each (selector bit 3 replicates the sign of the selected byte; __byte_perm ignores
+// that bit, hence the PTX form)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+__device__ __forceinline__ int sx8(uint32_t w, int k) { return (int)prmt(w, 0, k | ((8 | k) << 4) | ((8 | k) << 8) | ((8 | k) << 12)); }
+__device__ __forceinline__ int sx16(uint32_t w, int hh) {
+    return (int)prmt(w, 0, (2 * hh) | ((2 * hh + 1) << 4) | ((8 | (2 * hh + 1)) << 8) | ((8 | (2 * hh + 1)) << 12));
+}
+__device__ __forceinline__ int zx16(uint32_t w, int hh) { return (int)prmt(w, 0, (2 * hh) | ((2 * hh + 1) << 4) | 0x4400); }
+
 // Latency-optimised form for NP <= 256: everything that does not depend on the action is requested first, the flipped
 // vertex's old spin / field come from a shuffle, the visited-set slot is prefetched, observable row 1 and the normalised
 // score change come from per-graph tables.  All TPE lanes of the group must call it (group shuffles); lanes of an episode
