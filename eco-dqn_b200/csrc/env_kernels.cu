@@ -350,11 +350,19 @@ env_step_ring_kernel(const eco_graphs_t g, const eco_env_t env, const int32_t* _
     constexpr int D = STAGES - 1;
     const long long b0 = sglobal;
     int an[D + 1], gn[D + 1];       // action / graph index of episodes b, b + stotal, ..., b + D * stotal
+    double mlrn[D];                 // max local reward of the graphs of episodes b, ..., b + (D - 1) * stotal: requested one
+                                    // iteration after the graph index arrived, consumed D iterations later (the dependent
+                                    // load graph_idx -> gscal sat on the critical path: 27 % of the kernel's stall samples)
 #pragma unroll
     for (int k = 0; k <= D; ++k) {
         an[k] = 0; gn[k] = 0;
         if (b0 + k * stotal < env.B) { an[k] = actions[b0 + k * stotal]; gn[k] = env.graph_idx[b0 + k * stotal]; }
     }
+#pragma unroll
+    for (int k = 0; k < D; ++k) mlrn[k] = g.gscal[(size_t)gn[k] * 4 + 0];
+    // word of the best-configuration bitmask that holds the flipped vertex, also requested one iteration ahead (FAST)
+    uint32_t old_word_next = 0;
+    if (FAST && b0 < env.B) old_word_next = env.diff_bits[(size_t)b0 * env.NW + (clamp_action(an[0]) >> 5)];
 #pragma unroll
     for (int k = 0; k < D; ++k) issue(b0 + k * stotal, clamp_action(an[k]), gn[k], k, b0 + k * stotal < env.B);
     int st = 0;
@@ -371,6 +379,9 @@ env_step_ring_kernel(const eco_graphs_t g, const eco_env_t env, const int32_t* _
         const long long bD = b + D * stotal, bN = b + (D + 1) * stotal;
         int a_new = 0, gi_new = 0;
         if (bN < env.B) { a_new = actions[bN]; gi_new = env.graph_idx[bN]; }
+        const double mlr_new = g.gscal[(size_t)gn[D] * 4 + 0];
+        const uint32_t old_word_cur = old_word_next;
+        if (FAST && b + stotal < env.B) old_word_next = env.diff_bits[(size_t)(b + stotal) * env.NW + (clamp_action(an[1]) >> 5)];
         issue(bD, clamp_action(an[D]), gn[D], (st + D) % STAGES, bD < env.B);
         const int a_cur = an[0], gi_cur = gn[0];
 
@@ -393,7 +404,7 @@ env_step_ring_kernel(const eco_graphs_t g, const eco_env_t env, const int32_t* _
         const int h_a_old = valid ? S_h[a] : 0;
         const int s_a_new = -s_a_old;
         const int delta = s_a_old * h_a_old;                            // spinsystem.py:393
-        const double mlr = g.gscal[(size_t)gi * 4 + 0];
+        const double mlr = mlrn[0];
         const float* gtab = g.gain_tab + (size_t)gi * tab_stride(NP) + NP;
 
         // lanes 0 / 16: scalar state, dependent lookups requested now, used after the vertex loop
@@ -405,7 +416,8 @@ env_step_ring_kernel(const eco_graphs_t g, const eco_env_t env, const int32_t* _
             key = make_ulonglong2(S_ep->key[0], S_ep->key[1]);
             total_reward = S_ep->total_reward;
             zob = *reinterpret_cast<const ulonglong2*>(s_zob + 2 * a);
-            old_word = env.diff_bits[(size_t)b * env.NW + (a >> 5)];
+            old_word = FAST ? old_word_cur : env.diff_bits[(size_t)b * env.NW + (a >> 5)];
+            // (the normalised score change stays a table gather: an inline fp64 division on this chain costs 160 us per launch)
             if (use_tab) delta_n = __ldg(g.dn_tab + (size_t)gi * tab_stride(NP) + NP + delta);
             else qn = g.gscal[(size_t)gi * 4 + 1];
         }
@@ -574,6 +586,9 @@ env_step_ring_kernel(const eco_graphs_t g, const eco_env_t env, const int32_t* _
 #pragma unroll
         for (int k = 0; k < D; ++k) { an[k] = an[k + 1]; gn[k] = gn[k + 1]; }
         an[D] = a_new; gn[D] = gi_new;
+#pragma unroll
+        for (int k = 0; k + 1 < D; ++k) mlrn[k] = mlrn[k + 1];
+        mlrn[D - 1] = mlr_new;
     }
 }
 
