@@ -107,3 +107,19 @@ def test_no_cuda_means_loud_failure():
         pytest.skip("GPU present")
     with pytest.raises(RuntimeError):
         engine.GraphSet(np.array([[0, 1], [1, 0]])[None])
+
+
+def test_small_int_division_identity(tmp_path):
+    """env_step_device.cuh::small_div (observable row 1 without a table or fp64): gain / mlr by the correctly rounded
+    reciprocal and two FMAs equals the reference's fp64 division followed by the fp32 cast, for every |mlr| <= 2048 and
+    |gain| <= 70000 -- exhaustively, in C (oracle/small_div_check.c)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "small_div_check")
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", os.path.join(root, "oracle", "small_div_check.c"), "-o", exe, "-lm"],
+                   check=True)
+    out = subprocess.run([exe, "2048", "70000"], check=True, capture_output=True, text=True, timeout=600).stdout.split()
+    assert int(out[0]) == 2 * 2048 * (2 * 70000 + 1) and int(out[1]) == 0, out
