@@ -269,6 +269,9 @@ void eco_dp_destroy(eco_dp_t* dp);
  * __test_network_batched (reference experiments/utils.py:169-207) and, with ECO_POLICY_GREEDY, the Greedy
  * baseline (experiments/utils.py:218-227).  actions_scratch_dev [B] int32.  With ECO_ENV_IRREVERSIBLE the network
  * policy takes the argmax over the spins still at -1 (eco_env_masked_argmax) and episodes end when none is left.
+ * For the plain ECO-DQN configuration on the resident tensor-core kernel (N <= 208, at least two episodes per SM) the whole
+ * call is ONE kernel launch (forward + argmax + env step of every step; same results bit for bit); the environment
+ * variable ECO_FUSED_STEP=0 selects two launches per step instead.
  * --------------------------------------------------------------------------------------------------------- */
 int eco_rollout(const eco_graphs_t* g, eco_env_t* env, const eco_mpnn_t* w, int32_t n_steps, int32_t policy,
                 float norm_max, int32_t* actions_scratch_dev, void* mpnn_scratch_dev, int32_t impl,
