@@ -26,14 +26,16 @@
 //   edge stage    ReLU(W_e [a_ij ; x_j]) = ReLU(a_ij w0 + P_j): two dense N x N contractions instead of the
 //                 reference's [B,N,N,63] intermediate; the MMAs of k-step block r are issued as soon as the workers have
 //                 stored S / D of round r, so the contraction runs behind the CUDA-core stage that feeds it.
-//   schedule      19 warps.  Warps 0-15 only ever run epilogues (TMEM -> registers -> split -> smem): two groups of 8
+//   schedule      20 warps.  Warps 0-15 only ever run epilogues (TMEM -> registers -> split -> smem): two groups of 8
 //                 (2 warps per TMEM lane quadrant), each owning up to two column chunks (208 vertices: 64, 48 | 48, 48)
 //                 that it processes interleaved -- the MMAs of one chunk run under the epilogue of the other.  Warp 16
-//                 issues the N x N contractions (edge stage, aggregation per column half) and, in the gaps, reads out
-//                 the PREVIOUS episode (pooling, W_p, Q, argmax).  Warps 17 / 18 issue the linear-layer MMAs of group
-//                 0 / 1: a worker warp that has written its part of a batch's operands fences and arrives on the
-//                 issuer's mbarrier (no CTA or group barrier inside a layer); the issuer commits every batch to one of
-//                 the group's three mbarriers (B1, B2, B3) that the workers wait on before they touch its results.
+//                 issues the N x N contractions (edge stage, aggregation per column half).  Warps 17 / 18 issue the
+//                 linear-layer MMAs of group 0 / 1: a worker warp that has written its part of a batch's operands fences
+//                 and arrives on the issuer's mbarrier (no CTA or group barrier inside a layer); the issuer commits every
+//                 batch to one of the group's three mbarriers (B1, B2, B3) that the workers wait on before they touch
+//                 its results.  Warp 19 works through the tail of the PREVIOUS episode (pooling, W_p, Q, argmax and, in a
+//                 rollout, SpinSystemBase.step for that episode) while the others are on the next one.
+//   rollout       FUSED: one launch per rollout -- every CTA takes its own episodes through all steps (see FusedEnv).
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
