@@ -1,6 +1,8 @@
+"""Quick check of the resident tcgen05 kernel against the CUDA-core kernel at several graph sizes (worst |dq| in units of the
+parity tolerance); used while changing the MMA shapes (instruction N trimmed to 8 ceil(N/8))."""
 import os, sys
 import numpy as np, torch
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 import eco_dqn_b200.engine as engine
 from eco_dqn_b200 import _lib
