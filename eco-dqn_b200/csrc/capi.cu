@@ -236,6 +236,33 @@ int eco_graphs_update(eco_graphs_t* g, int32_t first, int32_t count, const int8_
     return prepare(g, st, first, count);
 }
 
+int eco_graphs_load_edges_dev(eco_graphs_t* g, int32_t first, int32_t count, const int64_t* offsets_dev, const int32_t* rows_dev,
+                              const int32_t* cols_dev, const int8_t* weights_dev, int64_t n_entries, int32_t symmetric,
+                              void* stream) {
+    ECO_CHECK_ARG(g && g->J && offsets_dev, ECO_ERR_INVALID, "eco_graphs_load_edges_dev: null argument");
+    ECO_CHECK_ARG(first >= 0 && count >= 1 && first + count <= g->G, ECO_ERR_INVALID,
+                  "eco_graphs_load_edges_dev: slots [%d, %d) outside the set of %d graphs", first, first + count, g->G);
+    ECO_CHECK_ARG(n_entries >= 0 && (n_entries == 0 || (rows_dev && cols_dev && weights_dev)), ECO_ERR_INVALID,
+                  "eco_graphs_load_edges_dev: %lld entries without edge arrays", (long long)n_entries);
+    cudaStream_t st = (cudaStream_t)stream;
+    ECO_CUDA(cudaMemsetAsync(g->J + (size_t)first * g->NP * g->NP, 0, (size_t)count * g->NP * g->NP, st));
+    static int* err_words[64] = {nullptr};               // one device word per GPU of the process, allocated on first use
+    int dev = 0;
+    ECO_CUDA(cudaGetDevice(&dev));
+    ECO_CHECK_ARG(dev >= 0 && dev < 64, ECO_ERR_UNSUPPORTED, "eco_graphs_load_edges_dev: device ordinal %d", dev);
+    if (!err_words[dev]) ECO_CUDA(cudaMalloc(&err_words[dev], sizeof(int)));
+    int* err_dev = err_words[dev];
+    ECO_CUDA(cudaMemsetAsync(err_dev, 0, sizeof(int), st));
+    int rc = launch_graph_scatter_edges(g, first, count, offsets_dev, rows_dev, cols_dev, weights_dev, n_entries, symmetric,
+                                        err_dev, st);
+    if (rc != ECO_OK) return rc;
+    int err = 0;
+    ECO_CUDA(cudaMemcpyAsync(&err, err_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ECO_CUDA(cudaStreamSynchronize(st));
+    ECO_CHECK_ARG(err == 0, ECO_ERR_INVALID, "eco_graphs_load_edges_dev: an entry names a vertex outside [0, %d)", g->N);
+    return prepare(g, st, first, count);
+}
+
 // ------------------------------------------------------------------------------------------------ env
 size_t eco_env_workspace_bytes(int32_t B, int32_t N, int32_t T) {
     if (B < 1 || !shape_ok(N) || T < 1 || T > 65535) return 0;

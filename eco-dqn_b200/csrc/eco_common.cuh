@@ -105,6 +105,9 @@ __device__ __forceinline__ int group_max(int v) {
 }
 
 // ---- internal launchers (one translation unit each) -------------------------------------------------------
+int launch_graph_scatter_edges(const eco_graphs_t* g, int first, int count, const int64_t* offsets, const int32_t* rows,
+                               const int32_t* cols, const int8_t* wts, long long n_entries, int symmetric, int* err_dev,
+                               cudaStream_t st);
 int launch_graph_prepare(const eco_graphs_t* g, int first, int count, cudaStream_t st);
 int launch_graph_pad(const eco_graphs_t* g, const int8_t* dense_dev, int first, int count, cudaStream_t st);
 int launch_env_reset(const eco_graphs_t* g, eco_env_t* env, const int32_t* gidx, const int8_t* spins, cudaStream_t st);

@@ -143,6 +143,38 @@ __global__ void __launch_bounds__(256) graph_prepare_kernel(eco_graphs_t g, int 
     }
 }
 
+// Edge lists -> the padded dense int8 layout (eco_graphs_load_edges_dev).  One thread per entry; the graph of an entry is
+// found by bisection over the (count + 1) offsets.  Out-of-range vertices raise *err instead of writing.
+__global__ void graph_scatter_edges_kernel(int8_t* __restrict__ J, const int N, const int NP, const int count,
+                                           const int64_t* __restrict__ offsets, const int32_t* __restrict__ rows,
+                                           const int32_t* __restrict__ cols, const int8_t* __restrict__ wts,
+                                           const long long n_entries, const int symmetric, int* __restrict__ err) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_entries; e += (long long)gridDim.x * blockDim.x) {
+        int lo = 0, hi = count;                       // largest k with offsets[k] <= e
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (offsets[mid] <= e) lo = mid; else hi = mid;
+        }
+        const int i = rows[e], j = cols[e];
+        if (i < 0 || i >= N || j < 0 || j >= N) { atomicExch(err, 1); continue; }
+        int8_t* Jk = J + (size_t)lo * NP * NP;
+        Jk[(size_t)i * NP + j] = wts[e];
+        if (symmetric) Jk[(size_t)j * NP + i] = wts[e];
+    }
+}
+
+int launch_graph_scatter_edges(const eco_graphs_t* g, int first, int count, const int64_t* offsets, const int32_t* rows,
+                               const int32_t* cols, const int8_t* wts, long long n_entries, int symmetric, int* err_dev,
+                               cudaStream_t st) {
+    if (n_entries == 0) return ECO_OK;
+    const long long want = (n_entries + 255) / 256;
+    const int blocks = (int)(want < 148 * 16 ? want : 148 * 16);
+    graph_scatter_edges_kernel<<<blocks, 256, 0, st>>>(g->J + (size_t)first * g->NP * g->NP, g->N, g->NP, count, offsets, rows,
+                                                       cols, wts, n_entries, symmetric, err_dev);
+    ECO_LAUNCH_CHECK();
+    return ECO_OK;
+}
+
 int launch_graph_pad(const eco_graphs_t* g, const int8_t* dense_dev, int first, int count, cudaStream_t st) {
     const size_t total = (size_t)count * g->NP * (g->NP / 16);
     const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);

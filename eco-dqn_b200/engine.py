@@ -108,24 +108,33 @@ def graphs_to_int8(graphs):
 
 
 class GraphSet:
-    def __init__(self, graphs, device=None, validate=True, min_cut=False):
+    def __init__(self, graphs, device=None, validate=True, min_cut=False, _edges=None):
         """min_cut=True: the scorer constants (and every mask the env kernels derive from the graphs) are those of
-        OptimisationTarget.MIN_CUT (reference score_solver.py:423-505) instead of CUT."""
+        OptimisationTarget.MIN_CUT (reference score_solver.py:423-505) instead of CUT.
+        (`_edges`: see GraphSet.from_edges -- the graphs arrive as edge lists, no dense matrix on the host.)"""
         self.device = _require_cuda(device)
         self.min_cut = bool(min_cut)
-        J = graphs_to_int8(graphs)
-        self.G, self.N = int(J.shape[0]), int(J.shape[1])
+        if _edges is None:
+            J = graphs_to_int8(graphs)
+            self.G, self.N = int(J.shape[0]), int(J.shape[1])
+        else:
+            self.G, self.N = len(_edges["offsets"]) - 1, int(_edges["n"])
         if self.N > _lib.MAX_SPINS:
             raise ValueError("N=%d exceeds ECO_MAX_SPINS=%d" % (self.N, _lib.MAX_SPINS))
         L = lib()
         with torch.cuda.device(self.device):
             nbytes = L.eco_graphs_workspace_bytes(self.G, self.N)
-            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._ws = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)    # (padding between the arrays stays defined)
             self.c = Graphs()
             check(L.eco_graphs_bind(C.byref(self.c), _ptr(self._ws), self.G, self.N))
             self.c.reserved = _lib.GRAPHS_MIN_CUT if self.min_cut else 0     # read by the prepare kernel
-            Jd = torch.from_numpy(J).to(self.device, non_blocking=False)
-            check(L.eco_graphs_load_dev(C.byref(self.c), _ptr(Jd), _stream()))
+            if _edges is None:
+                Jd = torch.from_numpy(J).to(self.device, non_blocking=False)
+                check(L.eco_graphs_load_dev(C.byref(self.c), _ptr(Jd), _stream()))
+            else:
+                dev = {k: torch.from_numpy(np.ascontiguousarray(_edges[k])).to(self.device) for k in ("offsets", "rows", "cols", "w")}
+                check(L.eco_graphs_load_edges_dev(C.byref(self.c), 0, self.G, _ptr(dev["offsets"]), _ptr(dev["rows"]), _ptr(dev["cols"]),
+                                                  _ptr(dev["w"]), int(_edges["offsets"][-1]), int(_edges["symmetric"]), _stream()))
             self.NP = int(self.c.NP)
             self.J = _view(self._ws, self.c.J, self.G * self.NP * self.NP, torch.int8, (self.G, self.NP, self.NP))
             self.gscal = _view(self._ws, self.c.gscal, self.G * 4, torch.float64, (self.G, 4))
@@ -144,6 +153,38 @@ class GraphSet:
                 raise ValueError("graph %d has no non-zero weighted degree" % int(np.nonzero(stat[:, 3] & 2)[0][0]))
             if stat[:, 2].max() > 32767:
                 raise NotImplementedError("weighted degree exceeds the int16 local-field range")
+
+    @classmethod
+    def from_edges(cls, n_vertices, graphs, device=None, validate=True, min_cut=False):
+        """Sparse ingest (C ABI `eco_graphs_load_edges_dev`): `graphs` is a list whose entries are either
+        `(rows, cols, weights)` -- every undirected edge once, as `read_mc_instance` returns them (GSet `.mc` files, reference
+        experiments/utils.py:395-406) -- or scipy sparse matrices (the csr pickles of :420-432, every stored entry).  Only
+        the edge arrays cross PCIe (5 bytes per entry instead of N*N); the dense int8 couplings are built on the device.
+        Weights must be integers in [-127, 127]."""
+        import scipy.sparse as sps
+        offsets, rows, cols, wts, symmetric = [0], [], [], [], None
+        for gph in graphs:
+            if sps.issparse(gph):
+                coo = gph.tocoo()
+                if coo.shape != (n_vertices, n_vertices):
+                    raise ValueError("sparse matrix of shape %s in a set of %d-vertex graphs" % (coo.shape, n_vertices))
+                r, c_, w_, sym = coo.row, coo.col, coo.data, False
+            else:
+                r, c_, w_ = gph
+                sym = True
+            if symmetric is None:
+                symmetric = sym
+            elif symmetric != sym:
+                raise ValueError("edge lists and sparse matrices cannot be mixed in one call")
+            w_ = np.asarray(w_)
+            if w_.size and (np.abs(w_) > 127).any() or (w_ != np.round(w_)).any():
+                raise NotImplementedError("couplings must be integers in [-127, 127]")
+            rows.append(np.asarray(r, dtype=np.int32)); cols.append(np.asarray(c_, dtype=np.int32)); wts.append(w_.astype(np.int8))
+            offsets.append(offsets[-1] + len(w_))
+        cat = lambda xs, dt: np.concatenate(xs).astype(dt) if offsets[-1] else np.zeros(1, dtype=dt)
+        edges = {"n": n_vertices, "offsets": np.asarray(offsets, dtype=np.int64), "rows": cat(rows, np.int32),
+                 "cols": cat(cols, np.int32), "w": cat(wts, np.int8), "symmetric": bool(symmetric)}
+        return cls(None, device=device, validate=validate, min_cut=min_cut, _edges=edges)
 
     @property
     def mlr(self):

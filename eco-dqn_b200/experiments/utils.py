@@ -212,11 +212,26 @@ def load_graph_set(graph_save_loc):
 
 
 def load_graph_set_device(graph_save_loc, device=None, min_cut=False):
-    """The same pickle straight into an engine.GraphSet: int8 couplings, one upload, no float64 copies kept (all graphs of
-    the file must share N, as the reference's batched tester assumes per graph anyway)."""
+    """The same pickle straight into an engine.GraphSet (all graphs of the file must share N, as the reference's batched
+    tester assumes per graph anyway).  A file of scipy sparse matrices (the csr pickles) goes through the sparse ingest --
+    only the stored entries cross PCIe, the dense int8 couplings are built on the device; anything else is uploaded as int8."""
     with open(graph_save_loc, 'rb') as f:
-        graphs = [to_dense_adjacency(g) for g in pickle.load(f)]
+        raw = pickle.load(f)
+    if len(raw) and all(sp.sparse.issparse(g) for g in raw):
+        return engine.GraphSet.from_edges(raw[0].shape[0], raw, device=device, min_cut=min_cut)
+    graphs = [to_dense_adjacency(g) for g in raw]
     return engine.GraphSet(engine.graphs_to_int8(np.stack(graphs)), device=device, min_cut=min_cut)
+
+
+def load_mc_instances_device(graph_dir, graph_names, device=None, min_cut=False):
+    """GSet `.mc` instances (all of one size) straight into an engine.GraphSet through the sparse ingest: the edge lists go to
+    the device (5 bytes per edge) and the dense int8 couplings are built there -- no N x N float64 matrix, which is what
+    `load_graph` (reference experiments/utils.py:391-418) builds per instance."""
+    insts = [read_mc_instance(os.path.join(graph_dir, 'instances', name + '.mc')) for name in graph_names]
+    n = insts[0][0]
+    if any(i[0] != n for i in insts):
+        raise ValueError("all instances of one GraphSet must have the same number of vertices")
+    return engine.GraphSet.from_edges(n, [(r, c, w) for _, _, r, c, w in insts], device=device, min_cut=min_cut)
 
 
 def mk_dir(export_dir, quite=False):

@@ -97,6 +97,17 @@ int    eco_graphs_load_dev(eco_graphs_t* g, const int8_t* J_dev, void* stream);
 /* replace the graphs in slots [first, first + count) (J_dev dense [count, N, N]) and refresh their constants: the
  * graph ring of the DQN trainer (a new random graph per episode, reference spinsystem.py:196) */
 int    eco_graphs_update(eco_graphs_t* g, int32_t first, int32_t count, const int8_t* J_dev, void* stream);
+/* Sparse ingest: the graphs of slots [first, first + count) from EDGE LISTS already on the device -- graph k owns entries
+ * offsets_dev[k] .. offsets_dev[k+1]-1 of rows_dev / cols_dev (0-based vertices) / weights_dev -- without a dense N x N copy
+ * crossing PCIe or existing on the host: the slots are zeroed, J[i][j] (and J[j][i] when `symmetric` != 0) are set to the
+ * entry's weight, then the constants are refreshed.  This is how the GSet `.mc` instances and the scipy-CSR pickles of the
+ * reference's loaders (experiments/utils.py:391-432: edge list -> dense float64 -> torch) reach the device: CSR is
+ * rows = repeat(arange(N), diff(indptr)), cols = indices, symmetric = 0.  Duplicate entries: the last writer wins (the
+ * reference's `matrix[i, j] = w` assignment); entries outside [0, N) make the call fail with ECO_ERR_INVALID (checked on
+ * the device, reported after a stream synchronise).  n_entries = offsets[count], passed by the caller. */
+int    eco_graphs_load_edges_dev(eco_graphs_t* g, int32_t first, int32_t count, const int64_t* offsets_dev,
+                                 const int32_t* rows_dev, const int32_t* cols_dev, const int8_t* weights_dev,
+                                 int64_t n_entries, int32_t symmetric, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Batched environment state (struct of arrays), B independent episodes.

@@ -368,3 +368,66 @@ def test_one_launch_rollout_equals_two_launches_per_step(eng, tmp_path, B):
     for k in res["two"]:
         assert np.array_equal(res["two"][k].view(np.uint8), res["fused"][k].view(np.uint8)), k
     assert (res["two"]["ha"][:, :steps] >= 0).all()
+
+
+def _edge_lists(rng, G, n, m):
+    """G random +-1 graphs as (rows, cols, weights) with every undirected edge once, and the dense matrices."""
+    out, dense = [], np.zeros((G, n, n), dtype=np.int8)
+    for g in range(G):
+        iu = np.triu_indices(n, 1)
+        pick = rng.choice(len(iu[0]), size=m, replace=False)
+        r, c = iu[0][pick], iu[1][pick]
+        w = rng.choice(np.array([-1, 1], dtype=np.int8), size=m)
+        dense[g, r, c] = w
+        dense[g, c, r] = w
+        out.append((r, c, w))
+    return out, dense
+
+
+@pytest.mark.parametrize("n,m", [(200, 1500), (800, 4694), (2000, 19990)])
+def test_sparse_ingest_equals_dense_upload(eng, n, m):
+    """eco_graphs_load_edges_dev (GraphSet.from_edges): edge lists -- and scipy CSR matrices -- produce byte for byte the graph
+    set that the dense int8 upload produces (couplings, scorer constants, degrees, lookup tables, operand images), at the
+    resident size and at GSet sizes (800 vertices / 4694 edges = G1-style, 2000 / 19 990 = BASELINE config C4)."""
+    import scipy.sparse as sps
+    rng = np.random.default_rng(n)
+    lists, dense = _edge_lists(rng, 3, n, m)
+    ref = eng.GraphSet(dense)
+    a = eng.GraphSet.from_edges(n, lists)
+    b = eng.GraphSet.from_edges(n, [sps.csr_matrix(dense[g].astype(np.int64)) for g in range(3)])
+    torch.cuda.synchronize()
+    for other in (a, b):
+        assert other.NP == ref.NP and other.pm1_only == ref.pm1_only and other.max_degree == ref.max_degree
+        assert torch.equal(other._ws, ref._ws)
+
+
+def test_sparse_ingest_rejects_bad_vertices_and_feeds_the_rollout(eng, tmp_path):
+    """An entry outside [0, N) fails the call; GSet-format `.mc` files and a csr pickle go through the loaders of
+    experiments/utils.py into graph sets whose rollouts equal those of the densely uploaded graphs."""
+    import pickle
+    import scipy.sparse as sps
+    from eco_dqn_b200.experiments.utils import load_mc_instances_device, load_graph_set_device
+    rng = np.random.default_rng(7)
+    n, m = 60, 300
+    lists, dense = _edge_lists(rng, 2, n, m)
+    bad = [(np.array([0, n]), np.array([1, 2]), np.array([1, 1], dtype=np.int8))]
+    with pytest.raises(ValueError):
+        eng.GraphSet.from_edges(n, bad)
+    os.makedirs(tmp_path / "instances")
+    for g, (r, c, w) in enumerate(lists):
+        with open(tmp_path / "instances" / ("g%d.mc" % g), "w") as f:
+            f.write("%d %d\n" % (n, m))
+            for i, j, v in zip(r, c, w):
+                f.write("%d %d %d\n" % (i + 1, j + 1, v))
+    with open(tmp_path / "set.pkl", "wb") as f:
+        pickle.dump([sps.csr_matrix(dense[g].astype(np.float64)) for g in range(2)], f)
+    ref = eng.GraphSet(dense)
+    for gs in (load_mc_instances_device(str(tmp_path), ["g0", "g1"]), load_graph_set_device(str(tmp_path / "set.pkl"))):
+        assert torch.equal(gs._ws, ref._ws)
+        cuts = []
+        for g_ in (gs, ref):
+            env = eng.BatchedSpinSystem(g_, 2, 2 * n, 1.0 / n)
+            env.reset(spins=np.ones((2, n), dtype=np.int8), graph_idx=np.arange(2, dtype=np.int32))
+            env.rollout(policy="greedy")
+            cuts.append(env.results()[0].cpu().numpy())
+        assert np.array_equal(cuts[0], cuts[1]) and (cuts[0] > 0).all()
