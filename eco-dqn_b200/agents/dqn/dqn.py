@@ -78,6 +78,8 @@ class DQN:
             raise ValueError("dp_mode must be 'peer' (gradient exchange over CUDA IPC peer memory, fused with Adam) or 'nccl'")
         self.dp_mode = dp_mode                # how the ranks' gradients are averaged (world > 1)
         self.cuda_graph = bool(cuda_graph)    # replay the update (TD target .. Adam .. re-pack) as one CUDA graph
+        self.overlap_target = os.environ.get("ECO_DQN_OVERLAP_TARGET", "1") != "0"   # TD target on a second stream (see _update)
+        self._tgt_stream = None
         self._cg = None
         if callable(loss):
             self.loss = loss
@@ -337,18 +339,36 @@ class DQN:
             # the reference feeds the whole minibatch through the network: norm.max() is the batch's max degree
             self._nm_buf.copy_(self._graphs.gstat[graph.long(), 0].max().clamp(min=1).to(torch.float32).reshape(1))
             gc = self._graphs_nm                       # norm_max = 0 -> the kernels read *dmax = _nm_buf
-            if self.double_dqn:
-                _, greedy = self._q_kernel(self.network, t["xn_next"], t["xg_next"], graph, 0.0, want_q=False, graphs_c=gc)
-                q_tgt, _ = self._q_kernel(self.target_network, t["xn_next"], t["xg_next"], graph, 0.0, graphs_c=gc)
-                q_value_target = q_tgt.gather(1, greedy.long().unsqueeze(1))
+
+            def td_target_of():
+                if self.double_dqn:
+                    _, greedy = self._q_kernel(self.network, t["xn_next"], t["xg_next"], graph, 0.0, want_q=False, graphs_c=gc)
+                    q_tgt, _ = self._q_kernel(self.target_network, t["xn_next"], t["xg_next"], graph, 0.0, graphs_c=gc)
+                    q_value_target = q_tgt.gather(1, greedy.long().unsqueeze(1))
+                else:
+                    q_tgt, _ = self._q_kernel(self.target_network, t["xn_next"], t["xg_next"], graph, 0.0, graphs_c=gc)
+                    q_value_target = q_tgt.max(1, True)[0]
+                if self.clip_Q_targets:
+                    q_value_target = q_value_target.clamp(min=0)
+                return t["reward"].unsqueeze(1) + (1 - t["done"].unsqueeze(1)) * self.gamma * q_value_target
+
+            # forward + backward of the online network in the hand-written kernels (eco_mpnn_grad, csrc/mpnn_grad.cu).  Its
+            # forward pass does not need the regression targets: the Double-DQN target (two forwards of the next states +
+            # a handful of small tensor ops) runs on a second stream underneath it and is waited for just before the readout
+            # (eco_mpnn_grad_ev); in the captured update the two branches are parallel paths of the CUDA graph.
+            if self.overlap_target:
+                main = torch.cuda.current_stream()
+                if self._tgt_stream is None:
+                    self._tgt_stream = torch.cuda.Stream(device=self.device)
+                self._tgt_stream.wait_stream(main)
+                with torch.cuda.stream(self._tgt_stream):
+                    td_target = td_target_of().reshape(-1).to(torch.float32).contiguous()
+                    ready = torch.cuda.Event()
+                    ready.record(self._tgt_stream)
+                td_target.record_stream(main)
+                loss = self._grad_kernel(t["xn"], t["xg"], graph, 0.0, t["action"], td_target, graphs_c=gc, ready=ready)
             else:
-                q_tgt, _ = self._q_kernel(self.target_network, t["xn_next"], t["xg_next"], graph, 0.0, graphs_c=gc)
-                q_value_target = q_tgt.max(1, True)[0]
-            if self.clip_Q_targets:
-                q_value_target = q_value_target.clamp(min=0)
-            td_target = t["reward"].unsqueeze(1) + (1 - t["done"].unsqueeze(1)) * self.gamma * q_value_target
-            # forward + backward of the online network in the hand-written kernels (eco_mpnn_grad, csrc/mpnn_grad.cu)
-            loss = self._grad_kernel(t["xn"], t["xg"], graph, 0.0, t["action"], td_target, graphs_c=gc)
+                loss = self._grad_kernel(t["xn"], t["xg"], graph, 0.0, t["action"], td_target_of(), graphs_c=gc)
             if self.world > 1 and not self._fused_dp:
                 self._allreduce_grads()
             if self.max_grad_norm is not None:
@@ -433,7 +453,7 @@ class DQN:
             self._g_loss = self._update(self.replay_buffer.gather(self._g_idx))
         torch.cuda.synchronize(self.device)
 
-    def _grad_kernel(self, xn, xg, graph, norm_max, action, td_target, graphs_c=None):
+    def _grad_kernel(self, xn, xg, graph, norm_max, action, td_target, graphs_c=None, ready=None):
         """loss and d loss / d weights of the regression step (dqn.py:436-447) through eco_mpnn_grad; the gradient
         lands in `p.grad` of every parameter (views of one flat buffer, state_dict order)."""
         B = xn.shape[0]
@@ -446,10 +466,10 @@ class DQN:
         xn, xg, graph = xn.contiguous(), xg.contiguous(), graph.to(torch.int32).contiguous()
         action = action.to(torch.int32).contiguous()
         target = td_target.reshape(-1).to(torch.float32).contiguous()
-        check(lib().eco_mpnn_grad(C.byref(self._graphs.c if graphs_c is None else graphs_c), C.byref(w.c), B, engine._ptr(graph), engine._ptr(xn),
-                                  engine._ptr(xg), float(norm_max), engine._ptr(action), engine._ptr(target),
-                                  self._loss_kind, engine._ptr(loss), engine._ptr(flat), engine._ptr(self._grad_scratch),
-                                  engine._stream()))
+        check(lib().eco_mpnn_grad_ev(C.byref(self._graphs.c if graphs_c is None else graphs_c), C.byref(w.c), B, engine._ptr(graph),
+                                     engine._ptr(xn), engine._ptr(xg), float(norm_max), engine._ptr(action), engine._ptr(target),
+                                     self._loss_kind, engine._ptr(loss), engine._ptr(flat), engine._ptr(self._grad_scratch),
+                                     C.c_void_p(ready.cuda_event if ready is not None else 0), engine._stream()))
         params = dict(self.network.named_parameters())
         off = 0
         for key, shp in zip(engine.STATE_DICT_KEYS, engine.STATE_DICT_SHAPES):

@@ -388,9 +388,9 @@ int eco_mpnn_forward(const eco_graphs_t* g, const eco_mpnn_t* w, int32_t B, cons
 
 size_t eco_mpnn_grad_scratch_bytes(int32_t B, int32_t N) { return (B >= 1 && N >= 1) ? mpnn_grad_scratch_bytes(B, N) : 0; }
 
-int eco_mpnn_grad(const eco_graphs_t* g, const eco_mpnn_t* w, int32_t B, const int32_t* gidx, const float* xn, const float* xg,
-                  float norm_max, const int32_t* actions, const float* targets, int32_t loss_kind, float* loss, float* grad,
-                  void* scratch, void* stream) {
+int eco_mpnn_grad_ev(const eco_graphs_t* g, const eco_mpnn_t* w, int32_t B, const int32_t* gidx, const float* xn, const float* xg,
+                     float norm_max, const int32_t* actions, const float* targets, int32_t loss_kind, float* loss, float* grad,
+                     void* scratch, void* targets_ready_event, void* stream) {
     ECO_CHECK_ARG(g && gidx && xn && xg && actions && targets && loss && grad && scratch, ECO_ERR_INVALID,
                   "eco_mpnn_grad: null argument");
     ECO_CHECK_ARG(B >= 1 && B <= 65535, ECO_ERR_INVALID, "eco_mpnn_grad: B must be in 1..65535 (minibatch), got %d", B);
@@ -401,7 +401,13 @@ int eco_mpnn_grad(const eco_graphs_t* g, const eco_mpnn_t* w, int32_t B, const i
     int rc = check_weights(w, "eco_mpnn_grad");
     if (rc) return rc;
     return launch_mpnn_grad(g, w, B, gidx, xn, xg, norm_max, actions, targets, loss_kind == ECO_LOSS_HUBER, loss, grad, scratch,
-                            (cudaStream_t)stream);
+                            (cudaEvent_t)targets_ready_event, (cudaStream_t)stream);
+}
+
+int eco_mpnn_grad(const eco_graphs_t* g, const eco_mpnn_t* w, int32_t B, const int32_t* gidx, const float* xn, const float* xg,
+                  float norm_max, const int32_t* actions, const float* targets, int32_t loss_kind, float* loss, float* grad,
+                  void* scratch, void* stream) {
+    return eco_mpnn_grad_ev(g, w, B, gidx, xn, xg, norm_max, actions, targets, loss_kind, loss, grad, scratch, nullptr, stream);
 }
 
 int eco_mpnn_adam(const eco_mpnn_t* w, const float* grad, float* exp_avg, float* exp_avg_sq, int32_t step, float lr, float beta1,

@@ -132,7 +132,7 @@ bool mpnn_tc_supported(const eco_graphs_t* g);
 size_t mpnn_grad_scratch_bytes(int B, int N);
 int launch_mpnn_grad(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int32_t* gidx, const float* xn, const float* xg,
                      float norm_max, const int32_t* actions, const float* targets, int huber, float* loss, float* grad,
-                     void* scratch, cudaStream_t st);
+                     void* scratch, cudaEvent_t targets_ready, cudaStream_t st);
 int launch_mpnn_adam(const eco_mpnn_t* w, const float* grad, float* m, float* v, int step, float lr, float beta1, float beta2,
                      float eps, float weight_decay, cudaStream_t st);
 bool mpnn_tcl_supported(const eco_graphs_t* g);

@@ -408,7 +408,7 @@ size_t mpnn_grad_scratch_bytes(int B, int N) {
 
 int launch_mpnn_grad(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int32_t* gidx, const float* xn, const float* xg,
                      float norm_max, const int32_t* actions, const float* targets, int huber, float* loss, float* grad,
-                     void* scratch, cudaStream_t st) {
+                     void* scratch, cudaEvent_t targets_ready, cudaStream_t st) {
     const int NP = g->NP, V = B * NP;
     const size_t pl = (size_t)V * F;
     float* base = (float*)scratch;
@@ -445,6 +445,8 @@ int launch_mpnn_grad(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const in
         ECO_LAUNCH_CHECK();
     }
     // ---- loss and backward ----
+    // (the regression targets may still be on their way on another stream: the forward above does not need them)
+    if (targets_ready) ECO_CUDA(cudaStreamWaitEvent(st, targets_ready, 0));
     k_readout<<<S, 256, 0, st>>>(*g, *w, B, P(P_H3), actions, targets, huber, P(P_DHA), part);
     ECO_LAUNCH_CHECK();
     float* dcur = P(P_DHA);

@@ -241,6 +241,14 @@ int    eco_mpnn_grad(const eco_graphs_t* g, const eco_mpnn_t* w, int32_t B, cons
                      const float* xn_dev, const float* xg_dev, float norm_max, const int32_t* actions_dev,
                      const float* targets_dev, int32_t loss_kind, float* loss_dev, float* grad_dev,
                      void* scratch_dev, void* stream);
+/* The same with the targets still being computed on ANOTHER stream: `targets_ready_event` (a cudaEvent_t recorded on that
+ * stream after the last write of targets_dev, or NULL) is waited for on `stream` just before the readout -- the forward
+ * pass with its saved activations (two thirds of the call) does not depend on the targets, so the Double-DQN target
+ * (dqn.py:414-432: two forwards of the next states) overlaps it.  Capturable into a CUDA graph (becomes a graph edge). */
+int    eco_mpnn_grad_ev(const eco_graphs_t* g, const eco_mpnn_t* w, int32_t B, const int32_t* graph_idx_dev,
+                        const float* xn_dev, const float* xg_dev, float norm_max, const int32_t* actions_dev,
+                        const float* targets_dev, int32_t loss_kind, float* loss_dev, float* grad_dev, void* scratch_dev,
+                        void* targets_ready_event, void* stream);
 
 /* The optimizer step that follows (reference src/agents/dqn/dqn.py:212 `optim.Adam(...)`, :449 `self.optimizer.step()`):
  * torch.optim.Adam semantics (weight_decay is added to the gradient, bias-corrected moments, no amsgrad) applied IN
