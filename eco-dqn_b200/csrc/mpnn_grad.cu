@@ -406,6 +406,23 @@ size_t mpnn_grad_scratch_bytes(int B, int N) {
     return align256(sizeof(float) * ((size_t)N_PLANES * B * NP * F + (size_t)NSPLIT_MAX * PART_STRIDE));
 }
 
+// second stream + events of launch_mpnn_grad, one set per device of the process (created on first use, never destroyed)
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+static SideStream& side_stream() {
+    static SideStream per_dev[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    SideStream& s = per_dev[dev & 63];
+    if (!s.stream) {
+        cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+        for (auto& e : s.ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    }
+    return s;
+}
+
 int launch_mpnn_grad(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const int32_t* gidx, const float* xn, const float* xg,
                      float norm_max, const int32_t* actions, const float* targets, int huber, float* loss, float* grad,
                      void* scratch, cudaEvent_t targets_ready, cudaStream_t st) {
@@ -449,19 +466,30 @@ int launch_mpnn_grad(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const in
     if (targets_ready) ECO_CUDA(cudaStreamWaitEvent(st, targets_ready, 0));
     k_readout<<<S, 256, 0, st>>>(*g, *w, B, P(P_H3), actions, targets, huber, P(P_DHA), part);
     ECO_LAUNCH_CHECK();
+    // The weight-gradient kernels only READ the activation gradients; nothing downstream of them but the final reduction needs
+    // their sums.  They run on a second stream beside the chain that carries the gradient back through the layers; what the
+    // chain has to respect is that a buffer a weight gradient still reads (dcur, DM of the layer above) is not overwritten
+    // yet: one event per layer.  (Inside a captured update these are parallel branches of the graph.)
+    SideStream& ss = side_stream();
+    cudaStream_t sw = ss.stream;
+    auto after_main = [&](int k) { ECO_CUDA(cudaEventRecord(ss.ev[k], st)); ECO_CUDA(cudaStreamWaitEvent(sw, ss.ev[k], 0)); return ECO_OK; };
     float* dcur = P(P_DHA);
     float* dnext = P(P_DHB);
     for (int l = 2; l >= 0; --l) {
         float* gl = part + G_LAYER0 + l * G_LAYER_STRIDE;
         const float* Hout = P(P_H1 + l);
-        k_wgrad<128><<<S, 256, wsm128, st>>>(dcur, Hout, P(P_H0 + l), P(P_M0 + l), V, gl + G_WUPD_OFF);
+        if (int rc = after_main(0)) return rc;                                 // dcur of this layer is complete
+        k_wgrad<128><<<S, 256, wsm128, sw>>>(dcur, Hout, P(P_H0 + l), P(P_M0 + l), V, gl + G_WUPD_OFF);
         ECO_LAUNCH_CHECK();
+        if (l < 2) ECO_CUDA(cudaStreamWaitEvent(st, ss.ev[2], 0));             // the layer above no longer reads dnext / DM
         k_gemm<true, 64><<<vt, 256, gsm64, st>>>(dcur, nullptr, Hout, V, w->w_upd[l], 128, 0, dnext, 0, 0);
         ECO_LAUNCH_CHECK();
         k_gemm<true, 64><<<vt, 256, gsm64, st>>>(dcur, nullptr, Hout, V, w->w_upd[l], 128, 64, P(P_DM), 0, 0);
         ECO_LAUNCH_CHECK();
-        k_wgrad<128><<<S, 256, wsm128, st>>>(P(P_DM), P(P_M0 + l), P(P_AGG0 + l), P(P_E), V, gl);
+        if (int rc = after_main(1)) return rc;                                 // DM is complete
+        k_wgrad<128><<<S, 256, wsm128, sw>>>(P(P_DM), P(P_M0 + l), P(P_AGG0 + l), P(P_E), V, gl);
         ECO_LAUNCH_CHECK();
+        ECO_CUDA(cudaEventRecord(ss.ev[2], sw));                               // both weight gradients of this layer have read their inputs
         k_gemm<true, 64><<<vt, 256, gsm64, st>>>(P(P_DM), nullptr, P(P_M0 + l), V, w->w_msg[l], 128, 0, P(P_DAGG), 0, 0);
         ECO_LAUNCH_CHECK();
         k_gemm<true, 64><<<vt, 256, gsm64, st>>>(P(P_DM), nullptr, P(P_M0 + l), V, w->w_msg[l], 128, 64, P(P_DE), 0, l < 2 ? 1 : 0);
@@ -470,14 +498,17 @@ int launch_mpnn_grad(const eco_graphs_t* g, const eco_mpnn_t* w, int B, const in
         ECO_LAUNCH_CHECK();
         float* t = dcur; dcur = dnext; dnext = t;
     }
-    k_wgrad<64><<<S, 256, wsm64, st>>>(P(P_DE), P(P_E), P(P_G), nullptr, V, part + G_WEF);
+    if (int rc = after_main(0)) return rc;                                     // DE is complete
+    k_wgrad<64><<<S, 256, wsm64, sw>>>(P(P_DE), P(P_E), P(P_G), nullptr, V, part + G_WEF);
     ECO_LAUNCH_CHECK();
+    ECO_CUDA(cudaEventRecord(ss.ev[3], sw));
     k_gemm<true, 64><<<vt, 256, gsm64, st>>>(P(P_DE), nullptr, P(P_E), V, w->w_edge_feat, 64, 0, P(P_DG), 0, 0);
     ECO_LAUNCH_CHECK();
     k_adj<EDGE_BWD><<<agrid, ADJ_ROWS * F, asm_bytes, st>>>(*g, gidx, P(P_DG), nullptr, P(P_DRP), P(P_DRM), norm_max);
     ECO_LAUNCH_CHECK();
     k_init_bwd<<<S, 256, 0, st>>>(*g, *w, B, xn, xg, P(P_H0), P(P_P), dcur, P(P_DRP), P(P_DRM), part);
     ECO_LAUNCH_CHECK();
+    ECO_CUDA(cudaStreamWaitEvent(st, ss.ev[3], 0));                            // every weight-gradient partial sum is written
     k_reduce<<<(N_PARAMS + 1 + 255) / 256, 256, 0, st>>>(part, S, grad, loss);
     ECO_LAUNCH_CHECK();
     return ECO_OK;
