@@ -285,3 +285,39 @@ def test_peer_adam_with_one_rank_equals_device_adam():
             assert torch.equal(a, b)
     assert opts[1].steps == 4 and int(opts[1].err_dev.item()) == 0
     opts[1].close()
+
+
+def test_captured_acting_step_fills_the_replay_consistently(tmp_path):
+    """n_envs > 1: `learn` replays the acting lock-step (observation snapshot, epsilon-greedy action, env step, replay append)
+    as one CUDA graph.  Before training starts every transition must still be what the environments produced: within an
+    episode the next observation of step t is the observation of step t + 1 of the same environment, the graph index stays,
+    `done` is raised on the last step only, actions are valid vertices, and the per-episode reward sums are the scores; the
+    host mirrors (replay size / position, env step counter) follow."""
+    gs = np.load(os.path.join(GOLDEN, "graphsets.npz"))
+    graphs = list(gs["er20"][:6])
+    E, T = 4, 40
+    agent = make_agent(tmp_path, graphs, T, n_envs=E, update_frequency=8, update_target_frequency=160,
+                       replay_start_size=10 ** 6, replay_buffer_size=1000, test_frequency=10 ** 9, test_episodes=6,
+                       save_network_frequency=10 ** 9, init_weight_std=0.01, final_exploration_step=600,
+                       final_exploration_rate=0.05)
+    assert agent._act_graph_ok()
+    agent.learn(timesteps=E * T * 2 + E * 7)               # two full episodes and seven steps of a third
+    rb = agent.replay_buffer
+    n_rows = E * T * 2 + E * 7
+    assert len(rb) == n_rows and rb._position == n_rows and int(agent._ag_pos.item()) == n_rows
+    assert agent._env.current_step == 7
+    xn, xg, xn2, xg2 = rb.xn[:n_rows].cpu(), rb.xg[:n_rows].cpu(), rb.xn_next[:n_rows].cpu(), rb.xg_next[:n_rows].cpu()
+    act, done, graph, rew = rb.action[:n_rows].cpu(), rb.done[:n_rows].cpu(), rb.graph[:n_rows].cpu(), rb.reward[:n_rows].cpu()
+    assert int(act.min()) >= 0 and int(act.max()) < 20
+    for e in range(E):
+        rows = torch.arange(e, n_rows, E)                  # environment e, step after step
+        for ep in range(2):
+            r = rows[ep * T:(ep + 1) * T]
+            assert torch.equal(xn2[r[:-1]], xn[r[1:]]) and torch.equal(xg2[r[:-1]], xg[r[1:]])
+            assert len(graph[r].unique()) == 1
+            assert done[r[:-1]].sum() == 0 and done[r[-1]] == 1
+            assert not torch.equal(xn[r[0]], xn[r[-1]])
+        assert done[rows[2 * T:]].sum() == 0
+    # the running scores of the current (third) episode are its reward sums
+    cur = torch.stack([rew[torch.arange(e, n_rows, E)[2 * T:]].double().sum() for e in range(E)])
+    assert torch.allclose(agent._scores.cpu(), cur, atol=1e-6)
