@@ -90,6 +90,12 @@ constexpr int FLAG_STOPPED = 2;
 constexpr uint64_t VISITED_SALT0 = 0x9E3779B97F4A7C15ull;  // stored key = key ^ salt, so 0 means "empty slot"
 constexpr uint64_t VISITED_SALT1 = 0xC2B2AE3D27D4EB4Full;
 
+// one 32-byte sector in ONE store (STG.E.256, sm_100): two 16-byte stores of a lane each fill half a sector
+__device__ __forceinline__ void st_f32x8(float* p, const float (&v)[8]) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+
 // ---- sub-warp group reductions (TPE lanes per episode, TPE <= 32 handled with shuffles) -------------------
 template <int W>
 __device__ __forceinline__ int group_sum(int v) {

@@ -15,6 +15,9 @@ namespace eco {
 union V8s { uint2 v; int8_t b[8]; };
 union V8h { uint4 v; int16_t h[8]; };
 union V8u { uint4 v; uint16_t h[8]; };
+union V4s { uint32_t v; int8_t b[4]; };      // four vertices: env_step_ring_kernel
+union V4h { uint2 v; int16_t h[4]; };
+union V4u { uint2 v; uint16_t h[4]; };
 
 __device__ __forceinline__ float feat_gain(int gain, double mlr) {
     // row 1: immediate_quality_changes / max_local_reward in fp64, then the driver's fp32 cast
@@ -61,7 +64,10 @@ __device__ __forceinline__ int zx16(uint32_t w, int hh) { return (int)prmt(w, 0,
 // vertex's old spin / field come from a shuffle, the visited-set slot is prefetched, observable row 1 and the normalised
 // score change come from per-graph tables.  All TPE lanes of the group must call it (group shuffles); lanes of an episode
 // out of range pass in_range = false with b clamped.
-template <int TPE>
+// WIDE: a lane's eight values of a feature row -- one 32-byte sector -- leave in ONE 256-bit store (two 16-byte stores each
+// fill half a sector: twice the write transactions, measured on env_step_ring_kernel).  The tail warp of mpnn_tc_kernel
+// instantiates the narrow form: 12 live feature registers instead of 24 inside the resident kernel's 96-register budget.
+template <int TPE, bool WIDE = true>
 __device__ __forceinline__ void env_step_group(const eco_graphs_t& g, const eco_env_t& env, long long b, const int lane,
                                                const bool in_range, const int policy, const int action,
                                                double* __restrict__ reward_out, uint8_t* __restrict__ done_out,
@@ -159,26 +165,35 @@ __device__ __forceinline__ void env_step_group(const eco_graphs_t& g, const eco_
     int nimp = 0;
     if (has && active) {
         float* x0 = env.xn + (size_t)b * 3 * NP + lane * 8;
+        auto vertex = [&](int k, float& o0, float& o1, float& o2) {
+            const int i = lane * 8 + k;
+            int si = s.b[k];
+            if (i == a) { si = s_a_new; s.b[k] = (int8_t)si; l.h[k] = (uint16_t)step_new; }
+            const int hi = h.h[k] + 2 * j.b[k] * s_a_new;
+            h.h[k] = (int16_t)hi;
+            const int gain = si * hi;
+            nimp += gain > 0;
+            o0 = (float)si;
+            o1 = use_tab ? __ldg(gtab + gain) : feat_gain(gain, mlr);
+            o2 = __ldg(env.tsf_tab + (step_new - l.h[k]));
+        };
+        if (WIDE) {
+            float f0[8], f1[8], f2[8];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            float f0[4], f1[4], f2[4];
+            for (int k = 0; k < 8; ++k) vertex(k, f0[k], f1[k], f2[k]);
+            st_f32x8(x0, f0);
+            st_f32x8(x0 + NP, f1);
+            st_f32x8(x0 + 2 * NP, f2);
+        } else {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-                const int k = half * 4 + kk;
-                const int i = lane * 8 + k;
-                int si = s.b[k];
-                if (i == a) { si = s_a_new; s.b[k] = (int8_t)si; l.h[k] = (uint16_t)step_new; }
-                const int hi = h.h[k] + 2 * j.b[k] * s_a_new;
-                h.h[k] = (int16_t)hi;
-                const int gain = si * hi;
-                nimp += gain > 0;
-                f0[kk] = (float)si;
-                f1[kk] = use_tab ? __ldg(gtab + gain) : feat_gain(gain, mlr);
-                f2[kk] = __ldg(env.tsf_tab + (step_new - l.h[k]));
+            for (int half = 0; half < 2; ++half) {
+                float f0[4], f1[4], f2[4];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) vertex(half * 4 + kk, f0[kk], f1[kk], f2[kk]);
+                *reinterpret_cast<float4*>(x0 + 4 * half) = make_float4(f0[0], f0[1], f0[2], f0[3]);
+                *reinterpret_cast<float4*>(x0 + NP + 4 * half) = make_float4(f1[0], f1[1], f1[2], f1[3]);
+                *reinterpret_cast<float4*>(x0 + 2 * NP + 4 * half) = make_float4(f2[0], f2[1], f2[2], f2[3]);
             }
-            *reinterpret_cast<float4*>(x0 + 4 * half) = make_float4(f0[0], f0[1], f0[2], f0[3]);
-            *reinterpret_cast<float4*>(x0 + NP + 4 * half) = make_float4(f1[0], f1[1], f1[2], f1[3]);
-            *reinterpret_cast<float4*>(x0 + 2 * NP + 4 * half) = make_float4(f2[0], f2[1], f2[2], f2[3]);
         }
         *reinterpret_cast<uint4*>(hf + lane * 8) = h.v;
         if ((a >> 3) == lane) {

@@ -484,7 +484,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         }
         if (c.lane == 0 && act_out) act_out[be] = bi;
         if (FUSED)        // every lane holds the same (bv, bi) after the butterfly: the warp steps the episode it has just decided
-            env_step_group<32>(g, fe.env, be, c.lane, true, ECO_POLICY_ACTIONS, bi, nullptr, nullptr, fe.hist_a, fe.hist_r, fe.hist_s);
+            env_step_group<32, false>(g, fe.env, be, c.lane, true, ECO_POLICY_ACTIONS, bi, nullptr, nullptr, fe.hist_a, fe.hist_r, fe.hist_s);
         TL(64);
     };
     // Not PACKED: the next episode's inputs do not pass through registers.  The threads of group 1 copy them with cp.async

@@ -294,14 +294,21 @@ def test_env_random_actions_multi_graph_vs_oracle(eng, n, p, B, steps):
     assert np.array_equal(bs.cpu().numpy(), np.stack([e.best_spins for e in cpu]).astype(np.int8))
 
 
-@pytest.mark.parametrize("n", [129, 200, 241, 256])
-def test_env_step_staged_ring_matches_subwarp_kernel(eng, n):
+@pytest.mark.parametrize("n,variant", [(129, "fast"), (200, "fast"), (241, "fast"), (256, "fast"),
+                                       (200, "weights"), (232, "long")])
+def test_env_step_staged_ring_matches_subwarp_kernel(eng, n, variant):
     """B >= 4096 with caller-supplied actions runs env_step_ring_kernel (persistent warps, async-copy ring); smaller batches
     run the sub-warp kernel that the oracle tests pin.  Same episodes, same actions (out-of-range ones included): every
-    state array, observation, reward and done flag must be identical."""
+    state array, observation, reward and done flag must be identical.  "fast": the rollout configuration (+-1 couplings,
+    T + 1 <= 1024: the stripped vertex loop); "weights": couplings in -3 .. 3 and "long": T = 1100, both through the general loop."""
     rng = np.random.default_rng(1000 + n)
     B, G, T, steps = 4096 + 37, 5, 24, 24       # T small: episodes finish inside the test, done episodes stay untouched
+    if variant == "long":
+        T = 1100
     Js = _random_graphs(rng, G, n, 0.06)
+    if variant == "weights":
+        mag = np.triu(rng.integers(1, 4, size=Js.shape), 1).astype(np.int8)
+        Js = Js * (mag + mag.transpose(0, 2, 1))
     gidx = rng.integers(0, G, size=B).astype(np.int32)
     spins = (2 * rng.integers(0, 2, size=(B, n)) - 1).astype(np.int8)
     gs = eng.GraphSet(Js)
