@@ -548,7 +548,7 @@ def run_ours(args):
                 n1 = 20
                 c1 = Rollout(er_graphs(100, n1, 0.15, seed=0), 5000, 2 * n1, load_weights("er20_g0"), seed=3)
                 side["c1_er20"] = c1.side_block("ER_20spin greedy test rollout, configs[0]: 100 graphs x 50 random inits, 2N steps "
-                                                "(tcgen05 kernel packs 9 graphs per CTA pass)", c1.timed(2, 5), 5, 5000 * 2 * n1)
+                                                "(tcgen05 kernel packs 6 graphs per CTA pass)", c1.timed(2, 5), 5, 5000 * 2 * n1)
                 del c1
                 n4 = 2000
                 c4 = Rollout(gnm_graphs(8, n4, 19990, seed=0), 128, 2 * n4, wd, seed=4)

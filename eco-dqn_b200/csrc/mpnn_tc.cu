@@ -260,7 +260,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
     } while (0)
     __shared__ uint64_t bars[9];      // 0: edge contraction; 1, 2: linear MMAs of group 0 / 1 (B1); 3, 4: aggregation columns of
                                       // group 0 / 1; 5, 6: B2 of group 0 / 1; 7, 8: B3 of group 0 / 1
-    __shared__ uint64_t sig[2];       // workers -> contraction issuer: [1] layer inputs ready  ([0] unused)
+    __shared__ uint64_t sig[2];       // workers -> contraction issuer: [1] layer inputs ready; [0] PACKED: |A| region cleared, fetch the next pack
     __shared__ uint64_t sdbar[4];     // worker warps -> contraction issuer: blocks 4r .. 4r+3 of the edge operands S, D are in TMEM
     __shared__ uint64_t tail_sig, tail_done;   // workers -> tail warp: an episode's readout partials are complete; and back
     __shared__ uint64_t gsig[2][2];   // the warps of group g -> its linear-layer issuer: operands of the next MMA batch are
@@ -382,6 +382,20 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                              &bar_ops[which]);
             }
         }
+    };
+    // PACKED, all 32 lanes of one warp (the contraction issuer): one run per lane instead of kk * NP/8 serial issues by a worker
+    // thread (a pack of nine ER-20 graphs: 27 runs per image, ~4 k cycles of one thread on the workers' critical path, twice)
+    auto fetch_ops_warp = [&](int which, int pack) {
+        unsigned char* dst = which ? smem + SM_ABS : smem + SM_A;
+        const int kk = min(K, B - pack * K), NBs = NPs >> 3;
+        if (c.lane == 0) mbar_expect_tx(&bar_ops[which], (uint32_t)kk * NPs * NPs * 2);
+        __syncwarp();
+        for (int idx = c.lane; idx < kk * NBs; idx += 32) {
+            const int j = idx / NBs, cb = idx % NBs;
+            const uint16_t* src = g.tc_ops + ((size_t)graph_idx[pack * K + j] * 2 + which) * NPs * NPs;
+            bulk_g2s(dst + ((size_t)(j * NBs + cb) * NB + j * NBs) * 128, src + (size_t)cb * NBs * 64, NBs * 128, &bar_ops[which]);
+        }
+        __syncwarp();
     };
     auto zero_image = [&](unsigned char* dst) {             // all worker threads; generic proxy, fenced for the bulk copies
         for (int off = c.tid * 16; off < NP * NP * 2; off += THREADS * 16)
@@ -517,10 +531,97 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(wsm_i + 4 * i)), "l"(w.w_init + 4 * i) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    // PACKED: readout + argmax of the K episodes of a pack by ONE warp (the tail warp, like readout_warp_a / _b): the same sums
+    // in the same order as the all-worker readout it replaces (four CTA barriers and ~9 k cycles of all sixteen epilogue warps
+    // per pack, exposed under an edge contraction of ~2.7 k), now beside the next pack's stages.
+    auto readout_packed_warp = [&](const int be) {
+        TL(60);
+        const int bpe = NPs >> 4;                         // 16-vertex blocks per episode
+        for (int idx = c.lane; idx < K * 64; idx += 32) {                  // pooled[e][f] = mean_i h_i[f]
+            const int e = idx >> 6, f = idx & 63;
+            float t = 0.f;
+            for (int j = 0; j < bpe; ++j) t += pp_blk[(e * bpe + j) * 64 + f];
+            pooled_e[idx] = t / (float)Ns;
+        }
+        __syncwarp();
+        TL(61);
+        // p[e][f] = W_p[f, :] pooled[e], k ascending; this lane: f = lane, lane + 32.  Rows of W_p^T: coalesced 128-byte loads,
+        // 32 of them in flight per lane
+        constexpr int KMAX = PACK_NPMAX / 16;
+        float p0[KMAX], p1[KMAX];
+#pragma unroll
+        for (int e = 0; e < KMAX; ++e) { p0[e] = 0.f; p1[e] = 0.f; }
+        const float* wt = reinterpret_cast<const float*>(pk + PK_WPT) + c.lane;
+#pragma unroll 1
+        for (int k0 = 0; k0 < 64; k0 += 16) {
+            float wa[16], wb[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { wa[j] = __ldg(wt + (k0 + j) * 64); wb[j] = __ldg(wt + (k0 + j) * 64 + 32); }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+#pragma unroll
+                for (int e = 0; e < KMAX; ++e) {
+                    if (e < K) {
+                        const float pv = pooled_e[e * 64 + k0 + j];
+                        p0[e] = fmaf(wa[j], pv, p0[e]);
+                        p1[e] = fmaf(wb[j], pv, p1[e]);
+                    }
+                }
+            }
+        }
+        TL(62);
+        const float wr0 = __ldg(w.w_read + c.lane), wr1 = __ldg(w.w_read + 32 + c.lane);
+        __syncwarp();                                      // pooled_e is dead: c0 goes to its first K entries
+#pragma unroll
+        for (int e = 0; e < KMAX; ++e) {
+            if (e < K) {                                   // tef[e][f] = w_r[f] ReLU(p[e][f])
+                tef[e * 64 + c.lane] = wr0 * fmaxf(p0[e], 0.f);
+                tef[e * 64 + 32 + c.lane] = wr1 * fmaxf(p1[e], 0.f);
+            }
+        }
+        __syncwarp();
+        if (c.lane < K) {                                  // c0[e] = b + sum_f tef[e][f], f ascending
+            float c0v = bread;
+            for (int f = 0; f < 64; ++f) c0v += tef[c.lane * 64 + f];
+            pooled_e[c.lane] = c0v;
+        }
+        __syncwarp();
+        TL(63);
+        for (int e = 0, i0 = 0; e < K; ++e, i0 += NPs) {   // Q of every vertex; the final value goes to qpart row 0
+            const int ep = be * K + e;
+            const float c0v = pooled_e[e];
+            for (int v = c.lane; v < NPs; v += 32) {
+                const int i = i0 + v;
+                const float qv = c0v + ((qpart[i] + qpart[NPMAX + i]) + (qpart[2 * NPMAX + i] + qpart[3 * NPMAX + i]));
+                const bool ok = v < Ns && ep < B;
+                if (ok && q_out) q_out[(size_t)ep * NPs + v] = qv;
+                qpart[i] = ok ? qv : -INFINITY;
+            }
+        }
+        __syncwarp();
+        TL(65);
+        for (int e = 0; e < K; ++e) {                      // argmax per episode, lowest index on ties
+            const int ep = be * K + e;
+            float bv = -INFINITY;
+            int bi = 0x7fffffff;
+            for (int v = c.lane; v < Ns; v += 32) {
+                const float qv = qpart[e * NPs + v];
+                if (qv > bv) { bv = qv; bi = v; }          // (v ascending: the first maximum stays)
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (c.lane == 0 && ep < B && act_out) act_out[ep] = bi;
+        }
+        TL(64);
+    };
     if (c.warp == NWARPS) {
         // ================= contraction issuer ===============================================================
 
-        uint32_t sp0 = 0, sp1 = 0, op = 0;
+        uint32_t sp0 = 0, sp1 = 0, sp2 = 0, op = 0;
         for (int it = 0; it < n_items; ++it) {
             mbar_wait(&bar_ops[0], op);               // A and |A| of this episode have landed (async proxy -> async proxy)
             mbar_wait(&bar_ops[1], op); op ^= 1u;
@@ -566,15 +667,25 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
                 __syncwarp();
                 TL(54);
             }
+            if (PACKED && it + 1 < n_items) {
+                // the next pack's operand images.  A has no reader left once the last aggregation of layer 2 retired (the halves
+                // retire in order; completion 3 it + 2 of that half's barrier); |A| overlays H / E: free once the workers have
+                // finished the pack and cleared the off-diagonal blocks (sig[0])
+                mbar_wait(&bars[N8 > ncols0 ? 4 : 3], (uint32_t)((3 * it + 2) & 1));
+                fetch_ops_warp(0, item_ep(it + 1));
+                mbar_wait(&sig[0], sp2); sp2 ^= 1u;
+                fetch_ops_warp(1, item_ep(it + 1));
+            }
         }
     }
-    if (!PACKED && c.warp == NWARPS + 3) {
+    if (c.warp == NWARPS + 3) {
         // ================= episode tail ====================================================================
         uint32_t ph = 0;
-        for (int it = 0; it < n_items; ++it) {
+        for (int it = 0; it < n_items - (PACKED ? 1 : 0); ++it) {    // (PACKED: the last pack is read out by all workers)
             mbar_wait(&tail_sig, ph);
             ph ^= 1u;
-            readout_warp_b(item_ep(it), readout_warp_a());
+            if (PACKED) readout_packed_warp(item_ep(it));
+            else readout_warp_b(item_ep(it), readout_warp_a());
             if (FUSED) __threadfence();                    // the episode's new state / observations, before the arrival below
             __syncwarp();
             if (c.lane == 0) mbar_arrive(&tail_done);      // the partial sums may be overwritten (next episode's last layer)
@@ -649,10 +760,9 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         else if (c.grp == 1) stage_inputs(blockIdx.x);
     }
 
-    // ================= readout + argmax of one episode (mpnn.py:143-159; experiments/utils.py:57-66) =================
-    // Reads only qpart / ppart, which the next episode does not touch before its last layer: it is run while the workers
-    // would otherwise wait for the next episode's edge contraction.
-    auto readout = [&](const int be) {
+    // PACKED: the same readout by all sixteen epilogue warps -- for the CTA's LAST pack only, whose tail nothing runs beside
+    // (~9 k cycles instead of the ~30 k one warp takes; identical sums in identical order)
+    auto readout_packed_all = [&](const int be) {
         if (PACKED) {
             // be = pack.  All K episodes at once, every sum in a fixed order.
             const int bpe = NPs >> 4;                     // 16-vertex blocks per episode
@@ -818,7 +928,6 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             uint4 wm[64 / (8 * SUBS)], wu[64 / (8 * SUBS)];
             ldg_weights<64>(c, pk + PK_WM, wm);
             ldg_weights<64>(c, pk + PK_WU, wu);
-            if (PACKED && last_b >= 0) readout(last_b);   // the previous pack's readout, under this pack's edge contraction
             wait_all(c);
             TL(7);
             sttm_weights<64>(c, wm, T_WM);
@@ -947,7 +1056,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             // readout weights of this thread's two features: requested before the wait (last layer only)
             float wa = 0.f, wb = 0.f;
             if (l == 2) { wa = __ldg(w.w_read + 64 + fa); wb = __ldg(w.w_read + 64 + fa + 8); }
-            if (!PACKED && l == 2 && last_b >= 0) {         // the tail warp has read the previous episode's partial sums
+            if (l == 2 && last_b >= 0) {                    // the tail warp has read the previous episode's (pack's) partial sums
                 mbar_wait(&tail_done, phase_tail);
                 phase_tail ^= 1u;
             }
@@ -958,7 +1067,7 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
             }
             TL(23);
             // A has no reader left once the LAST half retired (the halves retire in order)
-            if (l == 2 && c.tid == (chunk_split < nchunks ? THREADS / 2 : 0) && has_next) fetch_ops(0, b_next);
+            if (!PACKED && l == 2 && c.tid == (chunk_split < nchunks ? THREADS / 2 : 0) && has_next) fetch_ops(0, b_next);   // (PACKED: warp 16)
             // h' of a chunk: next layer's H^T, or (last layer) the readout partials straight from the fp32 registers
             auto epi_h = [&](int ci, int c0, int width) {
                 if (l < 2) {
@@ -1066,17 +1175,20 @@ mpnn_tc_kernel(const eco_graphs_t g, const eco_mpnn_t w, const int B, const int3
         }
         workers_sync();
         if (PACKED && has_next) {                         // the off-diagonal blocks of |A| were overwritten by H / E: clear
+            TL(42);
             zero_image(smem + SM_ABS);
             workers_sync();
+            TL(43);
         }
-        if (c.tid == 0 && has_next) fetch_ops(1, b_next);   // H / E (which |A| overlays) have no reader left
-        if (!PACKED && c.tid == 0) mbar_arrive(&tail_sig);       // -> tail warp: this episode's partial sums are complete
+        if (c.tid == 0 && has_next) {                     // H / E (which |A| overlays) have no reader left
+            if (PACKED) mbar_arrive(&sig[0]);             // -> contraction issuer: fetches the pack's |A| blocks with all its lanes
+            else fetch_ops(1, b_next);
+        }
+        if (c.tid == 0 && (!PACKED || has_next)) mbar_arrive(&tail_sig);   // -> tail warp: this episode's (pack's) partial sums are complete
         last_b = b;
         TL(41);
     }
-    if (c.warp < NWARPS && last_b >= 0) {
-        if (PACKED) readout(last_b);
-    }
+    if (PACKED && c.warp < NWARPS && last_b >= 0) readout_packed_all(last_b);
 #undef TL
 
     tc_fence_before();
@@ -1120,6 +1232,7 @@ int launch_mpnn_tc_fused(const eco_graphs_t* g, const eco_mpnn_t* w, int B, cons
         ECO_CUDA((cudaFuncSetAttribute(mpnn_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)));
         ECO_CUDA((cudaFuncSetAttribute(mpnn_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)));
         ECO_CUDA((cudaFuncSetAttribute(mpnn_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)));
+        ECO_CUDA((cudaFuncSetAttribute(mpnn_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)));
         ECO_CUDA((cudaFuncSetAttribute(mpnn_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)));
     }
     const int packK = PACK_NPMAX / g->NP;                  // small graphs: several per CTA iteration
@@ -1139,7 +1252,8 @@ int launch_mpnn_tc_fused(const eco_graphs_t* g, const eco_mpnn_t* w, int B, cons
         if (n_steps < 1 || B < 2 * grid) { set_error("launch_mpnn_tc_fused: needs n_steps >= 1 and two episodes per CTA"); return ECO_ERR_INVALID; }
         fe.env = *fused; fe.hist_a = ha; fe.hist_r = hr; fe.hist_s = hs; fe.n_steps = n_steps;
     }
-    if (packed) mpnn_tc_kernel<true, false><<<grid, LAUNCH_THREADS, SM_TOTAL, st>>>(*g, *w, B, gidx, xn, xg, norm_max, q, actions, nullptr, packK, fe);
+    if (packed && dbg) mpnn_tc_kernel<true, true><<<grid, LAUNCH_THREADS, SM_TOTAL, st>>>(*g, *w, B, gidx, xn, xg, norm_max, q, actions, dbg, packK, fe);
+    else if (packed) mpnn_tc_kernel<true, false><<<grid, LAUNCH_THREADS, SM_TOTAL, st>>>(*g, *w, B, gidx, xn, xg, norm_max, q, actions, nullptr, packK, fe);
     else if (dbg) mpnn_tc_kernel<false, true><<<grid, LAUNCH_THREADS, SM_TOTAL, st>>>(*g, *w, B, gidx, xn, xg, norm_max, q, actions, dbg, 1, fe);
     else if (fused) mpnn_tc_kernel<false, false, true><<<grid, LAUNCH_THREADS, SM_TOTAL, st>>>(*g, *w, B, gidx, xn, xg, norm_max, q, actions, nullptr, 1, fe);
     else mpnn_tc_kernel<false, false><<<grid, LAUNCH_THREADS, SM_TOTAL, st>>>(*g, *w, B, gidx, xn, xg, norm_max, q, actions, nullptr, 1, fe);
