@@ -34,7 +34,8 @@
 //                 and arrives on the issuer's mbarrier (no CTA or group barrier inside a layer); the issuer commits every
 //                 batch to one of the group's three mbarriers (B1, B2, B3) that the workers wait on before they touch
 //                 its results.  Warp 19 works through the tail of the PREVIOUS episode (pooling, W_p, Q, argmax and, in a
-//                 rollout, SpinSystemBase.step for that episode) while the others are on the next one.
+//                 rollout, SpinSystemBase.step for that episode; packed mode: the K episodes of the previous pack) while
+//                 the others are on the next one.
 //   rollout       FUSED: one launch per rollout -- every CTA takes its own episodes through all steps (see FusedEnv).
 #include <cuda_bf16.h>
 #include <stdlib.h>
@@ -229,7 +230,8 @@ __device__ __forceinline__ void issue_part(const Ctx& c, uint32_t acc_col, uint3
 
 // PACKED: K = packK >= 2 small graphs (NP <= 96) are processed side by side as ONE block-diagonal graph of K * NP <= 192
 // vertices ("pack"): the tensor part below does not know about it; only the inputs (per-vertex episode), the operand
-// images (diagonal blocks), feature 63 and the readout (pooling / argmax per episode) are per episode.
+// images (diagonal blocks: fetched by the 32 lanes of the contraction issuer), feature 63 and the readout (pooling / argmax
+// per episode: the tail warp, readout_packed_warp) are per episode.
 // FUSED (rollouts of the ECO-DQN configuration): the warp that has just taken an episode's argmax also applies the flip --
 // SpinSystemBase.step for that episode (env_step_device.cuh), state and next observations written back -- and, because
 // episodes never interact, the CTA then simply carries on: it takes ITS episodes through all `n_steps` steps of the rollout
