@@ -411,6 +411,52 @@ def test_mpnn_tc_packed_small_graphs_vs_oracle(eng, n, B, norm_max):
     assert np.array_equal(a, q.argmax(1))
 
 
+@pytest.mark.parametrize("n,B", [(20, 148 * 6 * 2 + 77), (40, 148 * 4 * 3 + 5)])
+def test_mpnn_tc_packed_many_packs_per_cta(eng, n, B):
+    """More packs than CTAs: every CTA works through several packs, so all but its last pack are read out by the tail warp
+    beside the next pack's stages (the last one by all epilogue warps), and the operand-image blocks of the next pack are
+    fetched by the contraction issuer.  Q against the oracle; and an episode's Q bits must not depend on where in the launch
+    it was evaluated: the first episodes again as a batch of their own (one pack per CTA, all-worker readout)."""
+    from oracle.mpnn import mpnn_forward, KEYS
+    from eco_dqn_b200 import _lib
+    rng = np.random.default_rng(31 * n + B)
+    G = 64
+    Js = _random_graphs(rng, G, n, 0.3 if n < 40 else 0.15)
+    gidx = rng.integers(0, G, size=B).astype(np.int32)
+    spins = (2 * rng.integers(0, 2, size=(B, n)) - 1).astype(np.int8)
+    wd = {k: (rng.standard_normal(s) * (0.3 if len(s) > 1 else 0.1)).astype(np.float32)
+          for k, s in zip(KEYS, eng.STATE_DICT_SHAPES)}
+    w = eng.MPNNWeights(wd)
+    gs = eng.GraphSet(Js)
+    acts = [rng.integers(0, n, size=B).astype(np.int32) for _ in range(3)]
+
+    def run(count):
+        env = eng.BatchedSpinSystem(gs, count, 2 * n, 1.0 / n)
+        env.reset(spins=spins[:count], graph_idx=gidx[:count])
+        for a in acts:
+            env.step(torch.from_numpy(a[:count].copy()))
+        q, a = env.q_values(w, impl=_lib.MPNN_TCGEN05, norm_max=-1.0)
+        return env, q.clone(), a.clone()
+
+    env, q, a = run(B)
+    q2, a2 = env.q_values(w, impl=_lib.MPNN_TCGEN05, norm_max=-1.0)
+    assert torch.equal(q, q2) and torch.equal(a, a2)                      # run-to-run deterministic
+    small = 37
+    _, qs, a_s = run(small)
+    assert torch.equal(q[:small], qs) and torch.equal(a[:small], a_s)     # same bits wherever the episode sits in the launch
+    obs7 = env.observation().cpu().numpy()
+    q, a = q.cpu().numpy(), a.cpu().numpy()
+    assert np.array_equal(a, q.argmax(1))
+    check = np.concatenate([np.arange(0, 64), rng.choice(B, size=192, replace=False), np.arange(B - 64, B)])
+    for b in check:                                                        # per-episode norm.max() (norm_max < 0)
+        full = np.concatenate([obs7[b:b + 1], Js[gidx[b]][None].astype(np.float32)], axis=1)
+        ref = mpnn_forward(wd, full).numpy().reshape(-1)
+        assert np.allclose(q[b], ref, rtol=Q_RTOL, atol=Q_ATOL_FRAC * np.abs(ref).max()), b
+    q_si, _ = env.q_values(w, impl=_lib.MPNN_SIMT, norm_max=-1.0)
+    q_si = q_si.cpu().numpy()
+    assert np.all(np.abs(q - q_si) <= Q_RTOL * np.abs(q_si) + Q_ATOL_FRAC * np.abs(q_si).max(1, keepdims=True))
+
+
 def test_full_size_invariants_ba200(eng):
     """BASELINE config 2 size (B=4096, N=200): size-independent properties after a greedy + random walk."""
     gsets = np.load(os.path.join(GOLDEN, "graphsets.npz"))
